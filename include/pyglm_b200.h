@@ -1,0 +1,175 @@
+/*
+ * pyglm_b200.h -- C ABI of the B200-native engine for pyglm's data-parallel hot path.
+ *
+ * The reference (slinderman/theano_pyglm) has no FFI: its operator boundary is
+ *   seval(expr, syms, vals)                       pyglm/utils/theano_func_wrapper.py:12-51
+ * evaluated on Theano shared variables filled by
+ *   Population.add_data / set_data                pyglm/population.py:198-231
+ * Each entry point below replaces one family of `seval` call sites; the reference
+ * file:line it stands in for is cited on the declaration.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy types.
+ *   - every function returns 0 on success or a negative PYGLM_B200_E* code;
+ *     pyglm_b200_last_error() returns a thread-local message for the last failure.
+ *   - numerics never raise: NaN / +-inf are produced exactly where the reference
+ *     formula would produce them (callers keep their own guards,
+ *     coord_descent.py:170-182, gibbs.py:1012-1019).
+ *   - "host" entry points take host buffers and perform the H2D / D2H copies
+ *     themselves (synchronous on return); "_dev" entry points take device pointers,
+ *     enqueue on `stream` (a cudaStream_t passed as void*) and do not synchronise.
+ *   - a dataset handle belongs to one GPU and one host thread at a time (the
+ *     reference is single-threaded per engine, parallel_util.py:227).
+ *   - neuron order, feature order (pre-major, basis fastest) and gradient order
+ *     (bias, then w_ir) are the reference's sorted-key order
+ *     (theano_func_wrapper.py:53-67, packvec.py:17-44).
+ */
+#ifndef PYGLM_B200_H
+#define PYGLM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYGLM_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PYGLM_B200_API __attribute__((visibility("default")))
+#else
+#define PYGLM_B200_API
+#endif
+
+/* status codes */
+#define PYGLM_B200_OK          0
+#define PYGLM_B200_EINVAL     -1   /* bad shape / argument                       */
+#define PYGLM_B200_ECUDA      -2   /* CUDA runtime error (see last_error)        */
+#define PYGLM_B200_ENOMEM     -3   /* device allocation failed                   */
+#define PYGLM_B200_ESTATE     -4   /* call out of order (e.g. gibbs before begin)*/
+#define PYGLM_B200_EUNSUPPORTED -5 /* shape not supported by the requested path  */
+
+/* nonlinearity: components/nlin.py:17-29 (exp) and :32-47 ('explinear' == softplus) */
+#define PYGLM_B200_NLIN_EXP       0
+#define PYGLM_B200_NLIN_SOFTPLUS  1
+
+/* storage type of the filtered spike train X (reference: float64 `fS`) */
+#define PYGLM_B200_X_F32  0
+#define PYGLM_B200_X_F64  1
+
+/* arithmetic path for ll / gradient */
+#define PYGLM_B200_PATH_AUTO   0
+#define PYGLM_B200_PATH_FP64   1   /* FP64 CUDA-core contractions (exact path)                 */
+#define PYGLM_B200_PATH_TC     2   /* tcgen05 3xTF32 contractions, FP32 epilogue, FP64 sums    */
+
+typedef struct pyglm_b200_dataset pyglm_b200_dataset;
+
+PYGLM_B200_API const char* pyglm_b200_last_error(void);
+PYGLM_B200_API int32_t     pyglm_b200_abi_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * Data ingest + spike-history filtering (kernel K1).
+ * Replaces LinearBasisImpulses.preprocess_data / DirichletImpulses.preprocess_data
+ * (components/impulse.py:114-130, :378-394) -> convolve_with_basis
+ * (utils/basis.py:201-236) and Glm.set_data / imp_model.set_data
+ * (glm.py:99-110, impulse.py:132-133).
+ *
+ * S       host uint8 [(halo+T)][N] row-major spike counts (time-major like data["S"];
+ *         counts are small non-negative integers, population.py:345-349).  The first
+ *         `halo` rows are left context only (time-sharded use: the previous shard's
+ *         last R bins); X and the likelihood cover rows [halo, halo+T).
+ * ibasis  host float64 [R][B] interpolated basis (impulse.py:92-112); row k-1 is lag k.
+ * X[t][pre*B+b] = sum_{k=1..R} ibasis[k-1][b] * S[t-k][pre]   (zero row prepended, basis.py:220)
+ * ---------------------------------------------------------------------------------- */
+PYGLM_B200_API int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t N, double dt,
+                              const double* ibasis, int32_t R, int32_t B,
+                              int32_t x_dtype, int32_t device,
+                              pyglm_b200_dataset** out);
+PYGLM_B200_API int pyglm_b200_dataset_destroy(pyglm_b200_dataset* ds);
+
+/* shape query: any pointer may be NULL */
+PYGLM_B200_API int pyglm_b200_dataset_info(const pyglm_b200_dataset* ds, int64_t* T, int32_t* N, int32_t* B,
+                            int32_t* R, int64_t* ldx, int32_t* x_dtype, int32_t* device);
+
+/* copy the filtered spike train back: out is host float64 [T][N][B] == data['fS']
+ * (impulse.py:130).  Parity / debugging only. */
+PYGLM_B200_API int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out);
+
+/* raw device pointers for zero-copy views (torch.from_blob style); owned by the handle */
+PYGLM_B200_API void* pyglm_b200_dataset_device_X(const pyglm_b200_dataset* ds);
+PYGLM_B200_API void* pyglm_b200_dataset_device_S(const pyglm_b200_dataset* ds);
+
+/* re-run K1 on the resident spikes (bench / profiling of the filter alone) */
+PYGLM_B200_API int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Log-likelihood and gradient for postsynaptic neurons n in [n_lo, n_hi)  (kernels K2f/K2b).
+ * Replaces, for every n in the range, one call each of
+ *   seval(glm.ll, syms, nvars)                    population.py:80-84, coord_descent.py:52-57
+ *   seval(g_glm_ll, syms, nvars)                  coord_descent.py:30,72-77 (grads.py:9-28)
+ * with glm.ll = sum_t(-dt*lam + log(lam)*S[:,n]) (glm.py:52),
+ *      lam   = nlin(bias + I_imp @ (A[:,n]*W[:,n]))           (glm.py:33-45),
+ *      I_imp = sum_b ir[t,pre,b] * w[pre,b]                   (impulse.py:58 / :308).
+ *
+ * bias  float64 [N]              x['glms'][n]['bias']['bias'][0]
+ * w     float64 [N][N*B]         row n = x['glms'][n]['imp']['w_ir'] (pre-major, basis fastest);
+ *                                for DirichletImpulses pass beta = |g|/sum|g| (impulse.py:286-291)
+ * A     int8    [N][N] or NULL   x['net']['graph']['A'] (row = presynaptic); NULL = complete graph
+ * W     float64 [N][N] or NULL   x['net']['weights']['W'] reshaped (N,N); NULL = ones (weights.py:32)
+ * out_ll      float64 [n_hi-n_lo]
+ * out_g_bias  float64 [n_hi-n_lo]          d ll_n / d bias_n            (may be NULL => ll only)
+ * out_g_w     float64 [n_hi-n_lo][N*B]     d ll_n / d w[n][pre*B+b]     (may be NULL => ll only)
+ * ---------------------------------------------------------------------------------- */
+PYGLM_B200_API int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
+                       const double* bias, const double* w, const int8_t* A, const double* W,
+                       int32_t nlin, int32_t n_lo, int32_t n_hi, int32_t path,
+                       double* out_ll, double* out_g_bias, double* out_g_w);
+
+/* same, device pointers, asynchronous on `stream` */
+PYGLM_B200_API int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
+                           const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
+                           int32_t nlin, int32_t n_lo, int32_t n_hi, int32_t path,
+                           double* d_out_ll, double* d_out_g_bias, double* d_out_g_w,
+                           void* stream);
+
+/* firing rate lam[t][n] for n in [n_lo,n_hi): host float64 [T][n_hi-n_lo].
+ * Replaces seval(glm.lam, ...) in Population.eval_state (population.py:88-123); this is
+ * the quantity the reference's only numeric assertion checks
+ * (test/generate_synth_data.py:124-129). */
+PYGLM_B200_API int pyglm_b200_firing_rate(pyglm_b200_dataset* ds,
+                           const double* bias, const double* w, const int8_t* A, const double* W,
+                           int32_t nlin, int32_t n_lo, int32_t n_hi, double* out_lam);
+
+/* ------------------------------------------------------------------------------------
+ * Batched delta-log-likelihood for the collapsed Gibbs sampler over A/W (kernel K4).
+ * Replaces CollapsedGibbsNetworkColumnUpdate._precompute_vars / _precompute_other_current /
+ * _glm_ll (inference/gibbs.py:812-864, :910-937) for a batch of edges.
+ *
+ * gibbs_begin   uploads the state and makes I_net[:, n] resident for n in [n_lo, n_hi)
+ *               (== seval(glm.I_net) with the current A, W; glm.py:39).
+ * gibbs_delta_ll  for edge m = (pres[m] -> cols[m]) and candidate weights w_cand[m][0..Q):
+ *               out_ll[m][q] = sum_t(-dt*f(x) + S[t,col] log f(x)),
+ *               x = bias[col] + I_other[t] + w_cand[m][q] * I_imp[t, pre]     (gibbs.py:914)
+ *               where I_other is I_net[:,col] with A[pre,col] := 0 (gibbs.py:838-861).
+ *               Columns within one call must be distinct.
+ * gibbs_commit  sets A[pre,col] = a_new, W[pre,col] = w_new and rank-1 updates the resident
+ *               I_net (the reference instead recomputes the gemv for the next edge).
+ * ---------------------------------------------------------------------------------- */
+PYGLM_B200_API int pyglm_b200_gibbs_begin(pyglm_b200_dataset* ds,
+                           const double* bias, const double* w, const int8_t* A, const double* W,
+                           int32_t nlin, int32_t n_lo, int32_t n_hi);
+PYGLM_B200_API int pyglm_b200_gibbs_delta_ll(pyglm_b200_dataset* ds, int32_t M,
+                              const int32_t* cols, const int32_t* pres,
+                              int32_t Q, const double* w_cand, double* out_ll);
+PYGLM_B200_API int pyglm_b200_gibbs_commit(pyglm_b200_dataset* ds, int32_t M,
+                            const int32_t* cols, const int32_t* pres,
+                            const int8_t* a_new, const double* w_new);
+/* copy the sampler's current A (int8 [N][N]) / W (float64 [N][N]) back; either may be NULL */
+PYGLM_B200_API int pyglm_b200_gibbs_get_state(const pyglm_b200_dataset* ds, int8_t* A, double* W);
+PYGLM_B200_API int pyglm_b200_gibbs_end(pyglm_b200_dataset* ds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYGLM_B200_H */

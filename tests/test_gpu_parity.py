@@ -1,0 +1,189 @@
+"""GPU parity: CUDA engine (through the C ABI) vs the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-6 relative on log-likelihood, 1e-5 on gradients;
+integer work bit-exact.  The FP64 path is held to much tighter bounds.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyglm_oracle as orc
+from tests.helpers import make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-6
+GRAD_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def eng(engine_lib):
+    import theano_pyglm_b200 as pg
+    return pg
+
+
+def oracle_all(p, nlin):
+    fS = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    ll, gb, gw = orc.population_ll_grad(fS, p['S'], p['dt'], p['bias'], p['w'], p['A'], p['W'], nlin)
+    return fS, ll, gb, gw.reshape(p['N'], -1)
+
+
+@pytest.mark.parametrize("T,N,B,x_dtype", [(3000, 4, 5, "f32"), (3000, 4, 5, "f64"), (5000, 27, 5, "f32"),
+                                           (1111, 37, 10, "f32"), (700, 3, 1, "f64"), (2048, 70, 7, "f32")])
+def test_filter_matches_oracle(eng, T, N, B, x_dtype):
+    p = make_problem(T, N, B)
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype)
+    fS = ds.fS()
+    ref_fft = orc.convolve_with_basis(p['S'].astype(np.float64), p['ibasis'])      # as the reference calls it
+    ref_dir = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    if x_dtype == "f64":
+        assert np.array_equal(fS, ref_dir)            # same summation order -> bit-exact
+    else:
+        assert np.array_equal(fS, ref_dir.astype(np.float32).astype(np.float64))   # correctly rounded FP32
+    assert np.max(np.abs(fS - ref_fft)) <= 1e-6 * max(1.0, np.max(np.abs(ref_fft)))
+    ds.close()
+
+
+def test_filter_halo_matches_unsharded(eng):
+    """Time-sharded ingest: shard k with an R-bin left halo reproduces rows of the unsharded X."""
+    p = make_problem(4000, 6, 5)
+    R = p['ibasis'].shape[0]
+    full = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f64").fS()
+    for lo, hi in [(0, 1000), (1000, 2500), (2500, 4000)]:
+        halo = min(R, lo)
+        ds = eng.Dataset(p['S'][lo - halo:hi], p['dt'], p['ibasis'], halo=halo, x_dtype="f64")
+        assert np.array_equal(ds.fS(), full[lo:hi])
+        ds.close()
+
+
+@pytest.mark.parametrize("nlin", [orc.NLIN_SOFTPLUS, orc.NLIN_EXP])
+@pytest.mark.parametrize("T,N,B,network", [(3000, 4, 5, False), (6000, 27, 5, False), (2500, 40, 10, True),
+                                           (999, 5, 3, True)])
+def test_ll_grad_fp64_path(eng, T, N, B, network, nlin):
+    p = make_problem(T, N, B, network=network)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 17.0          # exp(3) ~ 20 Hz
+    _, ll, gb, gw = oracle_all(p, nlin)
+    for x_dtype, tol in (("f64", 1e-11), ("f32", 2e-7)):
+        ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype)
+        ll_g, gb_g, gw_g = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="fp64")
+        assert rel_err(ll_g, ll) < tol
+        assert rel_err(gb_g, gb) < max(tol, 1e-9) * 10
+        assert rel_err(gw_g, gw) < max(tol, 1e-9) * 10
+        # ll-only call and a sub-range of neurons
+        lo, hi = N // 3, N - 1
+        ll_sub = ds.ll(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, n_lo=lo, n_hi=hi, path="fp64")
+        assert rel_err(ll_sub, ll[lo:hi]) < tol
+        ds.close()
+
+
+def test_ll_grad_null_network_is_complete_graph(eng):
+    p = make_problem(2000, 6, 5)
+    _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f64")
+    ll_g, gb_g, gw_g = ds.ll_grad(p['bias'], p['w'], None, None, path="fp64")
+    assert rel_err(ll_g, ll) < 1e-11 and rel_err(gw_g, gw) < 1e-9
+    ds.close()
+
+
+def test_firing_rate_matches_simulated_activation(eng):
+    """The reference's own assertion (test/generate_synth_data.py:124-129):
+    lam from the likelihood graph == f_nlin(X) accumulated by Population.simulate."""
+    rng = np.random.default_rng(7)
+    N, B, nT, dt = 4, 5, 4000, 0.001
+    from tests.helpers import make_ibasis
+    ib = make_ibasis(B)
+    bias = 20.0 + 0.1 * rng.standard_normal(N)
+    w = orc.sample_group_lasso(rng, N * N, B, 0.0, 10.0, 1.0).reshape(N, N, B) * 0.02
+    A = np.ones((N, N), dtype=np.int8)
+    W = np.ones((N, N))
+    imps = np.einsum('npb,rb->pnr', w, ib)             # (pre, post, R): impulse.py:65, population.py:281
+    S, Xsim = orc.simulate(bias, imps, A, W, nT, dt, orc.NLIN_SOFTPLUS, rng)
+    ds = eng.Dataset(S, dt, ib, x_dtype="f64")
+    lam = ds.firing_rate(bias, w.reshape(N, -1), A, W)
+    assert np.allclose(lam, orc.nlin(Xsim, orc.NLIN_SOFTPLUS))          # the reference's np.allclose
+    assert rel_err(lam, orc.nlin(Xsim, orc.NLIN_SOFTPLUS)) < 1e-10
+    ds.close()
+
+
+def test_empty_and_tiny_inputs(eng):
+    p = make_problem(50, 3, 5)
+    # T = 0: empty recording -> zero ll and gradient
+    ds = eng.Dataset(p['S'][:0], p['dt'], p['ibasis'])
+    ll, gb, gw = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="fp64")
+    assert np.all(ll == 0) and np.all(gb == 0) and np.all(gw == 0)
+    assert ds.fS().shape == (0, 3, 5)
+    ds.close()
+    # T shorter than the filter, and a silent population
+    for S in (p['S'], np.zeros_like(p['S'])):
+        ds = eng.Dataset(S, p['dt'], p['ibasis'], x_dtype="f64")
+        q = dict(p, S=S)
+        fS, ll, gb, gw = oracle_all(q, orc.NLIN_SOFTPLUS)
+        assert np.array_equal(ds.fS(), fS)
+        ll_g, gb_g, gw_g = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="fp64")
+        assert rel_err(ll_g, ll) < 1e-11
+        assert np.allclose(gw_g, gw, rtol=1e-9, atol=1e-12)
+        ds.close()
+    # empty neuron range
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'])
+    assert ds.ll(p['bias'], p['w'], n_lo=2, n_hi=2).shape == (0,)
+    ds.close()
+
+
+def test_bad_arguments_raise(eng):
+    p = make_problem(100, 3, 5)
+    with pytest.raises(ValueError):
+        eng.Dataset(p['S'].astype(np.float64) + 0.5, p['dt'], p['ibasis'])
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'])
+    with pytest.raises(eng.EngineError):
+        ds.ll(p['bias'], p['w'], n_lo=2, n_hi=9)
+    with pytest.raises(eng.EngineError):
+        ds.gibbs_delta_ll([0], [1], np.zeros((1, 11)))       # before gibbs_begin
+    ds.close()
+
+
+@pytest.mark.parametrize("x_dtype", ["f64", "f32"])
+def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
+    """K4 vs gibbs.py:910-937 / :1002-1039 restated: candidate log-likelihoods, then identical
+    A decisions for the same uniforms, through a whole shuffled column sweep with commits."""
+    T, N, B = 4000, 6, 5
+    p = make_problem(T, N, B, network=True, dirichlet=True, seed=99)
+    rng = np.random.default_rng(5)
+    mu_w, sig_w, mu_ref, sig_ref = 0.0, 1.0, -0.2, 0.5
+    p_A = np.full((N, N), 0.5)
+    np.fill_diagonal(p_A, 1.0 - 1e-3)
+    fS = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype)
+    A_ref, W_ref = p['A'].copy(), p['W'].copy()
+    ds.gibbs_begin(p['bias'], p['w'], A_ref, W_ref, nlin="explinear")
+    tol = 1e-10 if x_dtype == "f64" else 1e-6
+    for n_post in (1, 4):
+        order = rng.permutation(N)
+        unif = rng.random(N)
+        wnew = rng.standard_normal(N)
+
+        def w_draw(n_pre, a_new, mu, sig, W_nns, log_L, _w=wnew):
+            return mu + sig * _w[n_pre]
+        rec = orc.collapsed_column_sweep(fS, p['S'], p['dt'], n_post, p['bias'][n_post], p['w'][n_post], A_ref, W_ref,
+                                         p_A, orc.NLIN_SOFTPLUS, mu_w, sig_w, mu_ref, sig_ref, order, unif, w_draw)
+        for i, n_pre in enumerate(order):
+            mu, sig = (mu_ref, sig_ref) if n_pre == n_post else (mu_w, sig_w)
+            cand = np.concatenate([orc.gh_candidates(mu, sig), [0.0]])
+            out = ds.gibbs_delta_ll([n_post], [n_pre], cand[None, :])[0]
+            assert np.allclose(out[:10], rec[i]['log_L'], rtol=tol, atol=0)
+            assert abs(out[10] - rec[i]['ll_noA']) <= tol * abs(rec[i]['ll_noA'])
+            lp_noA, lp_A = orc.collapsed_edge_log_odds(out[:10], out[10], p_A[n_pre, n_post])
+            a_new = orc.log_sum_exp_sample([lp_noA, lp_A], unif[i])
+            assert a_new == rec[i]['A']                      # identical accept / reject
+            ds.gibbs_commit([n_post], [n_pre], [a_new], [mu + sig * wnew[n_pre]])
+    A_g, W_g = ds.gibbs_state()
+    assert np.array_equal(A_g, A_ref)                            # integer state bit-exact
+    assert np.array_equal(W_g, W_ref)
+    # batched call over distinct columns == one-by-one calls
+    cols = np.array([0, 2, 3, 5]); pres = np.array([3, 3, 0, 5])
+    cand = rng.standard_normal((4, 11))
+    batch = ds.gibbs_delta_ll(cols, pres, cand)
+    for m in range(4):
+        one = ds.gibbs_delta_ll(cols[m:m + 1], pres[m:m + 1], cand[m:m + 1])
+        assert np.array_equal(batch[m], one[0])
+    ds.gibbs_end()
+    ds.close()

@@ -1,0 +1,459 @@
+// C ABI of the engine (include/pyglm_b200.h): dataset handle, host<->device plumbing, dispatch.
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "llgrad_tc.cuh"
+
+namespace pyglm {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int ensure(size_t count)
+    {
+        if (count <= n) return PYGLM_B200_OK;
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            return PYGLM_B200_ENOMEM;
+        }
+        n = count;
+        return PYGLM_B200_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace pyglm
+
+using namespace pyglm;
+
+struct pyglm_b200_dataset {
+    int device = 0;
+    int64_t T = 0;
+    int N = 0, B = 0, R = 0, halo = 0;
+    double dt = 0.0;
+    int x_dtype = PYGLM_B200_X_F32;
+    int64_t ldx = 0;
+    cudaStream_t stream = nullptr;
+
+    DevBuf<uint8_t> S, St;
+    DevBuf<unsigned char> X;
+    DevBuf<double> ibasis;
+
+    // parameter staging (host entry points) and workspaces
+    DevBuf<double> p_bias, p_w, p_W, M, Weff, Rres, llp, gbp, Gp, o_ll, o_gb, o_gw, lam;
+    DevBuf<int8_t> p_A;
+    TcWorkspace tc;
+
+    // Gibbs state
+    bool gibbs_active = false;
+    int g_nlo = 0, g_ncols = 0, g_nlin = 0;
+    DevBuf<double> g_bias, g_w, g_W, Inet, partial, g_wcand, g_out, g_wnew;
+    DevBuf<int8_t> g_A, g_anew;
+    DevBuf<int32_t> g_cols, g_pres;
+};
+
+#define DS_GUARD(ds)                                                   \
+    PYGLM_REQUIRE((ds) != nullptr, "null dataset handle");             \
+    PYGLM_CUDA(cudaSetDevice((ds)->device))
+
+#define TRY(expr)                                                      \
+    do { int rc_ = (expr); if (rc_ != PYGLM_B200_OK) return rc_; } while (0)
+
+extern "C" {
+
+const char* pyglm_b200_last_error(void) { return g_err; }
+int32_t pyglm_b200_abi_version(void) { return PYGLM_B200_ABI_VERSION; }
+
+int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t N, double dt,
+                              const double* ibasis, int32_t R, int32_t B,
+                              int32_t x_dtype, int32_t device, pyglm_b200_dataset** out)
+{
+    PYGLM_REQUIRE(out != nullptr, "dataset_create: out is null");
+    *out = nullptr;
+    PYGLM_REQUIRE(T >= 0 && N >= 1 && halo >= 0, "dataset_create: bad shape T=%lld N=%d halo=%d", (long long)T, N, halo);
+    PYGLM_REQUIRE(R >= 1 && B >= 1 && B <= kMaxBasis, "dataset_create: bad basis shape R=%d B=%d (B<=%d)", R, B, kMaxBasis);
+    PYGLM_REQUIRE(S != nullptr || (T + halo) == 0, "dataset_create: S is null");
+    PYGLM_REQUIRE(ibasis != nullptr, "dataset_create: ibasis is null");
+    PYGLM_REQUIRE(x_dtype == PYGLM_B200_X_F32 || x_dtype == PYGLM_B200_X_F64, "dataset_create: bad x_dtype %d", x_dtype);
+    PYGLM_REQUIRE(dt > 0.0, "dataset_create: dt must be positive");
+    PYGLM_CUDA(cudaSetDevice(device));
+
+    pyglm_b200_dataset* ds = new (std::nothrow) pyglm_b200_dataset();
+    PYGLM_REQUIRE(ds != nullptr, "dataset_create: host allocation failed");
+    ds->device = device; ds->T = T; ds->N = N; ds->B = B; ds->R = R; ds->halo = halo; ds->dt = dt;
+    ds->x_dtype = x_dtype;
+    ds->ldx = round_up((int64_t)N * B, 4);
+    auto fail = [&](int rc) { pyglm_b200_dataset_destroy(ds); return rc; };
+
+    cudaError_t e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return fail(PYGLM_B200_ECUDA); }
+
+    const size_t nS = (size_t)(T + halo) * N;
+    const size_t esz = x_dtype == PYGLM_B200_X_F32 ? 4 : 8;
+    int rc;
+    if ((rc = ds->S.ensure(nS ? nS : 1)) || (rc = ds->St.ensure((size_t)T * N ? (size_t)T * N : 1)) ||
+        (rc = ds->X.ensure((size_t)T * ds->ldx * esz ? (size_t)T * ds->ldx * esz : 1)) ||
+        (rc = ds->ibasis.ensure((size_t)R * B)))
+        return fail(rc);
+#define CK(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { set_error("%s -> %s", #call, cudaGetErrorString(e2)); return fail(PYGLM_B200_ECUDA); } } while (0)
+    if (nS) CK(cudaMemcpyAsync(ds->S.p, S, nS, cudaMemcpyHostToDevice, ds->stream));
+    CK(cudaMemcpyAsync(ds->ibasis.p, ibasis, (size_t)R * B * sizeof(double), cudaMemcpyHostToDevice, ds->stream));
+    CK(cudaMemsetAsync(ds->X.p, 0, ds->X.n, ds->stream));
+    if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->X.p, ds->ldx, x_dtype, ds->stream))) return fail(rc);
+    if ((rc = launch_transpose_spikes(ds->S.p, T, N, halo, ds->St.p, ds->stream))) return fail(rc);
+    CK(cudaStreamSynchronize(ds->stream));
+#undef CK
+    *out = ds;
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_dataset_destroy(pyglm_b200_dataset* ds)
+{
+    if (!ds) return PYGLM_B200_OK;
+    cudaSetDevice(ds->device);
+    if (ds->stream) { cudaStreamSynchronize(ds->stream); }
+    ds->S.release(); ds->St.release(); ds->X.release(); ds->ibasis.release();
+    ds->p_bias.release(); ds->p_w.release(); ds->p_W.release(); ds->p_A.release();
+    ds->M.release(); ds->Weff.release(); ds->Rres.release(); ds->llp.release(); ds->gbp.release();
+    ds->Gp.release(); ds->o_ll.release(); ds->o_gb.release(); ds->o_gw.release(); ds->lam.release();
+    ds->g_bias.release(); ds->g_w.release(); ds->g_W.release(); ds->g_A.release(); ds->Inet.release();
+    ds->partial.release(); ds->g_wcand.release(); ds->g_out.release(); ds->g_wnew.release();
+    ds->g_anew.release(); ds->g_cols.release(); ds->g_pres.release();
+    ds->tc.release();
+    if (ds->stream) cudaStreamDestroy(ds->stream);
+    delete ds;
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_dataset_info(const pyglm_b200_dataset* ds, int64_t* T, int32_t* N, int32_t* B,
+                            int32_t* R, int64_t* ldx, int32_t* x_dtype, int32_t* device)
+{
+    PYGLM_REQUIRE(ds != nullptr, "null dataset handle");
+    if (T) *T = ds->T;
+    if (N) *N = ds->N;
+    if (B) *B = ds->B;
+    if (R) *R = ds->R;
+    if (ldx) *ldx = ds->ldx;
+    if (x_dtype) *x_dtype = ds->x_dtype;
+    if (device) *device = ds->device;
+    return PYGLM_B200_OK;
+}
+
+void* pyglm_b200_dataset_device_X(const pyglm_b200_dataset* ds) { return ds ? (void*)ds->X.p : nullptr; }
+void* pyglm_b200_dataset_device_S(const pyglm_b200_dataset* ds) { return ds ? (void*)ds->S.p : nullptr; }
+
+int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
+{
+    DS_GUARD(ds);
+    PYGLM_REQUIRE(out != nullptr, "get_fS: out is null");
+    const int64_t NB = (int64_t)ds->N * ds->B;
+    if (ds->T == 0) return PYGLM_B200_OK;
+    PYGLM_CUDA(cudaStreamSynchronize(ds->stream));
+    if (ds->x_dtype == PYGLM_B200_X_F64) {
+        PYGLM_CUDA(cudaMemcpy2D(out, NB * sizeof(double), ds->X.p, ds->ldx * sizeof(double),
+                                NB * sizeof(double), ds->T, cudaMemcpyDeviceToHost));
+    } else {
+        // stream back in slabs and widen on the host
+        const int64_t slab = 1 << 16;
+        std::vector<float> tmp((size_t)slab * NB);
+        for (int64_t t0 = 0; t0 < ds->T; t0 += slab) {
+            const int64_t nt = (ds->T - t0 < slab) ? ds->T - t0 : slab;
+            PYGLM_CUDA(cudaMemcpy2D(tmp.data(), NB * sizeof(float),
+                                    (const float*)ds->X.p + t0 * ds->ldx, ds->ldx * sizeof(float),
+                                    NB * sizeof(float), nt, cudaMemcpyDeviceToHost));
+            double* o = out + t0 * NB;
+            for (int64_t i = 0; i < nt * NB; ++i) o[i] = (double)tmp[i];
+        }
+    }
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
+{
+    DS_GUARD(ds);
+    return launch_filter(ds->S.p, ds->T, ds->N, ds->halo, ds->ibasis.p, ds->R, ds->B, ds->X.p, ds->ldx,
+                         ds->x_dtype, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------
+static int resolve_path(const pyglm_b200_dataset* ds, int path, bool need_aux)
+{
+    if (path == PYGLM_B200_PATH_FP64) return PYGLM_B200_PATH_FP64;
+    const bool tc_ok = tc_supported(ds->T, ds->N, ds->B, ds->x_dtype) && !need_aux;
+    if (path == PYGLM_B200_PATH_TC) return tc_ok ? PYGLM_B200_PATH_TC : -1;
+    return tc_ok ? PYGLM_B200_PATH_TC : PYGLM_B200_PATH_FP64;
+}
+
+static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
+                            const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
+                            int nlin, int n_lo, int n_hi, int path,
+                            double* d_ll, double* d_gb, double* d_gw,
+                            double* d_act, double* d_lam, cudaStream_t stream)
+{
+    PYGLM_REQUIRE(nlin == PYGLM_B200_NLIN_EXP || nlin == PYGLM_B200_NLIN_SOFTPLUS, "bad nlin %d", nlin);
+    PYGLM_REQUIRE(0 <= n_lo && n_lo <= n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
+    PYGLM_REQUIRE(d_bias && d_w && d_ll, "ll_grad: null argument");
+    PYGLM_REQUIRE((d_gb == nullptr) == (d_gw == nullptr), "ll_grad: pass both gradient outputs or neither");
+    const int ncols = n_hi - n_lo;
+    if (ncols == 0) return PYGLM_B200_OK;
+    const int64_t NB = (int64_t)ds->N * ds->B;
+    if (ds->T == 0) {   // empty recording: ll = 0, gradients = 0
+        PYGLM_CUDA(cudaMemsetAsync(d_ll, 0, ncols * sizeof(double), stream));
+        if (d_gb) PYGLM_CUDA(cudaMemsetAsync(d_gb, 0, ncols * sizeof(double), stream));
+        if (d_gw) PYGLM_CUDA(cudaMemsetAsync(d_gw, 0, ncols * NB * sizeof(double), stream));
+        return PYGLM_B200_OK;
+    }
+    const int use = resolve_path(ds, path, d_act != nullptr || d_lam != nullptr);
+    if (use < 0) {
+        set_error("ll_grad: tensor-core path does not support this shape (N=%d B=%d x_dtype=%d)", ds->N, ds->B, ds->x_dtype);
+        return PYGLM_B200_EUNSUPPORTED;
+    }
+    if (use == PYGLM_B200_PATH_TC) {
+        TcArgs t{};
+        t.X = (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
+        t.B = ds->B; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
+        t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
+        t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
+        return launch_tc_ll_grad(t, ds->tc, stream);
+    }
+
+    const int Np = (int)round_up(ncols, 32);
+    const int64_t NBp = NB;
+    TRY(ds->M.ensure((size_t)NBp * Np));
+    TRY(ds->Weff.ensure((size_t)ncols * ds->N));
+    const int ntiles = simt_workspace_tiles(ds->T);
+    TRY(ds->llp.ensure((size_t)ntiles * Np));
+    TRY(ds->gbp.ensure((size_t)ntiles * Np));
+    SimtArgs a{};
+    a.X = ds->X.p; a.ldx = ds->ldx; a.x_dtype = ds->x_dtype;
+    a.S = ds->S.p; a.T = ds->T; a.N = ds->N; a.halo = ds->halo; a.B = ds->B;
+    a.dt = ds->dt; a.nlin = nlin; a.n_lo = n_lo; a.ncols = ncols; a.Np = Np;
+    a.bias = d_bias; a.M = ds->M.p; a.Weff = ds->Weff.p;
+    a.llp = ds->llp.p; a.gbp = ds->gbp.p;
+    a.out_ll = d_ll; a.out_gb = d_gb; a.out_gw = d_gw;
+    a.act_out = d_act; a.lam_out = d_lam;
+    if (d_gw) {
+        TRY(ds->Rres.ensure((size_t)ds->T * Np));
+        a.R = ds->Rres.p;
+        a.splits = simt_choose_splits(ds->T, ds->N, ds->B, Np);
+        TRY(ds->Gp.ensure((size_t)a.splits * round_up(NB, 64) * Np));
+        a.Gp = ds->Gp.p;
+    }
+    TRY(launch_build_M(d_w, d_A, d_W, ds->N, ds->B, n_lo, ncols, ds->M.p, Np, NBp, ds->Weff.p, stream));
+    return launch_simt_ll_grad(a, stream);
+}
+
+int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
+                           const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
+                           int32_t nlin, int32_t n_lo, int32_t n_hi, int32_t path,
+                           double* d_out_ll, double* d_out_g_bias, double* d_out_g_w, void* stream)
+{
+    DS_GUARD(ds);
+    return ll_grad_dev_impl(ds, d_bias, d_w, d_A, d_W, nlin, n_lo, n_hi, path, d_out_ll, d_out_g_bias, d_out_g_w,
+                            nullptr, nullptr, (cudaStream_t)stream);
+}
+
+// upload the parameter block of a host call into the handle's staging buffers
+static int stage_params(pyglm_b200_dataset* ds, const double* bias, const double* w, const int8_t* A, const double* W,
+                        DevBuf<double>& b_bias, DevBuf<double>& b_w, DevBuf<int8_t>& b_A, DevBuf<double>& b_W,
+                        cudaStream_t stream)
+{
+    PYGLM_REQUIRE(bias && w, "null bias / w");
+    const size_t N = ds->N, NB = (size_t)ds->N * ds->B;
+    TRY(b_bias.ensure(N));
+    TRY(b_w.ensure(N * NB));
+    PYGLM_CUDA(cudaMemcpyAsync(b_bias.p, bias, N * sizeof(double), cudaMemcpyHostToDevice, stream));
+    PYGLM_CUDA(cudaMemcpyAsync(b_w.p, w, N * NB * sizeof(double), cudaMemcpyHostToDevice, stream));
+    if (A) {
+        TRY(b_A.ensure(N * N));
+        PYGLM_CUDA(cudaMemcpyAsync(b_A.p, A, N * N, cudaMemcpyHostToDevice, stream));
+    }
+    if (W) {
+        TRY(b_W.ensure(N * N));
+        PYGLM_CUDA(cudaMemcpyAsync(b_W.p, W, N * N * sizeof(double), cudaMemcpyHostToDevice, stream));
+    }
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
+                       const double* bias, const double* w, const int8_t* A, const double* W,
+                       int32_t nlin, int32_t n_lo, int32_t n_hi, int32_t path,
+                       double* out_ll, double* out_g_bias, double* out_g_w)
+{
+    DS_GUARD(ds);
+    PYGLM_REQUIRE(out_ll != nullptr, "ll_grad: out_ll is null");
+    PYGLM_REQUIRE(0 <= n_lo && n_lo <= n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
+    const int ncols = n_hi - n_lo;
+    if (ncols == 0) return PYGLM_B200_OK;
+    const size_t NB = (size_t)ds->N * ds->B;
+    cudaStream_t st = ds->stream;
+    TRY(stage_params(ds, bias, w, A, W, ds->p_bias, ds->p_w, ds->p_A, ds->p_W, st));
+    const bool grad = out_g_bias != nullptr || out_g_w != nullptr;
+    TRY(ds->o_ll.ensure(ncols));
+    if (grad) { TRY(ds->o_gb.ensure(ncols)); TRY(ds->o_gw.ensure((size_t)ncols * NB)); }
+    TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, A ? ds->p_A.p : nullptr, W ? ds->p_W.p : nullptr,
+                         nlin, n_lo, n_hi, path, ds->o_ll.p, grad ? ds->o_gb.p : nullptr, grad ? ds->o_gw.p : nullptr,
+                         nullptr, nullptr, st));
+    PYGLM_CUDA(cudaMemcpyAsync(out_ll, ds->o_ll.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_g_bias) PYGLM_CUDA(cudaMemcpyAsync(out_g_bias, ds->o_gb.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (out_g_w) PYGLM_CUDA(cudaMemcpyAsync(out_g_w, ds->o_gw.p, (size_t)ncols * NB * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PYGLM_CUDA(cudaStreamSynchronize(st));
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_firing_rate(pyglm_b200_dataset* ds,
+                           const double* bias, const double* w, const int8_t* A, const double* W,
+                           int32_t nlin, int32_t n_lo, int32_t n_hi, double* out_lam)
+{
+    DS_GUARD(ds);
+    PYGLM_REQUIRE(out_lam != nullptr, "firing_rate: out is null");
+    PYGLM_REQUIRE(0 <= n_lo && n_lo <= n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
+    const int ncols = n_hi - n_lo;
+    if (ncols == 0 || ds->T == 0) return PYGLM_B200_OK;
+    cudaStream_t st = ds->stream;
+    TRY(stage_params(ds, bias, w, A, W, ds->p_bias, ds->p_w, ds->p_A, ds->p_W, st));
+    TRY(ds->o_ll.ensure(ncols));
+    TRY(ds->lam.ensure((size_t)ds->T * ncols));
+    TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, A ? ds->p_A.p : nullptr, W ? ds->p_W.p : nullptr,
+                         nlin, n_lo, n_hi, PYGLM_B200_PATH_FP64, ds->o_ll.p, nullptr, nullptr,
+                         nullptr, ds->lam.p, st));
+    PYGLM_CUDA(cudaMemcpyAsync(out_lam, ds->lam.p, (size_t)ds->T * ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PYGLM_CUDA(cudaStreamSynchronize(st));
+    return PYGLM_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// Gibbs
+// ------------------------------------------------------------------------------------
+static GibbsArgs gibbs_args(pyglm_b200_dataset* ds)
+{
+    GibbsArgs g{};
+    g.X = ds->X.p; g.ldx = ds->ldx; g.x_dtype = ds->x_dtype;
+    g.St = ds->St.p; g.T = ds->T; g.N = ds->N; g.B = ds->B;
+    g.dt = ds->dt; g.nlin = ds->g_nlin; g.n_lo = ds->g_nlo; g.ncols = ds->g_ncols;
+    g.bias = ds->g_bias.p; g.w = ds->g_w.p; g.A = ds->g_A.p; g.W = ds->g_W.p;
+    g.Inet = ds->Inet.p; g.partial = ds->partial.p; g.nchunks = gibbs_num_chunks(ds->T);
+    return g;
+}
+
+int pyglm_b200_gibbs_begin(pyglm_b200_dataset* ds,
+                           const double* bias, const double* w, const int8_t* A, const double* W,
+                           int32_t nlin, int32_t n_lo, int32_t n_hi)
+{
+    DS_GUARD(ds);
+    PYGLM_REQUIRE(nlin == PYGLM_B200_NLIN_EXP || nlin == PYGLM_B200_NLIN_SOFTPLUS, "bad nlin %d", nlin);
+    PYGLM_REQUIRE(0 <= n_lo && n_lo < n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
+    PYGLM_REQUIRE(A && W, "gibbs_begin needs explicit A and W");
+    cudaStream_t st = ds->stream;
+    ds->gibbs_active = false;
+    TRY(stage_params(ds, bias, w, A, W, ds->g_bias, ds->g_w, ds->g_A, ds->g_W, st));
+    const int ncols = n_hi - n_lo;
+    TRY(ds->Inet.ensure((size_t)ncols * (ds->T ? ds->T : 1)));
+    TRY(ds->o_ll.ensure(ncols));
+    // I_net[:, n] = I_imp @ (A[:,n] * W[:,n])  (glm.py:39) via the FP64 forward contraction
+    TRY(ll_grad_dev_impl(ds, ds->g_bias.p, ds->g_w.p, ds->g_A.p, ds->g_W.p, nlin, n_lo, n_hi, PYGLM_B200_PATH_FP64,
+                         ds->o_ll.p, nullptr, nullptr, ds->Inet.p, nullptr, st));
+    PYGLM_CUDA(cudaStreamSynchronize(st));
+    ds->g_nlo = n_lo; ds->g_ncols = ncols; ds->g_nlin = nlin;
+    ds->gibbs_active = true;
+    return PYGLM_B200_OK;
+}
+
+static int gibbs_check_edges(const pyglm_b200_dataset* ds, int M, const int32_t* cols, const int32_t* pres)
+{
+    PYGLM_REQUIRE(M >= 0 && M <= 65535, "gibbs: batch size %d outside [0,65535]", M);
+    PYGLM_REQUIRE(M == 0 || (cols && pres), "gibbs: null edge arrays");
+    std::vector<char> seen(ds->g_ncols, 0);
+    for (int m = 0; m < M; ++m) {
+        PYGLM_REQUIRE(cols[m] >= ds->g_nlo && cols[m] < ds->g_nlo + ds->g_ncols, "gibbs: column %d not resident", cols[m]);
+        PYGLM_REQUIRE(pres[m] >= 0 && pres[m] < ds->N, "gibbs: bad presynaptic index %d", pres[m]);
+        PYGLM_REQUIRE(!seen[cols[m] - ds->g_nlo], "gibbs: column %d appears twice in one batch", cols[m]);
+        seen[cols[m] - ds->g_nlo] = 1;
+    }
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_gibbs_delta_ll(pyglm_b200_dataset* ds, int32_t M, const int32_t* cols, const int32_t* pres,
+                              int32_t Q, const double* w_cand, double* out_ll)
+{
+    DS_GUARD(ds);
+    if (!ds->gibbs_active) { set_error("gibbs_delta_ll before gibbs_begin"); return PYGLM_B200_ESTATE; }
+    TRY(gibbs_check_edges(ds, M, cols, pres));
+    PYGLM_REQUIRE(Q >= 1 && Q <= kMaxCand, "gibbs_delta_ll: Q=%d outside [1,%d]", Q, kMaxCand);
+    if (M == 0) return PYGLM_B200_OK;
+    PYGLM_REQUIRE(w_cand && out_ll, "gibbs_delta_ll: null argument");
+    cudaStream_t st = ds->stream;
+    if (ds->T == 0) { for (int i = 0; i < M * Q; ++i) out_ll[i] = 0.0; return PYGLM_B200_OK; }
+    TRY(ds->g_cols.ensure(M)); TRY(ds->g_pres.ensure(M));
+    TRY(ds->g_wcand.ensure((size_t)M * Q)); TRY(ds->g_out.ensure((size_t)M * Q));
+    GibbsArgs g = gibbs_args(ds);
+    TRY(ds->partial.ensure((size_t)M * g.nchunks * Q));
+    g.partial = ds->partial.p;
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_cols.p, cols, M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_pres.p, pres, M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_wcand.p, w_cand, (size_t)M * Q * sizeof(double), cudaMemcpyHostToDevice, st));
+    TRY(launch_gibbs_delta(g, M, ds->g_cols.p, ds->g_pres.p, Q, ds->g_wcand.p, ds->g_out.p, st));
+    PYGLM_CUDA(cudaMemcpyAsync(out_ll, ds->g_out.p, (size_t)M * Q * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PYGLM_CUDA(cudaStreamSynchronize(st));
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_gibbs_commit(pyglm_b200_dataset* ds, int32_t M, const int32_t* cols, const int32_t* pres,
+                            const int8_t* a_new, const double* w_new)
+{
+    DS_GUARD(ds);
+    if (!ds->gibbs_active) { set_error("gibbs_commit before gibbs_begin"); return PYGLM_B200_ESTATE; }
+    TRY(gibbs_check_edges(ds, M, cols, pres));
+    if (M == 0) return PYGLM_B200_OK;
+    PYGLM_REQUIRE(a_new && w_new, "gibbs_commit: null argument");
+    cudaStream_t st = ds->stream;
+    TRY(ds->g_cols.ensure(M)); TRY(ds->g_pres.ensure(M));
+    TRY(ds->g_anew.ensure(M)); TRY(ds->g_wnew.ensure(M));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_cols.p, cols, M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_pres.p, pres, M * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_anew.p, a_new, M, cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->g_wnew.p, w_new, M * sizeof(double), cudaMemcpyHostToDevice, st));
+    GibbsArgs g = gibbs_args(ds);
+    TRY(launch_gibbs_commit(g, M, ds->g_cols.p, ds->g_pres.p, ds->g_anew.p, ds->g_wnew.p, st));
+    PYGLM_CUDA(cudaStreamSynchronize(st));
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_gibbs_get_state(const pyglm_b200_dataset* ds, int8_t* A, double* W)
+{
+    DS_GUARD(ds);
+    if (!ds->gibbs_active) { set_error("gibbs_get_state before gibbs_begin"); return PYGLM_B200_ESTATE; }
+    const size_t NN = (size_t)ds->N * ds->N;
+    PYGLM_CUDA(cudaStreamSynchronize(ds->stream));
+    if (A) PYGLM_CUDA(cudaMemcpy(A, ds->g_A.p, NN, cudaMemcpyDeviceToHost));
+    if (W) PYGLM_CUDA(cudaMemcpy(W, ds->g_W.p, NN * sizeof(double), cudaMemcpyDeviceToHost));
+    return PYGLM_B200_OK;
+}
+
+int pyglm_b200_gibbs_end(pyglm_b200_dataset* ds)
+{
+    DS_GUARD(ds);
+    ds->gibbs_active = false;
+    return PYGLM_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// Shared declarations for the pyglm_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pyglm_b200.h"
+
+namespace pyglm {
+
+void set_error(const char* fmt, ...);
+
+#define PYGLM_CUDA(call)                                                               \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            ::pyglm::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,           \
+                               cudaGetErrorString(e_));                                \
+            return (e_ == cudaErrorMemoryAllocation) ? PYGLM_B200_ENOMEM               \
+                                                     : PYGLM_B200_ECUDA;               \
+        }                                                                              \
+    } while (0)
+
+#define PYGLM_REQUIRE(cond, ...)                                                       \
+    do {                                                                               \
+        if (!(cond)) {                                                                 \
+            ::pyglm::set_error(__VA_ARGS__);                                           \
+            return PYGLM_B200_EINVAL;                                                  \
+        }                                                                              \
+    } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+constexpr int kMaxBasis = 16;   // B <= 16 (reference configs use 5 and 10)
+constexpr int kMaxCand = 16;    // Q <= 16 candidate weights per edge (reference: 10 GH nodes + w=0)
+
+// ---------------------------------------------------------------------------------
+// Launchers (defined in the .cu files).  All enqueue on `stream` and return a status.
+// ---------------------------------------------------------------------------------
+
+// K1: X[t][pre*B+b] = sum_{k=1..R} ibasis[k-1][b] * S[halo+t-k][pre]
+int launch_filter(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                  void* dX, int64_t ldx, int x_dtype, cudaStream_t stream);
+
+// St[n][t] = S[halo+t][n]
+int launch_transpose_spikes(const uint8_t* dS, int64_t T, int N, int halo, uint8_t* dSt, cudaStream_t stream);
+
+// M[j][n'] = A[pre][n] W[pre][n] w[n][j]   (n = n_lo+n', pre = j/B), zero padded to [NBp][Np];
+// Weff[n'][pre] = A[pre][n] W[pre][n]
+int launch_build_M(const double* d_w, const int8_t* d_A, const double* d_W, int N, int B, int n_lo, int ncols,
+                   double* d_M, int Np, int64_t NBp, double* d_Weff, cudaStream_t stream);
+
+struct SimtArgs {
+    const void* X; int64_t ldx; int x_dtype;
+    const uint8_t* S; int64_t T; int N; int halo; int B;
+    double dt; int nlin;
+    int n_lo, ncols, Np;
+    const double* bias;      // [N]
+    const double* M;         // [NBp][Np]
+    const double* Weff;      // [ncols][N]
+    double* R;               // [T][Np] residuals (nullptr: forward only)
+    double* llp; double* gbp;   // [tiles][Np] partials
+    double* Gp; int splits;  // [splits][NBp64][Np]
+    double* out_ll; double* out_gb; double* out_gw;   // [ncols], [ncols], [ncols][N*B]
+    double* act_out;         // optional [ncols][T] activation without bias (Gibbs I_net)
+    double* lam_out;         // optional [T][ncols] firing rate
+};
+int simt_workspace_tiles(int64_t T);
+int simt_choose_splits(int64_t T, int N, int B, int Np);
+int launch_simt_ll_grad(const SimtArgs& a, cudaStream_t stream);
+
+struct GibbsArgs {
+    const void* X; int64_t ldx; int x_dtype;
+    const uint8_t* St; int64_t T; int N; int B;
+    double dt; int nlin;
+    int n_lo, ncols;
+    const double* bias;      // [N]
+    const double* w;         // [N][N*B]
+    int8_t* A; double* W;    // device state [N][N]
+    double* Inet;            // [ncols][T]
+    double* partial;         // [M][nchunks][Q]
+    int nchunks;
+};
+int gibbs_num_chunks(int64_t T);
+int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const int32_t* d_pres, int Q,
+                       const double* d_wcand, double* d_out, cudaStream_t stream);
+int launch_gibbs_commit(const GibbsArgs& g, int M, const int32_t* d_cols, const int32_t* d_pres,
+                        const int8_t* d_anew, const double* d_wnew, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------
+// Device math shared by K2/K4: nonlinearity, its derivative and log, in FP64.
+// components/nlin.py:25 (exp), :43/:47 (log(1+exp(x)) a.k.a. 'explinear').
+// ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void nlin_eval(double x, int nlin, double& lam, double& dlam, double& loglam) {
+    if (nlin == PYGLM_B200_NLIN_EXP) {
+        lam = exp(x);
+        dlam = lam;
+        loglam = x;
+    } else {
+        const double e = exp(-fabs(x));
+        const double l1p = log1p(e);
+        lam = x > 0.0 ? x + l1p : l1p;
+        dlam = x > 0.0 ? 1.0 / (1.0 + e) : e / (1.0 + e);
+        loglam = log(lam);
+    }
+}
+#endif
+
+}  // namespace pyglm

@@ -1,0 +1,209 @@
+// K1: spike-history filtering.
+//   X[t][pre*B+b] = sum_{k=1..R} ibasis[k-1][b] * S[t-k][pre]
+// Reference: convolve_with_basis, pyglm/utils/basis.py:201-236 (zero row prepended :220,
+// 'full'[:T] :232-234), called from LinearBasisImpulses.preprocess_data (impulse.py:114-130).
+//
+// The reference runs B dense FFT convolutions.  Spike trains are sparse small integers
+// (~2% of bins non-zero), so this kernel gathers instead: each block owns a tile of TT output
+// bins x PC presynaptic columns, compacts the spikes of the tile (plus its R-bin left halo)
+// into per-column lists in shared memory, and every output bin sums ibasis rows over the
+// spikes inside its own window.  Accumulation is FP64 in increasing spike-time order (the
+// order oracle/convolve_with_basis_direct uses), the result is rounded once to the storage
+// type and leaves through a padded shared-memory tile so global stores are fully coalesced.
+#include "common.cuh"
+
+namespace pyglm {
+
+constexpr int kFiltThreads = 256;
+constexpr int kFiltWarps = kFiltThreads / 32;
+
+struct FiltSmemLayout {
+    size_t off_basis, off_out, off_ent, off_idx, off_s, total;
+};
+
+template <typename XT>
+static FiltSmemLayout filt_layout(int R, int B, int tt, int pc) {
+    FiltSmemLayout L;
+    const int rows = tt + R;
+    size_t o = 0;
+    L.off_basis = o; o += (size_t)R * B * sizeof(double);
+    L.off_out = o;   o += (size_t)tt * (pc * B + 1) * sizeof(XT);
+    o = (o + 7) & ~(size_t)7;
+    L.off_ent = o;   o += (size_t)rows * pc * sizeof(uint32_t);
+    L.off_idx = o;   o += (size_t)(rows + 1) * pc * sizeof(uint16_t);
+    L.off_s = o;     o += (size_t)rows * (pc + 4);
+    L.total = (o + 15) & ~(size_t)15;
+    return L;
+}
+
+template <typename XT, int BMAX>
+__global__ void __launch_bounds__(kFiltThreads)
+filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
+              const double* __restrict__ ibasis, int R, int B,
+              XT* __restrict__ X, int64_t ldx, int tt, int pc, FiltSmemLayout L)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    double*   sB   = reinterpret_cast<double*>(smem + L.off_basis);   // [R][B]
+    XT*       sOut = reinterpret_cast<XT*>(smem + L.off_out);         // [tt][pc*B+1]
+    uint32_t* sEnt = reinterpret_cast<uint32_t*>(smem + L.off_ent);   // [rows][pc]  (row<<8 | count)
+    uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.off_idx);   // [rows+1][pc] #spikes in tile rows [0,i)
+    uint8_t*  sS   = smem + L.off_s;                                  // [rows][pc+4]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rows = tt + R;
+    const int64_t t0 = (int64_t)blockIdx.x * tt;      // first output bin of the tile
+    const int c0 = blockIdx.y * pc;                   // first presynaptic column of the tile
+    const int sstride = pc + 4;
+    const int ostride = pc * B + 1;
+
+    // ---- stage the spike tile (tile row i <-> S row halo + t0 - R + i) and the basis
+    const int64_t g0 = (int64_t)halo + t0 - R;
+    const int64_t gmax = (int64_t)halo + T;
+    for (int e = tid; e < rows * pc; e += kFiltThreads) {
+        const int i = e / pc, c = e - i * pc;
+        const int64_t g = g0 + i;
+        uint8_t v = 0;
+        if (g >= 0 && g < gmax && c0 + c < N) v = S[g * N + c0 + c];
+        sS[i * sstride + c] = v;
+    }
+    for (int e = tid; e < R * B; e += kFiltThreads) sB[e] = ibasis[e];
+    __syncthreads();
+
+    // ---- compact each column's spikes: one warp per column, ballot prefix sums
+    for (int c = warp; c < pc; c += kFiltWarps) {
+        int count = 0;
+        for (int i0 = 0; i0 < rows; i0 += 32) {
+            const int i = i0 + lane;
+            const uint32_t v = (i < rows) ? sS[i * sstride + c] : 0u;
+            const uint32_t m = __ballot_sync(0xffffffffu, v != 0u);
+            const int pos = count + __popc(m & ((1u << lane) - 1u));
+            if (i < rows) sIdx[i * pc + c] = (uint16_t)pos;
+            if (v) sEnt[pos * pc + c] = ((uint32_t)i << 8) | v;
+            count += __popc(m);
+        }
+        if (lane == 0) sIdx[rows * pc + c] = (uint16_t)count;
+    }
+    __syncthreads();
+
+    // ---- gather: a warp task = 32 consecutive output bins of one column
+    const int ngroups = tt / 32;
+    for (int task = warp; task < ngroups * pc; task += kFiltWarps) {
+        const int tg = task / pc, c = task - tg * pc;
+        const int tl = tg * 32 + lane;          // output bin within the tile
+        const int i = tl + R;                   // its tile row; window = tile rows [tl, tl+R-1]
+        const int e0 = sIdx[(tg * 32) * pc + c];
+        const int e1 = sIdx[(tg * 32 + 31 + R) * pc + c];
+        double acc[BMAX];
+#pragma unroll
+        for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
+        for (int e = e0; e < e1; ++e) {
+            const uint32_t ent = sEnt[e * pc + c];        // warp-uniform broadcast
+            const int k = i - (int)(ent >> 8);            // lag
+            if (k >= 1 && k <= R) {
+                const double cnt = (double)(ent & 0xffu);
+                const double* row = sB + (size_t)(k - 1) * B;
+#pragma unroll
+                for (int b = 0; b < BMAX; ++b)
+                    if (b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(cnt, row[b]));
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < BMAX; ++b)
+            if (b < B) sOut[tl * ostride + c * B + b] = (XT)acc[b];
+    }
+    __syncthreads();
+
+    // ---- coalesced copy-out of the valid part of the tile
+    const int ncol = min(pc, N - c0);
+    const int width = ncol * B;
+    const int nrow = (int)min((int64_t)tt, T - t0);
+    XT* dst = X + t0 * ldx + (int64_t)c0 * B;
+    for (int e = tid; e < nrow * width; e += kFiltThreads) {
+        const int tl = e / width, j = e - tl * width;
+        dst[(int64_t)tl * ldx + j] = sOut[tl * ostride + j];
+    }
+}
+
+template <typename XT, int BMAX>
+static int launch_filter_t(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                           XT* dX, int64_t ldx, cudaStream_t stream)
+{
+    // pick the largest tile whose shared memory fits (<= 200 KB leaves room for 1 block/SM at worst)
+    const int cand[][2] = {{64, 32}, {32, 32}, {32, 16}, {32, 8}, {32, 4}};
+    int tt = 0, pc = 0;
+    FiltSmemLayout L{};
+    for (auto& c : cand) {
+        L = filt_layout<XT>(R, B, c[0], c[1]);
+        if (L.total <= 200 * 1024) { tt = c[0]; pc = c[1]; break; }
+    }
+    if (tt == 0) {
+        set_error("filter: R=%d B=%d needs more shared memory than one SM has", R, B);
+        return PYGLM_B200_EUNSUPPORTED;
+    }
+    if (tt + R > 65535) {
+        set_error("filter: R=%d too long", R);
+        return PYGLM_B200_EUNSUPPORTED;
+    }
+    auto kern = filter_kernel<XT, BMAX>;
+    PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+    dim3 grid((unsigned)ceil_div(T, tt), (unsigned)ceil_div(N, pc));
+    kern<<<grid, kFiltThreads, L.total, stream>>>(dS, T, N, halo, d_ibasis, R, B, dX, ldx, tt, pc, L);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
+int launch_filter(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                  void* dX, int64_t ldx, int x_dtype, cudaStream_t stream)
+{
+    if (B < 1 || B > kMaxBasis) {
+        set_error("filter: B=%d outside [1,%d]", B, kMaxBasis);
+        return PYGLM_B200_EUNSUPPORTED;
+    }
+    if (T <= 0) return PYGLM_B200_OK;
+    if (x_dtype == PYGLM_B200_X_F32) {
+        float* x = static_cast<float*>(dX);
+        if (B <= 5)  return launch_filter_t<float, 5>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B <= 10) return launch_filter_t<float, 10>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        return launch_filter_t<float, 16>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+    } else {
+        double* x = static_cast<double*>(dX);
+        if (B <= 5)  return launch_filter_t<double, 5>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B <= 10) return launch_filter_t<double, 10>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        return launch_filter_t<double, 16>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// St[n][t] = S[halo+t][n]: column-major copy of the spikes for the per-column streams
+// the Gibbs kernel reads (glm.py:52 indexes S[:, n], a strided column).
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose_spikes_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo, uint8_t* __restrict__ St)
+{
+    __shared__ uint8_t tile[32][33];
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t t = t0 + r;
+        const int n = n0 + tx;
+        tile[r][tx] = (t < T && n < N) ? S[((int64_t)halo + t) * N + n] : (uint8_t)0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r;
+        const int64_t t = t0 + tx;
+        if (n < N && t < T) St[(int64_t)n * T + t] = tile[tx][r];
+    }
+}
+
+int launch_transpose_spikes(const uint8_t* dS, int64_t T, int N, int halo, uint8_t* dSt, cudaStream_t stream)
+{
+    if (T <= 0) return PYGLM_B200_OK;
+    dim3 grid((unsigned)ceil_div(T, 32), (unsigned)ceil_div(N, 32));
+    transpose_spikes_kernel<<<grid, 256, 0, stream>>>(dS, T, N, halo, dSt);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
+}  // namespace pyglm

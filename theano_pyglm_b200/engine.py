@@ -1,0 +1,234 @@
+"""ctypes binding of the C ABI in include/pyglm_b200.h.
+
+This is the only place Python touches the CUDA engine.  There is no CPU fallback: if the
+shared library is missing or no GPU is visible, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpyglm_b200.so")
+
+NLIN_EXP, NLIN_SOFTPLUS = 0, 1
+X_F32, X_F64 = 0, 1
+PATH_AUTO, PATH_FP64, PATH_TC = 0, 1, 2
+_PATHS = {"auto": PATH_AUTO, "fp64": PATH_FP64, "tc": PATH_TC}
+_NLINS = {"exp": NLIN_EXP, "explinear": NLIN_SOFTPLUS, "softplus": NLIN_SOFTPLUS}
+
+EXPORTS = [
+    "pyglm_b200_last_error", "pyglm_b200_abi_version",
+    "pyglm_b200_dataset_create", "pyglm_b200_dataset_destroy", "pyglm_b200_dataset_info",
+    "pyglm_b200_dataset_get_fS", "pyglm_b200_dataset_device_X", "pyglm_b200_dataset_device_S",
+    "pyglm_b200_dataset_refilter",
+    "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_firing_rate",
+    "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_commit",
+    "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
+]
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen the engine; fail loudly if it has not been built (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EngineError(
+            "pyglm_b200 CUDA engine not built: %s is missing. Run `python -m theano_pyglm_b200.build` "
+            "(or __graft_entry__.build()). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    p, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.pyglm_b200_last_error.restype = C.c_char_p
+    lib.pyglm_b200_last_error.argtypes = []
+    lib.pyglm_b200_abi_version.restype = i32
+    lib.pyglm_b200_dataset_create.argtypes = [p, i64, i32, i32, f64, p, i32, i32, i32, i32, C.POINTER(p)]
+    lib.pyglm_b200_dataset_destroy.argtypes = [p]
+    lib.pyglm_b200_dataset_info.argtypes = [p] + [p] * 7
+    lib.pyglm_b200_dataset_get_fS.argtypes = [p, p]
+    lib.pyglm_b200_dataset_device_X.argtypes = [p]
+    lib.pyglm_b200_dataset_device_X.restype = p
+    lib.pyglm_b200_dataset_device_S.argtypes = [p]
+    lib.pyglm_b200_dataset_device_S.restype = p
+    lib.pyglm_b200_dataset_refilter.argtypes = [p, p]
+    lib.pyglm_b200_ll_grad.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p]
+    lib.pyglm_b200_ll_grad_dev.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p, p]
+    lib.pyglm_b200_firing_rate.argtypes = [p, p, p, p, p, i32, i32, i32, p]
+    lib.pyglm_b200_gibbs_begin.argtypes = [p, p, p, p, p, i32, i32, i32]
+    lib.pyglm_b200_gibbs_delta_ll.argtypes = [p, i32, p, p, i32, p, p]
+    lib.pyglm_b200_gibbs_commit.argtypes = [p, i32, p, p, p, p]
+    lib.pyglm_b200_gibbs_get_state.argtypes = [p, p, p]
+    lib.pyglm_b200_gibbs_end.argtypes = [p]
+    for name in EXPORTS:      # every declared symbol must resolve
+        getattr(lib, name)
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load_library().pyglm_b200_last_error().decode("utf-8", "replace")
+        raise EngineError("pyglm_b200 error %d: %s" % (rc, msg))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != tuple(shape):
+        a = a.reshape(shape)
+    return a
+
+
+def spikes_to_u8(S):
+    """Bin counts as uint8, bit-exact: data['S'] is float64 holding small non-negative integers
+    (population.py:345-349 caps a bin at 10)."""
+    S = np.asarray(S)
+    if S.dtype == np.uint8:
+        return np.ascontiguousarray(S)
+    if S.size and (np.any(S < 0) or np.any(S > 255) or np.any(S != np.floor(S))):
+        raise ValueError("spike counts must be integers in [0, 255]")
+    return np.ascontiguousarray(S.astype(np.uint8))
+
+
+def nlin_code(nlin):
+    if isinstance(nlin, str):
+        return _NLINS[nlin.lower()]
+    return int(nlin)
+
+
+class Dataset:
+    """One data sequence resident on one GPU: spikes + filtered spike train X (K1 output)."""
+
+    def __init__(self, S, dt, ibasis, halo=0, x_dtype="f32", device=0):
+        lib = load_library()
+        S = spikes_to_u8(S)
+        if S.ndim != 2:
+            raise ValueError("S must be (T, N)")
+        ibasis = _f64(ibasis)
+        if ibasis.ndim != 2:
+            raise ValueError("ibasis must be (R, B)")
+        self.T = int(S.shape[0]) - int(halo)
+        self.N = int(S.shape[1])
+        self.R, self.B = (int(v) for v in ibasis.shape)
+        self.dt = float(dt)
+        self.halo = int(halo)
+        self.device = int(device)
+        self.x_dtype = X_F64 if x_dtype in ("f64", X_F64, np.float64) else X_F32
+        self.h2d_bytes = S.nbytes + ibasis.nbytes
+        h = C.c_void_p()
+        _check(lib.pyglm_b200_dataset_create(_ptr(S), self.T, self.halo, self.N, self.dt, _ptr(ibasis),
+                                             self.R, self.B, self.x_dtype, self.device, C.byref(h)))
+        self._h = h
+        ldx = C.c_int64()
+        _check(lib.pyglm_b200_dataset_info(h, None, None, None, None, C.addressof(ldx), None, None))
+        self.ldx = int(ldx.value)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().pyglm_b200_dataset_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- K1
+    def fS(self):
+        """data['fS'] (T, N, B) float64, copied back from the device (impulse.py:130)."""
+        out = np.empty((self.T, self.N, self.B), dtype=np.float64)
+        _check(load_library().pyglm_b200_dataset_get_fS(self._h, _ptr(out)))
+        return out
+
+    def refilter(self, stream=0):
+        _check(load_library().pyglm_b200_dataset_refilter(self._h, C.c_void_p(stream)))
+
+    def device_X(self):
+        return load_library().pyglm_b200_dataset_device_X(self._h)
+
+    # -- K2
+    def _params(self, bias, w, A, W):
+        N, NB = self.N, self.N * self.B
+        bias = _f64(bias, (N,))
+        w = _f64(w, (N, NB))
+        A = None if A is None else np.ascontiguousarray(A, dtype=np.int8).reshape(N, N)
+        W = None if W is None else _f64(W, (N, N))
+        return bias, w, A, W
+
+    def ll_grad(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto", grad=True):
+        """(ll, g_bias, g_w) for neurons [n_lo, n_hi); host buffers in and out (the e2e call)."""
+        n_hi = self.N if n_hi is None else n_hi
+        nc = n_hi - n_lo
+        bias, w, A, W = self._params(bias, w, A, W)
+        ll = np.empty(nc)
+        gb = np.empty(nc) if grad else None
+        gw = np.empty((nc, self.N * self.B)) if grad else None
+        _check(load_library().pyglm_b200_ll_grad(self._h, _ptr(bias), _ptr(w), _ptr(A), _ptr(W), nlin_code(nlin),
+                                                 n_lo, n_hi, _PATHS.get(path, path), _ptr(ll), _ptr(gb), _ptr(gw)))
+        return (ll, gb, gw) if grad else ll
+
+    def ll(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto"):
+        return self.ll_grad(bias, w, A, W, nlin, n_lo, n_hi, path, grad=False)
+
+    def ll_grad_dev(self, d_bias, d_w, d_A, d_W, nlin, n_lo, n_hi, path, d_ll, d_gb, d_gw, stream):
+        """Device-pointer variant: arguments are integer device addresses (tensor.data_ptr())."""
+        vp = C.c_void_p
+        _check(load_library().pyglm_b200_ll_grad_dev(self._h, vp(d_bias), vp(d_w), vp(d_A) if d_A else None,
+                                                     vp(d_W) if d_W else None, nlin_code(nlin), n_lo, n_hi,
+                                                     _PATHS.get(path, path), vp(d_ll), vp(d_gb) if d_gb else None,
+                                                     vp(d_gw) if d_gw else None, vp(stream)))
+
+    def firing_rate(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None):
+        n_hi = self.N if n_hi is None else n_hi
+        bias, w, A, W = self._params(bias, w, A, W)
+        out = np.empty((self.T, n_hi - n_lo))
+        _check(load_library().pyglm_b200_firing_rate(self._h, _ptr(bias), _ptr(w), _ptr(A), _ptr(W), nlin_code(nlin),
+                                                     n_lo, n_hi, _ptr(out)))
+        return out
+
+    # -- K4
+    def gibbs_begin(self, bias, w, A, W, nlin="explinear", n_lo=0, n_hi=None):
+        n_hi = self.N if n_hi is None else n_hi
+        bias, w, A, W = self._params(bias, w, A, W)
+        _check(load_library().pyglm_b200_gibbs_begin(self._h, _ptr(bias), _ptr(w), _ptr(A), _ptr(W), nlin_code(nlin),
+                                                     n_lo, n_hi))
+
+    def gibbs_delta_ll(self, cols, pres, w_cand):
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        pres = np.ascontiguousarray(pres, dtype=np.int32)
+        w_cand = _f64(w_cand)
+        if w_cand.ndim == 1:
+            w_cand = w_cand.reshape(len(cols), -1)
+        M, Q = w_cand.shape
+        out = np.empty((M, Q))
+        _check(load_library().pyglm_b200_gibbs_delta_ll(self._h, M, _ptr(cols), _ptr(pres), Q, _ptr(w_cand), _ptr(out)))
+        return out
+
+    def gibbs_commit(self, cols, pres, a_new, w_new):
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        pres = np.ascontiguousarray(pres, dtype=np.int32)
+        a_new = np.ascontiguousarray(a_new, dtype=np.int8)
+        w_new = _f64(w_new)
+        _check(load_library().pyglm_b200_gibbs_commit(self._h, len(cols), _ptr(cols), _ptr(pres), _ptr(a_new), _ptr(w_new)))
+
+    def gibbs_state(self):
+        A = np.empty((self.N, self.N), dtype=np.int8)
+        W = np.empty((self.N, self.N))
+        _check(load_library().pyglm_b200_gibbs_get_state(self._h, _ptr(A), _ptr(W)))
+        return A, W
+
+    def gibbs_end(self):
+        _check(load_library().pyglm_b200_gibbs_end(self._h))
