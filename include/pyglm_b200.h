@@ -133,6 +133,10 @@ PYGLM_B200_API int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
                            double* d_out_ll, double* d_out_g_bias, double* d_out_g_w,
                            void* stream);
 
+/* which arithmetic path a call with `path` would take on this dataset: returns
+ * PYGLM_B200_PATH_FP64 / PYGLM_B200_PATH_TC, or PYGLM_B200_EUNSUPPORTED. */
+PYGLM_B200_API int pyglm_b200_resolve_path(const pyglm_b200_dataset* ds, int32_t path);
+
 /* firing rate lam[t][n] for n in [n_lo,n_hi): host float64 [T][n_hi-n_lo].
  * Replaces seval(glm.lam, ...) in Population.eval_state (population.py:88-123); this is
  * the quantity the reference's only numeric assertion checks

@@ -155,7 +155,10 @@ def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
     ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype)
     A_ref, W_ref = p['A'].copy(), p['W'].copy()
     ds.gibbs_begin(p['bias'], p['w'], A_ref, W_ref, nlin="explinear")
-    tol = 1e-10 if x_dtype == "f64" else 1e-6
+    # FP32 storage of X perturbs u = X.w at ~1e-8 relative; candidate lls are differences of O(1e4)
+    # sums, so the FP32-X bound is absolute.  Decision parity is asserted for both; the sampler
+    # itself uses FP64 X (Population picks x_dtype="f64" for MCMC).
+    rtol, atol = (1e-10, 1e-9) if x_dtype == "f64" else (1e-7, 2e-5)
     for n_post in (1, 4):
         order = rng.permutation(N)
         unif = rng.random(N)
@@ -169,8 +172,8 @@ def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
             mu, sig = (mu_ref, sig_ref) if n_pre == n_post else (mu_w, sig_w)
             cand = np.concatenate([orc.gh_candidates(mu, sig), [0.0]])
             out = ds.gibbs_delta_ll([n_post], [n_pre], cand[None, :])[0]
-            assert np.allclose(out[:10], rec[i]['log_L'], rtol=tol, atol=0)
-            assert abs(out[10] - rec[i]['ll_noA']) <= tol * abs(rec[i]['ll_noA'])
+            assert np.allclose(out[:10], rec[i]['log_L'], rtol=rtol, atol=atol)
+            assert abs(out[10] - rec[i]['ll_noA']) <= rtol * abs(rec[i]['ll_noA']) + atol
             lp_noA, lp_A = orc.collapsed_edge_log_odds(out[:10], out[10], p_A[n_pre, n_post])
             a_new = orc.log_sum_exp_sample([lp_noA, lp_A], unif[i])
             assert a_new == rec[i]['A']                      # identical accept / reject

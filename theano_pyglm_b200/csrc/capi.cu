@@ -262,6 +262,13 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     return launch_simt_ll_grad(a, stream);
 }
 
+int pyglm_b200_resolve_path(const pyglm_b200_dataset* ds, int32_t path)
+{
+    PYGLM_REQUIRE(ds != nullptr, "null dataset handle");
+    const int use = resolve_path(ds, path, false);
+    return use < 0 ? PYGLM_B200_EUNSUPPORTED : use;
+}
+
 int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
                            const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
                            int32_t nlin, int32_t n_lo, int32_t n_hi, int32_t path,

@@ -24,7 +24,7 @@ EXPORTS = [
     "pyglm_b200_dataset_create", "pyglm_b200_dataset_destroy", "pyglm_b200_dataset_info",
     "pyglm_b200_dataset_get_fS", "pyglm_b200_dataset_device_X", "pyglm_b200_dataset_device_S",
     "pyglm_b200_dataset_refilter",
-    "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_firing_rate",
+    "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_firing_rate",
     "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_commit",
     "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
 ]
@@ -61,6 +61,7 @@ def load_library():
     lib.pyglm_b200_dataset_refilter.argtypes = [p, p]
     lib.pyglm_b200_ll_grad.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p]
     lib.pyglm_b200_ll_grad_dev.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p, p]
+    lib.pyglm_b200_resolve_path.argtypes = [p, i32]
     lib.pyglm_b200_firing_rate.argtypes = [p, p, p, p, p, i32, i32, i32, p]
     lib.pyglm_b200_gibbs_begin.argtypes = [p, p, p, p, p, i32, i32, i32]
     lib.pyglm_b200_gibbs_delta_ll.argtypes = [p, i32, p, p, i32, p, p]
@@ -190,6 +191,15 @@ class Dataset:
                                                      vp(d_W) if d_W else None, nlin_code(nlin), n_lo, n_hi,
                                                      _PATHS.get(path, path), vp(d_ll), vp(d_gb) if d_gb else None,
                                                      vp(d_gw) if d_gw else None, vp(stream)))
+
+    def path_info(self, path="auto"):
+        """What a call with `path` runs on this dataset (used by bench.py's roofline bookkeeping)."""
+        use = load_library().pyglm_b200_resolve_path(self._h, _PATHS.get(path, path))
+        if use == PATH_TC:
+            return dict(name="tcgen05-3xtf32", dtype="tf32x3", x_passes=1, launches_per_eval=3, bound="hbm")
+        if use == PATH_FP64:
+            return dict(name="fp64-simt", dtype="f64", x_passes=2, launches_per_eval=5, bound="hbm")
+        raise EngineError("path %r unsupported for this dataset" % (path,))
 
     def firing_rate(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None):
         n_hi = self.N if n_hi is None else n_hi

@@ -1,0 +1,170 @@
+"""Population of coupled GLMs (interface of pyglm/population.py).
+
+Same public surface as the reference class -- Population(model); .add_data/.set_data/
+.preprocess_data; .sample(); .extract_vars(x, n); .get_variables(); .compute_ll/.compute_log_prior/
+.compute_log_p(x); .eval_state(x); .set_hyperparameters(model) -- and the same state-dict layout
+(population.py:149-162), but the N sequential `seval(glm.ll)` calls of population.py:80-84
+become one engine call over resident data.  Extra methods `ll_grad` / `glm_ll_grad` expose the
+batched likelihood + gradient the MAP and MCMC drivers consume.
+"""
+import numpy as np
+
+from . import engine
+from .components.latent import LatentVariables
+from .components.network import Network
+from .glm import Glm
+
+
+class Population:
+    def __init__(self, model, device=0, x_dtype=None, path="auto"):
+        self.model = model
+        self.N = model['N']
+        self.device = device
+        self.path = path
+        self.data_sequences = []
+        self.latent = LatentVariables(model)
+        self.network = Network(model, self.latent)
+        self.glm = Glm(model, self.network, self.latent)
+        # MCMC compares differences of log-likelihood sums against uniforms: keep X in FP64 there.
+        stochastic = model['network']['graph']['type'].lower() != 'complete'
+        self.x_dtype = x_dtype or ("f64" if stochastic else "f32")
+        self._current = None
+
+    # -- variables ------------------------------------------------------------------------------
+    def get_variables(self):
+        return {'latent': self.latent.get_variables(), 'net': self.network.get_variables(),
+                'glm': self.glm.get_variables()}
+
+    def set_hyperparameters(self, model):
+        self.latent.set_hyperparameters(model)
+        self.network.set_hyperparameters(model)
+        self.glm.set_hyperparameters(model)
+
+    def sample(self):
+        """Draw parameters from the prior, same draw order as population.py:149-162."""
+        v = {}
+        v['latent'] = self.latent.sample(v)
+        v['net'] = self.network.sample(v)
+        v['glms'] = []
+        for n in range(self.N):
+            xn = self.glm.sample(v)
+            xn['n'] = n
+            v['glms'].append(xn)
+        return v
+
+    def extract_vars(self, vals, n):
+        """Variables of the n-th GLM under key 'glm', everything else shared (population.py:164-175)."""
+        out = {}
+        for k, v in vals.items():
+            if k == 'glms':
+                out['glm'] = v[n]
+            else:
+                out[k] = v
+        return out
+
+    # -- data -----------------------------------------------------------------------------------
+    def preprocess_data(self, data):
+        """Upload the spikes and run the spike-history filter (K1) once; the handle stays resident.
+        The reference stores data['fS'] here (impulse.py:130); use `get_fS(data)` to pull it back."""
+        assert isinstance(data, dict), 'Data must be a dictionary'
+        self.latent.preprocess_data(data)
+        self.network.preprocess_data(data)
+        self.glm.preprocess_data(data)
+        data['_b200'] = engine.Dataset(data['S'], self.model['dt'], self.glm.imp_model.ibasis,
+                                       x_dtype=self.x_dtype, device=self.device)
+        data['preprocessed'] = True
+        return data
+
+    def add_data(self, data, set_as_current_data=True):
+        assert isinstance(data, dict), 'Data must be a dictionary'
+        assert 'S' in data, 'Data must contain an array of spike times'
+        assert isinstance(data['S'], np.ndarray), 'Spike times must be a numpy array'
+        if 'preprocessed' not in data or not data['preprocessed'] or '_b200' not in data:
+            data = self.preprocess_data(data)
+        self.data_sequences.append(data)
+        if set_as_current_data:
+            self.set_data(data)
+
+    def set_data(self, data):
+        """Condition on a data sequence.  O(1): selects the resident handle (the reference re-copies
+        S and fS into shared variables on every call, glm.py:99-110)."""
+        assert 'preprocessed' in data and data['preprocessed'] is True, \
+            'Data must be preprocessed before it can be set'
+        self._current = data
+
+    def get_fS(self, data=None):
+        return self._handle(data).fS()
+
+    def _handle(self, data=None):
+        data = self._current if data is None else data
+        if data is None:
+            raise RuntimeError("no data sequence set")
+        return data['_b200']
+
+    # -- probabilities ----------------------------------------------------------------------------
+    def ll_grad(self, x, n_lo=0, n_hi=None, data=None, grad=True):
+        """Per-neuron log-likelihoods (and gradients wrt the engine's dense blocks) on one sequence:
+        ll (n,), g_bias (n,), g_w (n, N*B) for neurons [n_lo, n_hi)."""
+        bias, w, A, W = self.glm.engine_params(x)
+        return self._handle(data).ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
+                                          path=self.path, grad=grad)
+
+    def compute_ll(self, vars):
+        """sum_n ll_n on the current data sequence (population.py:71-86)."""
+        return float(np.sum(self.ll_grad(vars, grad=False)))
+
+    def compute_log_prior(self, vars):
+        lp = 0.0
+        lp += self.latent.log_p(vars.get('latent', {}))
+        lp += self.network.log_p(vars['net'])
+        for n in range(self.N):
+            lp += self.glm.log_prior(vars['glms'][n])
+        return float(lp)
+
+    def compute_log_p(self, vars):
+        """log prior + sum over data sequences of lkhd_scale * ll (population.py:34-45, glm.py:62-63)."""
+        lp = self.compute_log_prior(vars)
+        scale = self.glm.lkhd_scale.get_value()
+        for data in self.data_sequences:
+            self.set_data(data)
+            lp += scale * self.compute_ll(vars)
+        return lp
+
+    def glm_log_p_grad(self, x, n):
+        """log posterior of neuron n's GLM variables and its gradient as a flat vector in the
+        reference's sorted-key order (bias, imp): what coord_descent.nlp/grad_nlp evaluate
+        (coord_descent.py:40-80) -- prior plus the likelihood summed over data sequences."""
+        xn = x['glms'][n]
+        lp = self.glm.log_prior(xn)
+        gp = self.glm.grad_log_prior(xn)
+        bias, w, A, W = self.glm.engine_params(x)
+        g_bias, g_w = 0.0, 0.0
+        scale = self.glm.lkhd_scale.get_value()
+        for data in self.data_sequences:
+            ll, gb, gw = data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, n_lo=n, n_hi=n + 1,
+                                               path=self.path)
+            lp += scale * ll[0]
+            g_bias = g_bias + scale * gb[0]
+            g_w = g_w + scale * gw[0]
+        g_imp = self.glm.imp_model.chain_rule(xn['imp'], g_w)
+        parts = [gp['bias']['bias'] + g_bias]
+        for k in sorted(g_imp):
+            parts.append(gp['imp'][k] + g_imp[k])
+        return float(lp), np.concatenate([np.ravel(p) for p in parts])
+
+    def eval_state(self, vars):
+        """Firing rates and currents for the current state (population.py:88-123), engine-side lam."""
+        bias, w, A, W = self.glm.engine_params(vars)
+        lam = self._handle().firing_rate(bias, w, A, W, nlin=self.glm.nlin_model.code)
+        state = {'net': {'graph': {'A': A if A is not None else np.ones((self.N, self.N))},
+                         'weights': {'W': W if W is not None else np.ones((self.N, self.N))}},
+                 'glms': []}
+        for n in range(self.N):
+            xn = vars['glms'][n]
+            state['glms'].append({'lam': lam[:, n], 'I_bias': bias[n],
+                                  'imp': {'impulse': self.glm.imp_model.impulse(xn['imp']),
+                                          'basis': self.glm.imp_model.ibasis}})
+        state['logprior'] = self.compute_log_prior(vars)
+        state['ll'] = self.compute_ll(vars)
+        state['logp'] = state['ll'] + state['logprior']
+        return state
