@@ -76,6 +76,35 @@ def test_ll_grad_fp64_path(eng, T, N, B, network, nlin):
         ds.close()
 
 
+@pytest.mark.parametrize("nlin", [orc.NLIN_SOFTPLUS, orc.NLIN_EXP])
+@pytest.mark.parametrize("T,N,B,network", [(3000, 4, 5, False), (6000, 27, 5, False), (1111, 10, 10, True),
+                                           (2500, 16, 10, True), (130, 5, 3, True), (40000, 27, 5, True)])
+def test_ll_grad_tensor_core_path(eng, T, N, B, network, nlin):
+    """tcgen05 path (FP16 split planes, FP32 epilogue, FP64 sums) at the north-star tolerances:
+    1e-6 relative on ll, 1e-5 on gradients, against the float64 oracle."""
+    p = make_problem(T, N, B, network=network)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 17.0
+    _, ll, gb, gw = oracle_all(p, nlin)
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+    assert ds.path_info("auto")["name"].startswith("tcgen05")
+    ll_g, gb_g, gw_g = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="tc")
+    assert np.max(np.abs(ll_g - ll) / np.abs(ll)) < LL_RTOL, (ll_g, ll)
+    assert rel_err(gb_g, gb) < GRAD_RTOL
+    assert rel_err(gw_g, gw) < GRAD_RTOL
+    # second call reuses the planes; sub-range of neurons; ll-only
+    lo, hi = 1, N - 1
+    ll_s, gb_s, gw_s = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, n_lo=lo, n_hi=hi, path="tc")
+    assert np.max(np.abs(ll_s - ll[lo:hi]) / np.abs(ll[lo:hi])) < LL_RTOL
+    assert rel_err(gw_s, gw[lo:hi]) < GRAD_RTOL
+    ll_only = ds.ll(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="tc")
+    assert np.max(np.abs(ll_only - ll) / np.abs(ll)) < LL_RTOL
+    # and it agrees with the exact FP64 path on the device
+    ll_x, gb_x, gw_x = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="fp64")
+    assert rel_err(gw_g, gw_x) < GRAD_RTOL and rel_err(gb_g, gb_x) < GRAD_RTOL
+    ds.close()
+
+
 def test_ll_grad_null_network_is_complete_graph(eng):
     p = make_problem(2000, 6, 5)
     _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)

@@ -1,13 +1,27 @@
-// K2 (tensor-core path): tcgen05 3xTF32 contractions with fused FP32 epilogue and FP64 sums.
+// K2 (tensor-core path): tcgen05 contractions on FP16 split planes, fused FP32 epilogue, FP64 sums.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace pyglm {
 
+// Device-resident derived data the tensor-core path keeps per dataset.
 struct TcWorkspace {
-    void* buf = nullptr;      // device scratch (operand splits, partial sums)
-    size_t bytes = 0;
-    void* tmap = nullptr;     // cached tensor maps (host)
+    // split planes of the filtered spike train: X * sx = X1 + X2 * 2^-11  (FP16 each)
+    __half* X1 = nullptr;
+    __half* X2 = nullptr;
+    int64_t ldp = 0;              // row pitch of the planes in elements (multiple of 8)
+    float* sx = nullptr;          // [NB] per-feature power-of-two scale
+    unsigned* colmax = nullptr;   // [NB] scratch for the scale search
+    bool planes_ready = false;
+    // per-call operands
+    __half* Mp = nullptr;         // [2][32][Kp] split planes of the scaled weight matrix
+    float* colpar = nullptr;      // [2][32]: 1/sm[n], bias[n]
+    double* part = nullptr;       // per-CTA partial sums
+    size_t part_elems = 0;
+    void* tmaps = nullptr;        // host copy of the two CUtensorMap descriptors
+    int num_sms = 0;
     void release();
 };
 
