@@ -105,6 +105,40 @@ def test_ll_grad_tensor_core_path(eng, T, N, B, network, nlin):
     ds.close()
 
 
+def test_tensor_core_path_at_benchmark_size(eng):
+    """BASELINE.json config C2 (N=27, T=1e6, B=5) is too big for the CPU oracle in a test, so the
+    tensor-core path is held to the north-star tolerances against the device FP64 path (itself
+    oracle-checked above), plus two size-independent properties: additivity of ll / gradients over
+    time shards (glm.py:52 is a sum over t) and the exact ll of an all-zero parameter vector."""
+    from bench import WORKLOADS, make_inputs
+    wl = WORKLOADS["c2"]
+    inp = make_inputs(wl, 1234)
+    N, T = wl["N"], wl["T"]
+    ds = eng.Dataset(inp["S"], inp["dt"], inp["ibasis"])
+    ll_x, gb_x, gw_x = ds.ll_grad(inp["bias"], inp["w"], path="fp64")
+    ll_t, gb_t, gw_t = ds.ll_grad(inp["bias"], inp["w"], path="tc")
+    assert np.max(np.abs(ll_t - ll_x) / np.abs(ll_x)) < LL_RTOL
+    assert rel_err(gb_t, gb_x) < GRAD_RTOL
+    assert rel_err(gw_t, gw_x) < GRAD_RTOL
+    # w = 0: activation is the bias, so ll has a closed form
+    ll_0 = ds.ll(inp["bias"], np.zeros_like(inp["w"]), path="tc")
+    lam = orc.nlin(inp["bias"], orc.NLIN_SOFTPLUS)
+    nspk = inp["S"].sum(axis=0, dtype=np.float64)
+    assert np.max(np.abs(ll_0 - (-inp["dt"] * lam * T + np.log(lam) * nspk)) / np.abs(ll_0)) < LL_RTOL
+    ds.close()
+    # time shards with an R-bin halo add up to the whole
+    R = inp["ibasis"].shape[0]
+    acc = [0.0, 0.0, 0.0]
+    for lo, hi in [(0, 300_000), (300_000, 650_001), (650_001, T)]:
+        halo = min(R, lo)
+        sh = eng.Dataset(inp["S"][lo - halo:hi], inp["dt"], inp["ibasis"], halo=halo)
+        out = sh.ll_grad(inp["bias"], inp["w"], path="tc")
+        acc = [a + o for a, o in zip(acc, out)]
+        sh.close()
+    assert np.max(np.abs(acc[0] - ll_x) / np.abs(ll_x)) < LL_RTOL
+    assert rel_err(acc[1], gb_x) < GRAD_RTOL and rel_err(acc[2], gw_x) < GRAD_RTOL
+
+
 def test_ll_grad_null_network_is_complete_graph(eng):
     p = make_problem(2000, 6, 5)
     _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)

@@ -15,7 +15,7 @@ SOURCES = ["capi.cu", "filter.cu", "llgrad_simt.cu", "llgrad_tc.cu", "gibbs.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
-]
+] + os.environ.get("PYGLM_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

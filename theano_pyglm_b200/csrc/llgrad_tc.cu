@@ -40,14 +40,23 @@ constexpr int kChunkBytes = kTileT * 64;    // 8192: one X-plane chunk [128 rows
 constexpr int kMChunkBytes = kNcol * 64;    // 2048: one M-plane chunk [32 rows][32 halves]
 constexpr int kRBytes = kTileT * 64;        // 8192: one residual plane [128 rows][32 halves]
 constexpr int kStages = 2;
-constexpr int kTmemCols = 256;
-constexpr int kThreads = 192;               // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue
+
+#ifndef PYGLM_TC_COLGROUPS
+#define PYGLM_TC_COLGROUPS 4
+#endif
+constexpr int kColGroups = PYGLM_TC_COLGROUPS;  // column groups: the epilogue runs 4 * kColGroups warps
+constexpr int kColsPerWarp = kNcol / kColGroups;
+constexpr int kEpiWarps = 4 * kColGroups;
+constexpr int kFirstEpiWarp = 3;                // warp 0: TMA, warp 1: forward MMA, warp 2: gradient MMA
+constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
 constexpr float kLoScale = 2048.0f;         // 2^11 between the two planes
 constexpr float kRScale = 64.0f;            // residual planes carry r * 2^6
 constexpr uint32_t kSw64 = 4;               // UMMA LayoutType::SWIZZLE_64B
+constexpr int kFlushTiles = 8;              // TMEM gradient accumulators are folded into FP64 every 8 tiles
 
 void TcWorkspace::release()
 {
+    cudaFree(Sp); Sp = nullptr;
     cudaFree(X1); cudaFree(X2); cudaFree(sx); cudaFree(colmax); cudaFree(Mp); cudaFree(colpar); cudaFree(part);
     X1 = X2 = nullptr; sx = nullptr; colmax = nullptr; Mp = nullptr; colpar = nullptr; part = nullptr;
     part_elems = 0; planes_ready = false;
@@ -83,6 +92,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a while; a poller must not)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
@@ -150,6 +170,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v)
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v)
+{
+    if constexpr (NC == 32) tmem_ld32(taddr, v);
+    else if constexpr (NC == 16) tmem_ld16(taddr, v);
+    else tmem_ld8(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -255,35 +300,58 @@ tc_prep_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A, con
 // Epilogue math (FP32): Poisson term and residual for one bin.
 //   softplus: lam = log(1+e^x), f' = sigmoid(x)     (nlin.py:43)     exp: lam = f' = e^x (nlin.py:25)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void poisson_terms(float x, float s, float dt, int nlin, float& term, float& r)
+// Branches are decided per warp (votes), so the hot path has no divergence bookkeeping:
+//   * softplus with every lane at x > 17.5: log(1+e^x) rounds to x and sigmoid(x) to 1 in FP32
+//     (e^-17.5 < 2^-25), so no transcendental is evaluated at all -- the regime of a population
+//     firing at tens of Hz (bias ~ 20, models/standard_glm.py:16-21);
+//   * the log / reciprocal needed where a spike occurred are evaluated only if some lane has one.
+template <int NLIN>
+__device__ __forceinline__ void poisson_terms(float x, float s, float dt, float& term, float& r)
 {
-    if (nlin == PYGLM_B200_NLIN_EXP) {
+    const bool any_spike = __any_sync(0xffffffffu, s != 0.f);
+    if constexpr (NLIN == PYGLM_B200_NLIN_EXP) {
         const float lam = expf(x);
         term = fmaf(-dt, lam, s * x);
         r = fmaf(-dt, lam, s);
-        return;
-    }
-    const float ax = fabsf(x);
-    const float e = __expf(-ax);                       // in (0,1]
-    float l1p;
-    if (e < 0.03125f) l1p = e * (1.0f - e * (0.5f - e * (0.33333334f - 0.25f * e)));   // log1p series, |err| < e^5/5
-    else              l1p = log1pf(e);
-    const float lam = x > 0.f ? x + l1p : l1p;
-    const float inv1pe = __frcp_rn(1.0f + e);
-    const float sig = x > 0.f ? inv1pe : e * inv1pe;
-    term = -dt * lam;
-    r = -dt * sig;
-    if (s != 0.f) {
-        term = fmaf(s, logf(lam), term);
-        r = fmaf(__fdiv_rn(s, lam), sig, r);
+    } else {
+        float lam, sig;
+        if (__all_sync(0xffffffffu, x > 17.5f)) {
+            lam = x;
+            sig = 1.0f;
+        } else {
+            const float e = __expf(-fabsf(x));                 // in (0,1]
+            float l1p = e * (1.0f - e * (0.5f - e * (0.33333334f - 0.25f * e)));   // log1p series, |err| < e^5/5
+            if (__any_sync(0xffffffffu, e >= 0.03125f)) {      // log(u) * e/(u-1) undoes the rounding of u = 1+e
+                const float u = 1.0f + e;
+                const float big = __logf(u) * __fdividef(e, u - 1.0f);
+                l1p = e >= 0.03125f ? big : l1p;
+            }
+            lam = x > 0.f ? x + l1p : l1p;
+            float inv1pe;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1pe) : "f"(1.0f + e));   // 1 ulp; f' enters r linearly
+            sig = x > 0.f ? inv1pe : e * inv1pe;
+        }
+        term = -dt * lam;
+        r = -dt * sig;
+        if (any_spike) {                                       // ~2% of bins have s != 0
+            term = fmaf(s, s != 0.f ? __logf(lam) : 0.f, term);
+            r = fmaf(__fdividef(s, lam), sig, r);
+        }
     }
 }
 
-// butterfly transpose-reduce: lane n ends with sum over the warp's 32 lanes of v[n]
+// butterfly transpose-reduce over the 32 lanes of a warp for NC per-thread values:
+// lane l ends with sum over lanes of v[l % NC]
+template <int NC>
 __device__ __forceinline__ float warp_column_sums(float* v, int lane)
 {
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
+    for (int off = 16; off >= NC; off >>= 1) {           // more lanes than columns: plain all-reduce steps
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+    }
+#pragma unroll
+    for (int off = (NC < 32 ? NC / 2 : 16); off >= 1; off >>= 1) {
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int i = 0; i < off; ++i) {
@@ -297,6 +365,7 @@ __device__ __forceinline__ float warp_column_sums(float* v, int lane)
 
 struct TcKernelArgs {
     const uint8_t* S; int64_t T; int N; int halo;
+    const uint8_t* Sp; int Np;     // padded copy of the spikes [T][Np], Np % 32 == 0 (vector loads)
     float dt; int nlin; int n_lo, ncols;
     int nch;                       // 32-feature chunks (1..5)
     int nmt;                       // 128-feature gradient tiles (1..2)
@@ -304,6 +373,10 @@ struct TcKernelArgs {
     const __half* Mp; int Kp;      // [2][32][Kp]
     const float* colpar;           // [2][32]
     double* part;                  // per CTA: [nmt][128][32] G, then [32] ll, [32] g_bias
+    int nfeat;                     // N*B real features
+    int flush;                     // fold the TMEM gradient accumulators into FP64 every `flush` tiles
+    int debug;                     // timing experiments only (PYGLM_TC_DEBUG): skip phases
+    long long* trace;              // optional [3][32][4] clock64 stamps of CTA 0 (PYGLM_TC_TRACE)
 };
 
 struct TcSmem {
@@ -317,63 +390,78 @@ __host__ __device__ inline TcSmem tc_smem_layout(int nch)
     L.stage_bytes = 2 * nch * kChunkBytes;
     L.off_M = kStages * L.stage_bytes;
     L.off_R = L.off_M + 2 * nch * kMChunkBytes;
-    L.off_bar = L.off_R + 2 * kRBytes;
+    L.off_bar = L.off_R + 2 * 2 * kRBytes;            // residual planes are double-buffered
     // slack so the second gradient tile's descriptor (4 chunks from chunk 4) stays inside the allocation
-    int end = L.off_bar + 256;
+    int end = L.off_bar + 512;
     const int reach = (kStages - 1) * L.stage_bytes + nch * kChunkBytes + 8 * kChunkBytes;
     L.total = end > reach ? end : reach;
     return L;
 }
 
+// TMEM columns: forward accumulators at 0: [X1 M1 | X1 M2 | X2 M1]; gradient buffer gb=0,1, tile mt=0,1 at
+// 96 + gb*192 + mt*96: [X1^T r1 | X1^T r2 | X2^T r1].  The second and third block of each carry 2^-11.
+constexpr int kFwdCols = 96;
+constexpr int kGradBase = kFwdCols;          // forward accumulators are single-buffered (drained at once)
+constexpr int kGradBuf = 2 * kFwdCols;       // one gradient buffer = two 128-feature tiles; double-buffered
+constexpr int kTmemAlloc = 512;
+
+template <int NLIN>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, TcKernelArgs a)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const TcSmem L = tc_smem_layout(a.nch);
-    unsigned char* sM = smem + L.off_M;
-    unsigned char* sR = smem + L.off_R;
+    unsigned char* sM = smem + L.off_M;               // per chunk: [M1 rows 0..31][M2 rows 0..31], 64 B rows
+    unsigned char* sR = smem + L.off_R;               // buffer b: [r1 plane][r2 plane]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* bar_full = bars;            // [2] TMA landed
-    uint64_t* bar_empty = bars + 2;       // [2] stage consumed by both MMAs
+    uint64_t* bar_empty = bars + 2;       // [2] X stage consumed by the gradient MMA
     uint64_t* bar_fwd_full = bars + 4;    // activation accumulators ready
-    uint64_t* bar_fwd_empty = bars + 5;   // ... drained by the epilogue
-    uint64_t* bar_r_ready = bars + 6;     // residual planes written
-    uint64_t* bar_bwd_full = bars + 7;    // gradient accumulators ready
-    uint64_t* bar_bwd_empty = bars + 8;   // ... drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* bar_fwd_empty = bars + 6;   // ... drained by the epilogue
+    uint64_t* bar_r_ready = bars + 8;     // [2] residual planes written
+    uint64_t* bar_r_free = bars + 10;     // [2] ... consumed by the gradient MMA
+    uint64_t* bar_g_full = bars + 12;     // [2] gradient accumulators of a tile complete
+    uint64_t* bar_g_empty = bars + 14;    // [2] ... folded into FP64
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    float* sPar = reinterpret_cast<float*>(bars + 18);   // [32] x (1/sm, bias)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nch = a.nch;
 
     if (threadIdx.x == 0) {
-        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
-        mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
-        mbar_init(bar_fwd_full, 1); mbar_init(bar_fwd_empty, 4);
-        mbar_init(bar_r_ready, 4);
-        mbar_init(bar_bwd_full, 1); mbar_init(bar_bwd_empty, 4);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_g_full[i], 1); mbar_init(&bar_g_empty[i], kEpiWarps);
+            mbar_init(&bar_r_ready[i], kEpiWarps); mbar_init(&bar_r_free[i], 1);
+        }
+        mbar_init(bar_fwd_full, 1); mbar_init(bar_fwd_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemCols) : "memory");
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemAlloc) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // weight planes -> shared memory, K-major rows of 64 B with the 64B swizzle applied by hand
+    // weight planes -> shared memory: K-major rows of 64 B, 64B swizzle applied by hand; within a
+    // chunk the 32 rows of M1 are followed by the 32 rows of M2 so one N=64 MMA sees [M1 | M2]
     {
-        const int per_plane = nch * kMChunkBytes;            // bytes
-        const int n16 = 2 * per_plane / 16;                  // 16-byte units in both planes
+        const int n16 = 2 * nch * kMChunkBytes / 16;         // 16-byte units over both planes
         for (int u = threadIdx.x; u < n16; u += kThreads) {
-            const int plane = u / (per_plane / 16);
-            const int v = u - plane * (per_plane / 16);
-            const int c = v / (kMChunkBytes / 16);           // chunk
-            const int w = v - c * (kMChunkBytes / 16);
+            const int c = u / (2 * kMChunkBytes / 16);       // chunk
+            const int v = u - c * (2 * kMChunkBytes / 16);
+            const int plane = v / (kMChunkBytes / 16);
+            const int w = v - plane * (kMChunkBytes / 16);
             const int row = w >> 2, q = w & 3;               // row n (64 B), 16-byte unit within the row
             const uint4 val = *reinterpret_cast<const uint4*>(
                 a.Mp + ((int64_t)(plane * kNcol + row) * a.Kp + c * kChunkF + q * 8));
-            *reinterpret_cast<uint4*>(sM + plane * per_plane + c * kMChunkBytes + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = val;
+            *reinterpret_cast<uint4*>(sM + c * 2 * kMChunkBytes + plane * kMChunkBytes + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = val;
         }
         fence_proxy_async();
+        if (threadIdx.x < kNcol) {
+            sPar[2 * threadIdx.x] = a.colpar[threadIdx.x];
+            sPar[2 * threadIdx.x + 1] = a.colpar[kNcol + threadIdx.x];
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -381,17 +469,20 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     const int64_t first = blockIdx.x, step = gridDim.x;
+    const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;   // tiles of this CTA
+    const int F = a.flush;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            int it = 0;
-            for (int64_t tile = first; tile < a.ntiles; tile += step, ++it) {
+            for (int it = 0; it < ntl; ++it) {
                 const int s = it & 1;
                 mbar_wait(&bar_empty[s], ((it >> 1) & 1) ^ 1);
+                if ((a.debug & 16) && it >= 2) { mbar_arrive(&bar_full[s]); continue; }
+                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
                 mbar_arrive_expect_tx(&bar_full[s], (uint32_t)L.stage_bytes);
                 unsigned char* st = smem + s * L.stage_bytes;
-                const int row0 = (int)(tile * kTileT);
+                const int row0 = (int)((first + (int64_t)it * step) * kTileT);
                 for (int c = 0; c < nch; ++c) {
                     tma_load_2d(st + c * kChunkBytes, &tmap1, &bar_full[s], c * kChunkF, row0);
                     tma_load_2d(st + (nch + c) * kChunkBytes, &tmap2, &bar_full[s], c * kChunkF, row0);
@@ -399,170 +490,238 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
+        // ================================ forward MMA issuer ==========================
         if (lane == 0) {
-            constexpr uint32_t idesc_fwd = umma_idesc(128, kNcol, 0, 0);     // A: X K-major,  B: M K-major
-            constexpr uint32_t idesc_bwd = umma_idesc(128, kNcol, 1, 1);     // A: X MN-major, B: r MN-major
-            const uint32_t sM1 = smem_u32(sM), sM2 = sM1 + nch * kMChunkBytes;
-            const uint32_t sR1 = smem_u32(sR), sR2 = sR1 + kRBytes;
-            const uint32_t t_da = tmem_base, t_db = tmem_base + 32;
-            int it = 0;
-            for (int64_t tile = first; tile < a.ntiles; tile += step, ++it) {
+            constexpr uint32_t idesc_f64 = umma_idesc(128, 64, 0, 0);     // A: X K-major,  B: [M1|M2] K-major
+            constexpr uint32_t idesc_f32 = umma_idesc(128, 32, 0, 0);
+            const uint32_t sMb = smem_u32(sM);
+            const uint32_t t_f = tmem_base;
+            for (int it = 0; it < ntl; ++it) {
                 const int s = it & 1;
-                const uint32_t ph = it & 1;
                 const uint32_t sX1 = smem_u32(smem + s * L.stage_bytes), sX2 = sX1 + nch * kChunkBytes;
                 mbar_wait(&bar_full[s], (it >> 1) & 1);
-                mbar_wait(bar_fwd_empty, ph ^ 1);
+                mbar_wait(bar_fwd_empty, (it & 1) ^ 1);
+                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
                 tc_fence_after();
-                // ---- forward: act = X1 M1 (t_da) ; X2 M1 + X1 M2 (t_db, carries 2^-11)
-                for (int c = 0; c < nch; ++c) {
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t acc = (c | ks) ? 1u : 0u;
-                        const uint64_t dx1 = umma_desc(sX1 + c * kChunkBytes + ks * 32, 16, 512);
-                        const uint64_t dx2 = umma_desc(sX2 + c * kChunkBytes + ks * 32, 16, 512);
-                        const uint64_t dm1 = umma_desc(sM1 + c * kMChunkBytes + ks * 32, 16, 512);
-                        const uint64_t dm2 = umma_desc(sM2 + c * kMChunkBytes + ks * 32, 16, 512);
-                        umma_f16(t_da, dx1, dm1, idesc_fwd, acc);
-                        umma_f16(t_db, dx2, dm1, idesc_fwd, acc);
-                        umma_f16(t_db, dx1, dm2, idesc_fwd, 1u);
-                    }
+                uint64_t dx1 = umma_desc(sX1, 16, 512), dx2 = umma_desc(sX2, 16, 512), dm = umma_desc(sMb, 16, 512);
+                for (int c = 0; c < ((a.debug & 1) ? 0 : nch); ++c) {
+                    umma_f16(t_f, dx1, dm, idesc_f64, c ? 1u : 0u);            // X1 [M1 | M2], features 0..15 of the chunk
+                    umma_f16(t_f + 64, dx2, dm, idesc_f32, c ? 1u : 0u);       // X2 M1
+                    umma_f16(t_f, dx1 + 2, dm + 2, idesc_f64, 1u);             // features 16..31 (+32 bytes)
+                    umma_f16(t_f + 64, dx2 + 2, dm + 2, idesc_f32, 1u);
+                    dx1 += kChunkBytes >> 4; dx2 += kChunkBytes >> 4; dm += (2 * kMChunkBytes) >> 4;
                 }
                 umma_commit(bar_fwd_full);
-                // ---- gradient: G = X1^T r1 (ga) ; X2^T r1 + X1^T r2 (gb), X tile reused from smem
-                mbar_wait(bar_r_ready, ph);
-                mbar_wait(bar_bwd_empty, ph ^ 1);
+                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 1] = clock64();
+            }
+        }
+    } else if (warp == 2) {
+        // ================================ gradient MMA issuer =========================
+        // Its own warp, so a forward MMA waiting for data never delays a gradient MMA (or the reverse).
+        // The TMEM accumulators do not keep full FP32 precision over long sums (measured: the gradient
+        // error grows linearly with the number of accumulated tiles), so every tile starts from zero
+        // in one of two accumulator buffers and the epilogue folds it into FP64.
+        if (lane == 0) {
+            constexpr uint32_t idesc_b64 = umma_idesc(128, 64, 1, 1);     // A: X MN-major, B: [r1|r2] MN-major
+            constexpr uint32_t idesc_b32 = umma_idesc(128, 32, 1, 1);
+            for (int j = 0; j < ntl; ++j) {
+                const int s = j & 1, b = j & 1, gb = j & 1;
+                const uint32_t sX1 = smem_u32(smem + s * L.stage_bytes), sX2 = sX1 + nch * kChunkBytes;
+                const uint32_t sR1 = smem_u32(sR + b * 2 * kRBytes);
+                mbar_wait(&bar_r_ready[b], (j >> 1) & 1);
+                mbar_wait(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
+                if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
                 tc_fence_after();
-                for (int mt = 0; mt < a.nmt; ++mt) {
-                    const uint32_t t_ga = tmem_base + 64 + mt * 64, t_gb = t_ga + 32;
+                // descriptors differ between k steps only in the start address: add (bytes >> 4)
+                const uint64_t dr0 = umma_desc(sR1, kRBytes, 512);                // LBO steps r1 -> r2
+                for (int mt = 0; mt < ((a.debug & 2) ? 0 : a.nmt); ++mt) {
+                    const uint32_t t_g = tmem_base + kGradBase + gb * kGradBuf + mt * kFwdCols;
+                    const uint64_t dx1_0 = umma_desc(sX1 + mt * 4 * kChunkBytes, kChunkBytes, 512);   // 4 chunks per tile
+                    const uint64_t dx2_0 = umma_desc(sX2 + mt * 4 * kChunkBytes, kChunkBytes, 512);
 #pragma unroll
-                    for (int ks = 0; ks < kTileT / 16; ++ks) {
+                    for (int ks = 0; ks < kTileT / 16; ++ks) {                    // 16 bins per step
                         const uint32_t acc = ks ? 1u : 0u;
-                        const uint32_t xo = mt * 4 * kChunkBytes + ks * 1024;    // 4 chunks per tile, 16 bins per step
-                        const uint64_t dx1 = umma_desc(sX1 + xo, kChunkBytes, 512);
-                        const uint64_t dx2 = umma_desc(sX2 + xo, kChunkBytes, 512);
-                        const uint64_t dr1 = umma_desc(sR1 + ks * 1024, kRBytes, 512);
-                        const uint64_t dr2 = umma_desc(sR2 + ks * 1024, kRBytes, 512);
-                        umma_f16(t_ga, dx1, dr1, idesc_bwd, acc);
-                        umma_f16(t_gb, dx2, dr1, idesc_bwd, acc);
-                        umma_f16(t_gb, dx1, dr2, idesc_bwd, 1u);
+                        const uint64_t off = (uint64_t)(ks * 1024 >> 4);
+                        umma_f16(t_g, dx1_0 + off, dr0 + off, idesc_b64, acc);       // X1^T [r1 | r2]
+                        umma_f16(t_g + 64, dx2_0 + off, dr0 + off, idesc_b32, acc);  // X2^T r1
                     }
                 }
-                umma_commit(bar_bwd_full);
                 umma_commit(&bar_empty[s]);
+                umma_commit(&bar_r_free[b]);
+                umma_commit(&bar_g_full[gb]);
+                if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 3] = clock64();
             }
         }
     } else {
         // ================================ epilogue warps ==============================
-        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        // kEpiWarps warps; warp w owns TMEM lane quarter q = w & 3 (hardware restriction) and the
+        // column group cg of kColsPerWarp postsynaptic columns.
+        const int q = warp & 3;
+        const int cg = (warp - kFirstEpiWarp) >> 2;
+        const int c0 = cg * kColsPerWarp;                // first column of this warp
         const int row = q * 32 + lane;                   // row of the tile == TMEM lane
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-        const float inv_sm = a.colpar[lane], bias_l = a.colpar[kNcol + lane];   // column `lane`
-        double gacc[2][kNcol];
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+        const float2* cpar = reinterpret_cast<const float2*>(sPar);     // (1/sm, bias) per column
+        double* gp = a.part + (int64_t)blockIdx.x * ((int64_t)a.nmt * 128 * kNcol + 2 * kNcol);
+        const int NBreal = a.nfeat;
+        double gacc[kColsPerWarp], gacc1[kColsPerWarp];  // gradient tiles 0 / 1 (features 0..127 / 128..): FP64 in registers
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int c = 0; c < kNcol; ++c) gacc[mt][c] = 0.0;
-        double ll_acc = 0.0, gb_acc = 0.0;               // lane n accumulates column n
-
-        int it = 0;
-        for (int64_t tile = first; tile < a.ntiles; tile += step, ++it) {
-            const uint32_t ph = it & 1;
-            const int64_t t = tile * kTileT + row;
-            const bool live = t < a.T;
-            // spikes of this bin for the requested columns (27 contiguous bytes at C2)
-            uint32_t sp[kNcol / 4];
-#pragma unroll
-            for (int i = 0; i < kNcol / 4; ++i) sp[i] = 0;
-            if (live) {
-                const uint8_t* srow = a.S + ((int64_t)a.halo + t) * a.N + a.n_lo;
-#pragma unroll
-                for (int c = 0; c < kNcol; ++c)
-                    if (c < a.ncols) sp[c >> 2] |= (uint32_t)srow[c] << ((c & 3) * 8);
-            }
-            mbar_wait(bar_fwd_full, ph);
+        for (int c = 0; c < kColsPerWarp; ++c) { gacc[c] = 0.0; gacc1[c] = 0.0; }
+        // fold tile j's TMEM gradient block into FP64; tile 1 (features >= 128, at most 32 real rows on this
+        // path) is read only by the warps that own real rows
+        auto fold_gradient = [&](int j) {
+            float g0[kColsPerWarp], g1[kColsPerWarp], g2[kColsPerWarp];
+            const int gb = j & 1;
+            const uint32_t t_g = t_lane + kGradBase + gb * kGradBuf;
+            mbar_wait(&bar_g_full[gb], (j >> 1) & 1);
             tc_fence_after();
-            float da[kNcol], db[kNcol];
-            tmem_ld32(t_lane + 0, da);
-            tmem_ld32(t_lane + 32, db);
+            if (!(a.debug & 8)) {
+                tmem_ld<kColsPerWarp>(t_g + 0, g0);
+                tmem_ld<kColsPerWarp>(t_g + 32, g1);
+                tmem_ld<kColsPerWarp>(t_g + 64, g2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) gacc[c] += (double)fmaf(g1[c] + g2[c], 1.0f / kLoScale, g0[c]);
+                if (a.nmt > 1 && 128 + q * 32 < NBreal) {                    // warp-uniform
+                    tmem_ld<kColsPerWarp>(t_g + kFwdCols + 0, g0);
+                    tmem_ld<kColsPerWarp>(t_g + kFwdCols + 32, g1);
+                    tmem_ld<kColsPerWarp>(t_g + kFwdCols + 64, g2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < kColsPerWarp; ++c) gacc1[c] += (double)fmaf(g1[c] + g2[c], 1.0f / kLoScale, g0[c]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_g_empty[gb]);
+        };
+        double ll_acc = 0.0, gb_acc = 0.0;               // lane l accumulates column c0 + (l % kColsPerWarp)
+        const int sw = (row >> 1) & 3;
+
+        // per-thread FP32 partial column sums, folded (butterfly + FP64) at the flush points
+        float pll[kColsPerWarp], pgb[kColsPerWarp];
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; ++c) { pll[c] = 0.f; pgb[c] = 0.f; }
+
+        // spikes of one bin for this warp's columns (kColsPerWarp bytes packed in registers); the next
+        // tile's are fetched a tile ahead.  Aligned column ranges use one vector load from the padded copy.
+        constexpr int kSpWords = kColsPerWarp / 4;
+        uint32_t sb[kSpWords], sb_next[kSpWords];
+        const bool vec_ok = ((a.n_lo + c0) % kColsPerWarp) == 0;
+        auto load_spikes = [&](int it, uint32_t (&dst)[kSpWords]) {
+            const int64_t t = (first + (int64_t)it * step) * kTileT + row;
+            const bool ok = it < ntl && t < a.T;
+#pragma unroll
+            for (int i = 0; i < kSpWords; ++i) dst[i] = 0;
+            if (!ok) return;
+            if (vec_ok) {
+                const uint8_t* src = a.Sp + t * a.Np + a.n_lo + c0;
+                if constexpr (kSpWords == 2) { const uint2 v = *reinterpret_cast<const uint2*>(src); dst[0] = v.x; dst[1] = v.y; }
+                else if constexpr (kSpWords == 4) { const uint4 v = *reinterpret_cast<const uint4*>(src); dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w; }
+                else {
+#pragma unroll
+                    for (int i = 0; i < kSpWords; ++i) dst[i] = reinterpret_cast<const uint32_t*>(src)[i];
+                }
+            } else {
+                const uint8_t* srow = a.Sp + t * a.Np + a.n_lo + c0;
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) dst[c >> 2] |= (uint32_t)srow[c] << ((c & 3) * 8);
+            }
+        };
+        load_spikes(0, sb_next);
+
+        for (int it = 0; it < ntl; ++it) {
+            const int b = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int64_t t = (first + (int64_t)it * step) * kTileT + row;
+            const float lv = t < a.T ? 1.0f : 0.0f;
+#pragma unroll
+            for (int i = 0; i < kSpWords; ++i) sb[i] = sb_next[i];
+            load_spikes(it + 1, sb_next);
+            const bool tr = a.trace && blockIdx.x == 0 && warp == kFirstEpiWarp && lane == 0 && it < 32;
+            if (tr) a.trace[(2 * 32 + it) * 4 + 0] = clock64();
+            mbar_wait(bar_fwd_full, it & 1);
+            if (tr) a.trace[(2 * 32 + it) * 4 + 1] = clock64();
+            tc_fence_after();
+            float d0[kColsPerWarp], d1[kColsPerWarp], d2[kColsPerWarp];
+            tmem_ld<kColsPerWarp>(t_lane + 0, d0);
+            tmem_ld<kColsPerWarp>(t_lane + 32, d1);
+            tmem_ld<kColsPerWarp>(t_lane + 64, d2);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_fwd_empty);
 
-            // act, Poisson term, residual; residual planes back to smem (MN-major, 64B swizzle)
-            uint32_t r1p[kNcol / 2], r2p[kNcol / 2];
+            // act, Poisson term, residual (padded columns have M = 0, bias = 0 and are ignored later)
 #pragma unroll
-            for (int c = 0; c < kNcol; ++c) {
-                const float ism = __shfl_sync(0xffffffffu, inv_sm, c);
-                const float bc = __shfl_sync(0xffffffffu, bias_l, c);
+            for (int c = 0; c < kColsPerWarp; ++c) {
+                const float2 cp = cpar[c0 + c];
                 float term = 0.f, r = 0.f;
-                if (live && c < a.ncols) {
-                    const float x = fmaf(fmaf(db[c], 1.0f / kLoScale, da[c]), ism, bc);
-                    const float s = (float)((sp[c >> 2] >> ((c & 3) * 8)) & 0xffu);
-                    poisson_terms(x, s, a.dt, a.nlin, term, r);
+                if (c0 + c < a.ncols) {                  // warp-uniform: padded columns cost nothing
+                    const float x = fmaf(fmaf(d1[c] + d2[c], 1.0f / kLoScale, d0[c]), cp.x, cp.y);
+                    poisson_terms<NLIN>(x, (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu), a.dt, term, r);
+                    r *= lv;                             // bins past the end of the recording contribute nothing
+                    pll[c] = fmaf(lv, term, pll[c]);
+                    pgb[c] += r;
                 }
-                da[c] = term;                            // reuse registers: da <- ll terms, db <- residuals
-                db[c] = r;
-                const float rs = r * kRScale;
-                const __half h1 = __float2half_rn(rs);
-                const __half h2 = __float2half_rn((rs - __half2float(h1)) * kLoScale);
-                const uint32_t u1 = __half_as_ushort(h1), u2 = __half_as_ushort(h2);
-                if (c & 1) { r1p[c >> 1] |= u1 << 16; r2p[c >> 1] |= u2 << 16; }
-                else       { r1p[c >> 1] = u1;        r2p[c >> 1] = u2; }
+                d1[c] = r;
             }
+            // residual planes back to smem as the gradient MMA's B operand (MN-major, 64B swizzle)
+            mbar_wait(&bar_r_free[b], ph ^ 1);
             {
-                unsigned char* d1 = sR + row * 64;
-                unsigned char* d2 = sR + kRBytes + row * 64;
-                const int sw = (row >> 1) & 3;
+                unsigned char* p1 = sR + b * 2 * kRBytes + row * 64;
+                unsigned char* p2 = p1 + kRBytes;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    *reinterpret_cast<uint4*>(d1 + ((u ^ sw) << 4)) = make_uint4(r1p[4 * u], r1p[4 * u + 1], r1p[4 * u + 2], r1p[4 * u + 3]);
-                    *reinterpret_cast<uint4*>(d2 + ((u ^ sw) << 4)) = make_uint4(r2p[4 * u], r2p[4 * u + 1], r2p[4 * u + 2], r2p[4 * u + 3]);
+                for (int u = 0; u < kColsPerWarp / 8; ++u) {
+                    uint32_t h1[4], h2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float ra = d1[8 * u + 2 * k] * kRScale, rb = d1[8 * u + 2 * k + 1] * kRScale;
+                        const __half2 hi = __floats2half2_rn(ra, rb);
+                        const float2 back = __half22float2(hi);
+                        const __half2 lo = __floats2half2_rn((ra - back.x) * kLoScale, (rb - back.y) * kLoScale);
+                        h1[k] = *reinterpret_cast<const uint32_t*>(&hi);
+                        h2[k] = *reinterpret_cast<const uint32_t*>(&lo);
+                    }
+                    const int unit = (c0 >> 3) + u;          // 16-byte unit (8 columns) within the 64-byte row
+                    *reinterpret_cast<uint4*>(p1 + ((unit ^ sw) << 4)) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                    *reinterpret_cast<uint4*>(p2 + ((unit ^ sw) << 4)) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
                 }
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_r_ready);
+            if (lane == 0) mbar_arrive(&bar_r_ready[b]);
+            if (tr) a.trace[(2 * 32 + it) * 4 + 2] = clock64();
+            if (a.trace && blockIdx.x == 0 && lane == 0 && it < 32) a.trace[384 + warp * 32 + it] = clock64();
 
-            // column sums of the ll terms and residuals (bias gradient) while the gradient MMA runs
-            ll_acc += (double)warp_column_sums(da, lane);
-            gb_acc += (double)warp_column_sums(db, lane);
-
-            // fold this tile's gradient block into FP64
-            mbar_wait(bar_bwd_full, ph);
-            tc_fence_after();
+            // column sums -> FP64 every F tiles; the previous tile's gradient block -> FP64 (its MMA ran
+            // while this tile's epilogue was busy)
+            if (((it + 1) % F) == 0 || it == ntl - 1) {
+                ll_acc += (double)warp_column_sums<kColsPerWarp>(pll, lane);
+                gb_acc += (double)warp_column_sums<kColsPerWarp>(pgb, lane);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                if (mt < a.nmt) {
-                    tmem_ld32(t_lane + 64 + mt * 64, da);
-                    tmem_ld32(t_lane + 64 + mt * 64 + 32, db);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < kNcol; ++c)
-                        gacc[mt][c] += (double)da[c] + (double)db[c] * (1.0 / kLoScale);
-                }
+                for (int c = 0; c < kColsPerWarp; ++c) { pll[c] = 0.f; pgb[c] = 0.f; }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_bwd_empty);
+            if (it >= 1) fold_gradient(it - 1);
+            if (tr) a.trace[(2 * 32 + it) * 4 + 3] = clock64();
         }
 
-        // ---- per-CTA partials: G rows (feature = mt*128 + row), then ll / g_bias
-        double* gp = a.part + (int64_t)blockIdx.x * ((int64_t)a.nmt * 128 * kNcol + 2 * kNcol);
+        if (ntl > 0) fold_gradient(ntl - 1);
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            if (mt < a.nmt) {
+        for (int c = 0; c < kColsPerWarp; ++c) gp[(int64_t)row * kNcol + c0 + c] = gacc[c];
+        if (a.nmt > 1) {
 #pragma unroll
-                for (int c = 0; c < kNcol; ++c) gp[((int64_t)mt * 128 + row) * kNcol + c] = gacc[mt][c];
-            }
+            for (int c = 0; c < kColsPerWarp; ++c) gp[((int64_t)128 + row) * kNcol + c0 + c] = gacc1[c];
         }
-        double* sred = reinterpret_cast<double*>(sR);    // residual planes are idle now: [4][2][32]
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // all epilogue warps past their last MMA wait
-        sred[(q * 2 + 0) * kNcol + lane] = ll_acc;
-        sred[(q * 2 + 1) * kNcol + lane] = gb_acc;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q == 0) {
+        // ---- per-CTA ll / g_bias partials
+        double* sred = reinterpret_cast<double*>(sR);    // residual planes are idle now: [4 quarters][2][32]
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // every epilogue warp is past its last wait
+        if (lane < kColsPerWarp) {
+            sred[(q * 2 + 0) * kNcol + c0 + lane] = ll_acc;
+            sred[(q * 2 + 1) * kNcol + c0 + lane] = gb_acc;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (warp == kFirstEpiWarp) {
             double l = 0.0, g = 0.0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) { l += sred[(k * 2 + 0) * kNcol + lane]; g += sred[(k * 2 + 1) * kNcol + lane]; }
@@ -575,35 +734,43 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemCols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemAlloc) : "memory");
     }
 }
 
-// Sum the per-CTA partials in CTA order and undo the scales.
+// Sum the per-CTA partials in a fixed order and undo the scales.  One block per feature row j
+// (plus one for ll / g_bias): 32 columns x 8 slices of the CTA range, combined slice 0..7.
 __global__ void __launch_bounds__(256)
 tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int B, int n_lo, int ncols,
                 const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
                 double* __restrict__ out_ll, double* __restrict__ out_gb, double* __restrict__ out_gw)
 {
+    __shared__ double sh[8][2 * kNcol];
     const int64_t NB = (int64_t)N * B;
     const int64_t per_cta = (int64_t)nmt * 128 * kNcol + 2 * kNcol;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (out_gw && idx < NB * ncols) {
-        const int nl = (int)(idx / NB);
-        const int64_t j = idx - (int64_t)nl * NB;
-        double s = 0.0;
-        for (int c = 0; c < nctas; ++c) s += part[c * per_cta + j * kNcol + nl];
+    const int nl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const bool tail = blockIdx.x == NB;                      // the ll / g_bias block
+    const int64_t off = tail ? (int64_t)nmt * 128 * kNcol : (int64_t)blockIdx.x * kNcol;
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = slice; c < nctas; c += 8) {
+        s0 += part[c * per_cta + off + nl];
+        if (tail) s1 += part[c * per_cta + off + kNcol + nl];
+    }
+    sh[slice][nl] = s0;
+    sh[slice][kNcol + nl] = s1;
+    __syncthreads();
+    if (slice != 0 || nl >= ncols) return;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { s0 += sh[k][nl]; s1 += sh[k][kNcol + nl]; }
+    if (tail) {
+        out_ll[nl] = s0;
+        if (out_gb) out_gb[nl] = s1;                         // residual column sums are carried unscaled
+    } else if (out_gw) {
+        const int64_t j = blockIdx.x;
         const int n = n_lo + nl, pre = (int)(j / B);
         const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
         const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
-        out_gw[idx] = (a * ww) * s / ((double)sx[j] * (double)kRScale);
-    }
-    if (idx < 2 * ncols) {
-        const int which = (int)(idx / ncols), nl = (int)(idx - (int64_t)which * ncols);
-        double s = 0.0;
-        for (int c = 0; c < nctas; ++c) s += part[c * per_cta + (int64_t)nmt * 128 * kNcol + which * kNcol + nl];
-        if (which == 0) out_ll[nl] = s;
-        else if (out_gb) out_gb[nl] = s;               // residual column sums are carried unscaled
+        out_gw[(int64_t)nl * NB + j] = (a * ww) * s0 / ((double)sx[j] * (double)kRScale);
     }
 }
 
@@ -656,6 +823,10 @@ static int ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     PYGLM_CUDA(cudaMalloc(&ws.colmax, NB * sizeof(unsigned)));
     PYGLM_CUDA(cudaMalloc(&ws.Mp, (size_t)2 * kNcol * kMaxChunks * kChunkF * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.colpar, 2 * kNcol * sizeof(float)));
+    ws.Np = (int)round_up(a.N, 32) + 32;          // slack: a column group may start anywhere below N
+    PYGLM_CUDA(cudaMalloc(&ws.Sp, (size_t)a.T * ws.Np));
+    PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)a.T * ws.Np, stream));
+    PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, a.S + (size_t)a.halo * a.N, a.N, a.N, a.T, cudaMemcpyDeviceToDevice, stream));
     PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, NB * sizeof(unsigned), stream));
     dim3 gmax((unsigned)std::min<int64_t>(a.T, 148 * 16), (unsigned)ceil_div(NB, 128));
     tc_colmax_kernel<<<gmax, 128, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.colmax);
@@ -694,11 +865,8 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     }
     const TcSmem L = tc_smem_layout(nch);
     const int smem_bytes = L.total + 1024;
-    static int smem_set = 0;
-    if (smem_set < smem_bytes) {
-        PYGLM_CUDA(cudaFuncSetAttribute(tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        smem_set = smem_bytes;
-    }
+    auto kern = a.nlin == PYGLM_B200_NLIN_EXP ? tc_fused_kernel<PYGLM_B200_NLIN_EXP> : tc_fused_kernel<PYGLM_B200_NLIN_SOFTPLUS>;
+    PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const CUtensorMap* maps = static_cast<const CUtensorMap*>(ws.tmaps);
     for (int c0 = 0; c0 < a.ncols; c0 += kNcol) {
         const int nc = std::min(kNcol, a.ncols - c0);
@@ -707,12 +875,38 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         PYGLM_CUDA(cudaGetLastError());
         TcKernelArgs k{};
         k.S = a.S; k.T = a.T; k.N = a.N; k.halo = a.halo; k.dt = (float)a.dt; k.nlin = a.nlin;
-        k.n_lo = n_lo; k.ncols = nc; k.nch = nch; k.nmt = nmt; k.ntiles = ntiles;
+        k.n_lo = n_lo; k.ncols = nc; k.nch = nch; k.nmt = nmt; k.ntiles = ntiles; k.nfeat = NB;
+        k.Sp = ws.Sp; k.Np = ws.Np;
         k.Mp = ws.Mp; k.Kp = Kp; k.colpar = ws.colpar; k.part = ws.part;
-        tc_fused_kernel<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], k);
+        { const char* dbg = getenv("PYGLM_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
+        { const char* fl = getenv("PYGLM_TC_FLUSH"); k.flush = fl ? std::max(1, atoi(fl)) : kFlushTiles; }
+        static long long* d_trace = nullptr;
+        const bool want_trace = getenv("PYGLM_TC_TRACE") != nullptr;
+        if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, (384 + 32 * 32) * sizeof(long long)));
+        k.trace = want_trace ? d_trace : nullptr;
+        kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], k);
         PYGLM_CUDA(cudaGetLastError());
-        const int64_t work = std::max<int64_t>((int64_t)NB * nc, 2 * nc);
-        tc_final_kernel<<<(unsigned)ceil_div(work, 256), 256, 0, stream>>>(
+        if (want_trace) {
+            static int dumped = 0;
+            if (dumped++ == 5) {
+                long long h[384 + 32 * 32];
+                PYGLM_CUDA(cudaStreamSynchronize(stream));
+                PYGLM_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+                const long long t0 = h[0];
+                fprintf(stderr, "tile  tma_issue | fwd_iss fwd_done_iss bwd_iss bwd_done_iss | epi_start fwd_full r_ready iter_end\n");
+                for (int i = 0; i < 24; ++i) {
+                    fprintf(stderr, "%3d %9lld | %9lld %9lld %9lld %9lld | %9lld %9lld %9lld %9lld\n", i, h[(0 * 32 + i) * 4] - t0,
+                            h[(32 + i) * 4 + 0] - t0, h[(32 + i) * 4 + 1] - t0, h[(32 + i) * 4 + 2] - t0, h[(32 + i) * 4 + 3] - t0,
+                            h[(64 + i) * 4 + 0] - t0, h[(64 + i) * 4 + 1] - t0, h[(64 + i) * 4 + 2] - t0, h[(64 + i) * 4 + 3] - t0);
+                }
+                for (int i = 10; i < 13; ++i) {
+                    fprintf(stderr, "r_ready arrivals tile %d:", i);
+                    for (int w = kFirstEpiWarp; w < kFirstEpiWarp + kEpiWarps; ++w) fprintf(stderr, " %lld", h[384 + w * 32 + i] - t0);
+                    fprintf(stderr, "\n");
+                }
+            }
+        }
+        tc_final_kernel<<<(unsigned)(NB + 1), 256, 0, stream>>>(
             ws.part, nctas, nmt, a.N, a.B, n_lo, nc, ws.sx, a.A, a.W,
             a.out_ll + c0, a.out_gb ? a.out_gb + c0 : nullptr, a.out_gw ? a.out_gw + (int64_t)c0 * NB : nullptr);
         PYGLM_CUDA(cudaGetLastError());

@@ -14,6 +14,8 @@ struct TcWorkspace {
     int64_t ldp = 0;              // row pitch of the planes in elements (multiple of 8)
     float* sx = nullptr;          // [NB] per-feature power-of-two scale
     unsigned* colmax = nullptr;   // [NB] scratch for the scale search
+    uint8_t* Sp = nullptr;        // [T][Np] zero-padded copy of the spikes (Np % 32 == 0)
+    int Np = 0;
     bool planes_ready = false;
     // per-call operands
     __half* Mp = nullptr;         // [2][32][Kp] split planes of the scaled weight matrix
