@@ -1,0 +1,61 @@
+"""world_size-2 gloo test of the N>1 host path: time-sharded partial sums all-reduced into the whole
+(the reduction bench.py --gpus N performs over NCCL) and neuron-sharded columns all-gathered."""
+import os
+import socket
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pyglm_oracle as orc
+from tests.helpers import make_problem, rel_err
+from theano_pyglm_b200.utils.parallel_util import allgather_columns, allreduce_sum, neuron_shard, time_shard
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = make_problem(3000, 6, 5, network=True, seed=21)
+        R = p['ibasis'].shape[0]
+        S = p['S'].astype(np.float64)
+        # ---- time sharding: filter with halo, local ll/grad (the oracle stands in for the GPU), all-reduce
+        lo, hi, halo = time_shard(p['T'], world, rank, R)
+        fS = orc.convolve_with_basis_direct(S[lo - halo:hi], p['ibasis'])[halo:]
+        ll, gb, gw = orc.population_ll_grad(fS, S[lo:hi], p['dt'], p['bias'], p['w'], p['A'], p['W'], orc.NLIN_SOFTPLUS)
+        ll, gb, gw = allreduce_sum([ll, gb, gw])
+        # ---- neuron sharding: each rank evaluates its own columns, all-gather
+        n_lo, n_hi = neuron_shard(p['N'], world, rank)
+        fS_full = orc.convolve_with_basis_direct(S, p['ibasis'])
+        ll_cols = np.array([orc.glm_ll(fS_full, S, p['dt'], n, p['bias'][n], p['w'][n], p['A'], p['W'], orc.NLIN_SOFTPLUS)
+                            for n in range(n_lo, n_hi)])
+        ll_gathered = allgather_columns(ll_cols, p['N'])
+        if rank == 0:
+            q.put((ll, gb, gw, ll_gathered))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_and_neuron_sharding_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    ll, gb, gw, ll_gathered = q.get()
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    p = make_problem(3000, 6, 5, network=True, seed=21)
+    S = p['S'].astype(np.float64)
+    fS = orc.convolve_with_basis_direct(S, p['ibasis'])
+    ll0, gb0, gw0 = orc.population_ll_grad(fS, S, p['dt'], p['bias'], p['w'], p['A'], p['W'], orc.NLIN_SOFTPLUS)
+    assert rel_err(ll, ll0) < 1e-12 and rel_err(gb, gb0) < 1e-10 and rel_err(gw, gw0) < 1e-10
+    assert rel_err(ll_gathered, ll0) < 1e-12
