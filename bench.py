@@ -116,8 +116,9 @@ def load_peaks():
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle port timed on the host cores (bench.py may execute oracle/ only here)
 # --------------------------------------------------------------------------------------
-def cpu_eval_time(inp, wl, T_sample, repeats, shape="gemm"):
-    """Seconds for one ll+grad eval of all N neurons on the first T_sample bins."""
+def cpu_prepare(inp, wl, T_sample, shape="gemm"):
+    """Returns a closure running one ll+grad eval of all N neurons on the first T_sample bins with the
+    float64 oracle.  The filtered spike train is prepared outside (it is resident data for both arms)."""
     from oracle import pyglm_oracle as orc
     N, B = wl["N"], wl["B"]
     S = inp["S"][:T_sample].astype(np.float64)
@@ -125,14 +126,22 @@ def cpu_eval_time(inp, wl, T_sample, repeats, shape="gemm"):
     w3 = inp["w"].reshape(N, N, B)
     A = np.ones((N, N), dtype=np.int8)
     W = np.ones((N, N))
+    if shape == "gemm":
+        return lambda: orc.population_ll_grad(fS, S, inp["dt"], inp["bias"], w3, A, W, orc.NLIN_SOFTPLUS)
+
+    def per_neuron():   # reference-shaped: python loop over neurons, T x N x B product materialised (impulse.py:58)
+        for n in range(N):
+            orc.glm_ll_grad(fS, S, inp["dt"], n, inp["bias"][n], w3[n], A, W, orc.NLIN_SOFTPLUS)
+    return per_neuron
+
+
+def cpu_eval_time(inp, wl, T_sample, repeats, shape="gemm"):
+    """Best-of-`repeats` seconds for one CPU eval on the first T_sample bins."""
+    fn = cpu_prepare(inp, wl, T_sample, shape)
     best = float("inf")
     for _ in range(repeats):
         t0 = time.perf_counter()
-        if shape == "gemm":
-            orc.population_ll_grad(fS, S, inp["dt"], inp["bias"], w3, A, W, orc.NLIN_SOFTPLUS)
-        else:   # reference-shaped: python loop over neurons, T x N x B product materialised (impulse.py:58)
-            for n in range(N):
-                orc.glm_ll_grad(fS, S, inp["dt"], n, inp["bias"][n], w3[n], A, W, orc.NLIN_SOFTPLUS)
+        fn()
         best = min(best, time.perf_counter() - t0)
     return best
 
@@ -145,11 +154,12 @@ def run_reference(args, wl):
     T_sample = min(wl["T"], 100_000)
     scale = wl["T"] / T_sample
     cores = os.cpu_count() or 1
+    fn = cpu_prepare(inp, wl, T_sample, "gemm")
     for _ in range(args.warmup):
-        cpu_eval_time(inp, wl, T_sample, 1)
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_eval_time(inp, wl, T_sample, 1)
+        fn()
     dt_step = (time.perf_counter() - t0) / args.steps
     value = 1.0 / (dt_step * scale)
     sample = ("first %d of %d bins per step, whole-population BLAS GEMM form of the float64 oracle "
@@ -271,6 +281,11 @@ def run_ours(args, wl):
         passes = info.get("x_passes", 2)
         alg_bytes = passes * x_bytes + T * N + 16 * N * NB
         achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+        traffic = None          # dram__bytes_read+write of the dominant kernel, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(info.get("kernel", ""), {}).get(args.workload)
         per_step = ms_dev / args.steps
         h2d = (N + N * NB) * 8
         d2h = N * (2 + NB) * 8
@@ -289,7 +304,7 @@ def run_ours(args, wl):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(info.get("launches_per_eval", 5)) * args.steps,
             "roofline": {"bound": info.get("bound", "hbm"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": info.get("traffic"),
+                         "frac": achieved / peak, "traffic": traffic, "kernel": info.get("kernel"),
                          "peak_source": peak_src, "kernel_ms": ms_kernel,
                          "algorithmic_bytes": alg_bytes},
         }

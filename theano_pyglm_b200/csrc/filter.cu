@@ -14,8 +14,9 @@
 
 namespace pyglm {
 
-constexpr int kFiltThreads = 256;
+constexpr int kFiltThreads = 512;
 constexpr int kFiltWarps = kFiltThreads / 32;
+constexpr int kFiltSub = 64;        // output bins staged through shared memory at a time
 
 struct FiltSmemLayout {
     size_t off_basis, off_out, off_ent, off_idx, off_s, total;
@@ -27,7 +28,7 @@ static FiltSmemLayout filt_layout(int R, int B, int tt, int pc) {
     const int rows = tt + R;
     size_t o = 0;
     L.off_basis = o; o += (size_t)R * B * sizeof(double);
-    L.off_out = o;   o += (size_t)tt * (pc * B + 1) * sizeof(XT);
+    L.off_out = o;   o += (size_t)kFiltSub * (pc * B + 1) * sizeof(XT);
     o = (o + 7) & ~(size_t)7;
     L.off_ent = o;   o += (size_t)rows * pc * sizeof(uint32_t);
     L.off_idx = o;   o += (size_t)(rows + 1) * pc * sizeof(uint16_t);
@@ -44,7 +45,7 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double*   sB   = reinterpret_cast<double*>(smem + L.off_basis);   // [R][B]
-    XT*       sOut = reinterpret_cast<XT*>(smem + L.off_out);         // [tt][pc*B+1]
+    XT*       sOut = reinterpret_cast<XT*>(smem + L.off_out);         // [kFiltSub][pc*B+1]
     uint32_t* sEnt = reinterpret_cast<uint32_t*>(smem + L.off_ent);   // [rows][pc]  (row<<8 | count)
     uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.off_idx);   // [rows+1][pc] #spikes in tile rows [0,i)
     uint8_t*  sS   = smem + L.off_s;                                  // [rows][pc+4]
@@ -56,15 +57,26 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
     const int sstride = pc + 4;
     const int ostride = pc * B + 1;
 
-    // ---- stage the spike tile (tile row i <-> S row halo + t0 - R + i) and the basis
+    // ---- stage the spike tile (tile row i <-> S row halo + t0 - R + i) and the basis.
+    // One warp per tile row, lanes across columns, eight rows in flight per warp.
     const int64_t g0 = (int64_t)halo + t0 - R;
     const int64_t gmax = (int64_t)halo + T;
-    for (int e = tid; e < rows * pc; e += kFiltThreads) {
-        const int i = e / pc, c = e - i * pc;
-        const int64_t g = g0 + i;
-        uint8_t v = 0;
-        if (g >= 0 && g < gmax && c0 + c < N) v = S[g * N + c0 + c];
-        sS[i * sstride + c] = v;
+    for (int c = lane; c < pc; c += 32) {
+        const bool col_ok = c0 + c < N;
+        for (int i = warp; i < rows; i += 8 * kFiltWarps) {
+            uint8_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int ii = i + u * kFiltWarps;
+                const int64_t g = g0 + ii;
+                v[u] = (col_ok && ii < rows && g >= 0 && g < gmax) ? S[g * N + c0 + c] : (uint8_t)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int ii = i + u * kFiltWarps;
+                if (ii < rows) sS[ii * sstride + c] = v[u];
+            }
+        }
     }
     for (int e = tid; e < R * B; e += kFiltThreads) sB[e] = ibasis[e];
     __syncthreads();
@@ -85,42 +97,46 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
     }
     __syncthreads();
 
-    // ---- gather: a warp task = 32 consecutive output bins of one column
-    const int ngroups = tt / 32;
-    for (int task = warp; task < ngroups * pc; task += kFiltWarps) {
-        const int tg = task / pc, c = task - tg * pc;
-        const int tl = tg * 32 + lane;          // output bin within the tile
-        const int i = tl + R;                   // its tile row; window = tile rows [tl, tl+R-1]
-        const int e0 = sIdx[(tg * 32) * pc + c];
-        const int e1 = sIdx[(tg * 32 + 31 + R) * pc + c];
-        double acc[BMAX];
-#pragma unroll
-        for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
-        for (int e = e0; e < e1; ++e) {
-            const uint32_t ent = sEnt[e * pc + c];        // warp-uniform broadcast
-            const int k = i - (int)(ent >> 8);            // lag
-            if (k >= 1 && k <= R) {
-                const double cnt = (double)(ent & 0xffu);
-                const double* row = sB + (size_t)(k - 1) * B;
-#pragma unroll
-                for (int b = 0; b < BMAX; ++b)
-                    if (b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(cnt, row[b]));
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < BMAX; ++b)
-            if (b < B) sOut[tl * ostride + c * B + b] = (XT)acc[b];
-    }
-    __syncthreads();
-
-    // ---- coalesced copy-out of the valid part of the tile
     const int ncol = min(pc, N - c0);
     const int width = ncol * B;
-    const int nrow = (int)min((int64_t)tt, T - t0);
-    XT* dst = X + t0 * ldx + (int64_t)c0 * B;
-    for (int e = tid; e < nrow * width; e += kFiltThreads) {
-        const int tl = e / width, j = e - tl * width;
-        dst[(int64_t)tl * ldx + j] = sOut[tl * ostride + j];
+    for (int sub = 0; sub < tt; sub += kFiltSub) {
+        if (t0 + sub >= T) break;
+        // ---- gather: a warp task = 32 consecutive output bins of one column
+        for (int task = warp; task < (kFiltSub / 32) * ncol; task += kFiltWarps) {
+            const int tg = task / ncol, c = task - tg * ncol;
+            const int ts = tg * 32 + lane;          // output bin within the sub-tile
+            const int tl = sub + ts;                // ... within the tile
+            const int i = tl + R;                   // its tile row; window = tile rows [tl, tl+R-1]
+            const int e0 = sIdx[(sub + tg * 32) * pc + c];
+            const int e1 = sIdx[(sub + tg * 32 + 31 + R) * pc + c];
+            double acc[BMAX];
+#pragma unroll
+            for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
+            for (int e = e0; e < e1; ++e) {
+                const uint32_t ent = sEnt[e * pc + c];        // warp-uniform broadcast
+                const int k = i - (int)(ent >> 8);            // lag
+                if (k >= 1 && k <= R) {
+                    const double cnt = (double)(ent & 0xffu);
+                    const double* row = sB + (size_t)(k - 1) * B;
+#pragma unroll
+                    for (int b = 0; b < BMAX; ++b)
+                        if (b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(cnt, row[b]));
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < BMAX; ++b)
+                if (b < B) sOut[ts * ostride + c * B + b] = (XT)acc[b];
+        }
+        __syncthreads();
+        // ---- coalesced copy-out of the valid part of the sub-tile
+        const int nrow = (int)min((int64_t)kFiltSub, T - (t0 + sub));
+        XT* dst = X + (t0 + sub) * ldx + (int64_t)c0 * B;
+        for (int ts = warp; ts < nrow; ts += kFiltWarps) {
+            const XT* src = sOut + ts * ostride;
+            XT* drow = dst + (int64_t)ts * ldx;
+            for (int j = lane; j < width; j += 32) drow[j] = src[j];
+        }
+        __syncthreads();
     }
 }
 
@@ -128,8 +144,8 @@ template <typename XT, int BMAX>
 static int launch_filter_t(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
                            XT* dX, int64_t ldx, cudaStream_t stream)
 {
-    // pick the largest tile whose shared memory fits (<= 200 KB leaves room for 1 block/SM at worst)
-    const int cand[][2] = {{64, 32}, {32, 32}, {32, 16}, {32, 8}, {32, 4}};
+    // pick the largest tile whose shared memory fits (<= 200 KB: one resident block per SM at worst)
+    const int cand[][2] = {{256, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {64, 4}};
     int tt = 0, pc = 0;
     FiltSmemLayout L{};
     for (auto& c : cand) {

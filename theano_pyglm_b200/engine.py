@@ -196,9 +196,11 @@ class Dataset:
         """What a call with `path` runs on this dataset (used by bench.py's roofline bookkeeping)."""
         use = load_library().pyglm_b200_resolve_path(self._h, _PATHS.get(path, path))
         if use == PATH_TC:
-            return dict(name="tcgen05-3xtf32", dtype="tf32x3", x_passes=1, launches_per_eval=3, bound="hbm")
+            return dict(name="tcgen05-fused-f16split", dtype="f16x2-split/f32-acc/f64-sum", x_passes=1,
+                        launches_per_eval=3, bound="hbm", kernel="tc_fused_kernel")
         if use == PATH_FP64:
-            return dict(name="fp64-simt", dtype="f64", x_passes=2, launches_per_eval=5, bound="hbm")
+            return dict(name="fp64-simt", dtype="f64", x_passes=2, launches_per_eval=5, bound="hbm",
+                        kernel="simt_fwd_kernel+simt_bwd_kernel")
         raise EngineError("path %r unsupported for this dataset" % (path,))
 
     def firing_rate(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None):
