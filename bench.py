@@ -33,6 +33,9 @@ WORKLOADS = {
     "c1": dict(N=4, T=60_000, B=5, desc="standard_glm N=4 T=60s (C1)"),
     "c2": dict(N=27, T=1_000_000, B=5, desc="standard_glm N=27 T=1e6 bins B=5 R=200 (C2)"),
     "c3": dict(N=256, T=1_000_000, B=5, desc="network GLM N=256 T=1e6 bins B=5 (C3, ll+grad part)"),
+    # second headline metric: collapsed Gibbs over A/W, batched delta-ll (sparse_weighted_model)
+    "c3-gibbs": dict(N=256, T=1_000_000, B=5, gibbs=True, desc="network GLM N=256 T=1e6 bins: collapsed Gibbs over A/W (C3)"),
+    "gibbs-small": dict(N=32, T=200_000, B=5, gibbs=True, desc="network GLM N=32 T=2e5 bins: collapsed Gibbs over A/W (smoke size)"),
 }
 METRIC = "GLM ll+grad evals/sec"
 UNIT = "evals/s"
@@ -326,6 +329,140 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------------
+# Gibbs workload: edge-sweeps/sec (one sweep = N^2 edges x 11 delta-ll candidates, ARS excluded)
+# --------------------------------------------------------------------------------------
+def make_gibbs_inputs(wl, seed):
+    """Dirichlet impulses (beta rows sum to 1), normalised basis, ER graph with the
+    stabilised sparsity, Gaussian weights with a refractory diagonal, bias ~ N(20, 0.25^2), softplus."""
+    from theano_pyglm_b200.utils.basis import create_basis, interpolate_basis
+    N, T, B = wl["N"], wl["T"], wl["B"]
+    rng = np.random.default_rng(seed)
+    S = (rng.random((T, N)) < 0.02).astype(np.uint8)
+    prms = dict(type='cosine', n_eye=0, n_cos=B, a=1.0 / 120, b=0.5, orth=False, norm=True)
+    ib = interpolate_basis(create_basis(prms), 0.001, 0.2, True, "dirichlet")
+    g = rng.gamma(1.0, 1.0, size=(N, N, B))
+    w = (g / g.sum(axis=2, keepdims=True)).reshape(N, N * B)
+    rho = min(1.0, (0.7 + 0.2) ** 2 / N)
+    A = (rng.random((N, N)) < rho).astype(np.int8)
+    np.fill_diagonal(A, 1)
+    W = rng.standard_normal((N, N))
+    W[np.diag_indices(N)] = -0.2 + 0.5 * rng.standard_normal(N)
+    bias = 20.0 + 0.25 * rng.standard_normal(N)
+    return dict(S=S, ibasis=ib, bias=bias, w=w, A=A, W=W, dt=0.001, rho=rho)
+
+
+def run_gibbs(args, wl):
+    import torch
+    import theano_pyglm_b200 as pg
+    from scipy.special import logsumexp
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    N, T, B = wl["N"], wl["T"], wl["B"]
+    Q = 11
+    inp = make_gibbs_inputs(wl, 1234)
+    dev = torch.device("cuda", 0)
+    ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], x_dtype="f64", device=0)
+    ds.gibbs_begin(inp["bias"], inp["w"], inp["A"], inp["W"], nlin="explinear")
+    rng = np.random.default_rng(7)
+    orders = np.stack([rng.permutation(N) for _ in range(N)])          # shuffled presynaptic order per column
+    xs, ws = np.polynomial.hermite.hermgauss(10)
+    log_wgh = np.log(ws / np.sqrt(np.pi))
+    cols = np.arange(N, dtype=np.int32)
+
+    def candidates(pres):
+        diag = pres == cols
+        mu = np.where(diag, -0.2, 0.0)[:, None]
+        sig = np.where(diag, 0.5, 1.0)[:, None]
+        return np.concatenate([np.sqrt(2) * sig * xs[None, :] + mu, np.zeros((N, 1))], axis=1), mu[:, 0], sig[:, 0]
+
+    pA = np.where(np.eye(N, dtype=bool), 1.0 - 1e-8, inp["rho"])
+
+    def step_e2e(s):
+        """One lock-step of the sweep: every column resamples its s-th edge (host buffers in and out)."""
+        pres = orders[:, s % N].astype(np.int32)
+        cand, mu, sig = candidates(pres)
+        ll = ds.gibbs_delta_ll(cols, pres, cand)                        # (N, 11)
+        log_G = logsumexp(ll[:, :10] + log_wgh[None, :], axis=1)       # gibbs.py:1015-1022
+        lp_A = np.log(pA[pres, cols]) + log_G
+        lp_no = np.log1p(-pA[pres, cols]) + ll[:, 10]
+        p_no = np.exp(lp_no - np.logaddexp(lp_no, lp_A))
+        a_new = (rng.random(N) > p_no).astype(np.int8)                  # log_sum_exp.py:26-32
+        w_new = mu + sig * rng.standard_normal(N)                       # prior draw; ARS is not part of the metric
+        ds.gibbs_commit(cols, pres, a_new, w_new)
+
+    # device-timed: the batched delta-ll kernel alone, operands resident
+    d_cols = torch.from_numpy(cols).to(dev)
+    pres0 = orders[:, 0].astype(np.int32)
+    d_pres = torch.from_numpy(pres0).to(dev)
+    d_cand = torch.from_numpy(candidates(pres0)[0]).to(dev)
+    d_out = torch.empty((N, Q), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        ds.gibbs_delta_ll_dev(N, d_cols.data_ptr(), d_pres.data_ptr(), Q, d_cand.data_ptr(), d_out.data_ptr(),
+                              stream.cuda_stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    for s in range(2):
+        step_e2e(s)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step_e2e(2 + s)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
+
+    peak, peak_src = load_peaks()
+    alg_bytes = N * T * (8 + B * 8 + 1)          # per edge and bin: I_net f64 + X slice f64 + spike byte
+    achieved = alg_bytes / (ms_dev * 1e-3) / 1e9
+    line = {
+        "metric": "Gibbs edge-sweeps/sec", "value": 1.0 / (N * ms_dev * 1e-3), "unit": "sweeps/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "N": N, "T_bins": T, "B": B, "candidates_per_edge": Q,
+                   "step": "one lock-step = N edges (one per column) x 11 candidate weights; a sweep is N steps",
+                   "edges_per_s": N / (ms_dev * 1e-3), "l2": "inputs_exceed_l2"},
+        "clocks": clocks,
+        "e2e": {"value": 1.0 / (N * ms_e2e * 1e-3), "unit": "sweeps/s",
+                "h2d_bytes_per_step": N * (4 + 4 + Q * 8) + N * (4 + 4 + 1 + 8), "d2h_bytes_per_step": N * Q * 8,
+                "includes": "host decision rule (logsumexp, Bernoulli draw) and gibbs_commit"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "gibbs_delta_kernel", "peak_source": peak_src, "kernel_ms": ms_dev,
+                     "algorithmic_bytes": alg_bytes},
+    }
+    if not args.no_cpu:
+        from oracle import pyglm_oracle as orc
+        T_s = min(T, 100_000)
+        Ssub = inp["S"][:T_s].astype(np.float64)
+        fS_pre = orc.convolve_with_basis_direct(Ssub[:, :1], inp["ibasis"])          # one presynaptic column is enough
+        u = fS_pre[:, 0, :] @ inp["w"][0].reshape(N, B)[0]
+        I_other = 0.3 * u
+        cand = candidates(pres0)[0][0]
+        t0 = time.perf_counter()
+        for wq in cand:
+            orc.gibbs_glm_ll(inp["bias"][0], 0.0, I_other, u, wq, Ssub[:, 0], inp["dt"], orc.NLIN_SOFTPLUS)
+        t_edge = (time.perf_counter() - t0) * (T / T_s)
+        line["cpu_baseline"] = {"value": 1.0 / (t_edge * N * N), "unit": "sweeps/s", "cores": 1, "kind": "port",
+                                "sample": "11 delta-ll evaluations (gibbs.py:910-937 restated, numpy float64) for one "
+                                          "edge on the first %d of %d bins, scaled to N^2 edges" % (T_s, T)}
+    print(json.dumps(line), flush=True)
+    ds.gibbs_end()
+    ds.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,7 +474,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl.get("gibbs"):
+        run_gibbs(args, wl)
+    elif args.impl == "reference":
         run_reference(args, wl)
     else:
         run_ours(args, wl)

@@ -166,6 +166,11 @@ PYGLM_B200_API int pyglm_b200_gibbs_begin(pyglm_b200_dataset* ds,
 PYGLM_B200_API int pyglm_b200_gibbs_delta_ll(pyglm_b200_dataset* ds, int32_t M,
                               const int32_t* cols, const int32_t* pres,
                               int32_t Q, const double* w_cand, double* out_ll);
+/* same, device pointers for cols / pres / w_cand / out_ll, asynchronous on `stream`; the edge list is
+ * not validated (the caller guarantees distinct resident columns) */
+PYGLM_B200_API int pyglm_b200_gibbs_delta_ll_dev(pyglm_b200_dataset* ds, int32_t M,
+                              const int32_t* d_cols, const int32_t* d_pres,
+                              int32_t Q, const double* d_w_cand, double* d_out_ll, void* stream);
 PYGLM_B200_API int pyglm_b200_gibbs_commit(pyglm_b200_dataset* ds, int32_t M,
                             const int32_t* cols, const int32_t* pres,
                             const int8_t* a_new, const double* w_new);

@@ -55,7 +55,8 @@ struct pyglm_b200_dataset {
     cudaStream_t stream = nullptr;
 
     DevBuf<uint8_t> S, St;
-    DevBuf<unsigned char> X;
+    DevBuf<unsigned char> X, Xt;      // Xt: feature-major copy of X, built at the first gibbs_begin
+    bool xt_ready = false;
     DevBuf<double> ibasis;
 
     // parameter staging (host entry points) and workspaces
@@ -131,7 +132,7 @@ int pyglm_b200_dataset_destroy(pyglm_b200_dataset* ds)
     if (!ds) return PYGLM_B200_OK;
     cudaSetDevice(ds->device);
     if (ds->stream) { cudaStreamSynchronize(ds->stream); }
-    ds->S.release(); ds->St.release(); ds->X.release(); ds->ibasis.release();
+    ds->S.release(); ds->St.release(); ds->X.release(); ds->Xt.release(); ds->ibasis.release();
     ds->p_bias.release(); ds->p_w.release(); ds->p_W.release(); ds->p_A.release();
     ds->M.release(); ds->Weff.release(); ds->Rres.release(); ds->llp.release(); ds->gbp.release();
     ds->Gp.release(); ds->o_ll.release(); ds->o_gb.release(); ds->o_gw.release(); ds->lam.release();
@@ -190,6 +191,7 @@ int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
 int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
 {
     DS_GUARD(ds);
+    ds->xt_ready = false;
     return launch_filter(ds->S.p, ds->T, ds->N, ds->halo, ds->ibasis.p, ds->R, ds->B, ds->X.p, ds->ldx,
                          ds->x_dtype, (cudaStream_t)stream);
 }
@@ -354,7 +356,7 @@ int pyglm_b200_firing_rate(pyglm_b200_dataset* ds,
 static GibbsArgs gibbs_args(pyglm_b200_dataset* ds)
 {
     GibbsArgs g{};
-    g.X = ds->X.p; g.ldx = ds->ldx; g.x_dtype = ds->x_dtype;
+    g.X = ds->Xt.p; g.ldx = ds->ldx; g.x_dtype = ds->x_dtype;
     g.St = ds->St.p; g.T = ds->T; g.N = ds->N; g.B = ds->B;
     g.dt = ds->dt; g.nlin = ds->g_nlin; g.n_lo = ds->g_nlo; g.ncols = ds->g_ncols;
     g.bias = ds->g_bias.p; g.w = ds->g_w.p; g.A = ds->g_A.p; g.W = ds->g_W.p;
@@ -374,6 +376,13 @@ int pyglm_b200_gibbs_begin(pyglm_b200_dataset* ds,
     ds->gibbs_active = false;
     TRY(stage_params(ds, bias, w, A, W, ds->g_bias, ds->g_w, ds->g_A, ds->g_W, st));
     const int ncols = n_hi - n_lo;
+    if (!ds->xt_ready) {
+        const size_t esz = ds->x_dtype == PYGLM_B200_X_F32 ? 4 : 8;
+        const size_t NB = (size_t)ds->N * ds->B;
+        TRY(ds->Xt.ensure(NB * (ds->T ? ds->T : 1) * esz));
+        TRY(launch_transpose_X(ds->X.p, ds->T, (int64_t)NB, ds->ldx, ds->x_dtype, ds->Xt.p, st));
+        ds->xt_ready = true;
+    }
     TRY(ds->Inet.ensure((size_t)ncols * (ds->T ? ds->T : 1)));
     TRY(ds->o_ll.ensure(ncols));
     // I_net[:, n] = I_imp @ (A[:,n] * W[:,n])  (glm.py:39) via the FP64 forward contraction
@@ -422,6 +431,23 @@ int pyglm_b200_gibbs_delta_ll(pyglm_b200_dataset* ds, int32_t M, const int32_t* 
     PYGLM_CUDA(cudaMemcpyAsync(out_ll, ds->g_out.p, (size_t)M * Q * sizeof(double), cudaMemcpyDeviceToHost, st));
     PYGLM_CUDA(cudaStreamSynchronize(st));
     return PYGLM_B200_OK;
+}
+
+int pyglm_b200_gibbs_delta_ll_dev(pyglm_b200_dataset* ds, int32_t M, const int32_t* d_cols, const int32_t* d_pres,
+                                  int32_t Q, const double* d_w_cand, double* d_out_ll, void* stream)
+{
+    DS_GUARD(ds);
+    if (!ds->gibbs_active) { set_error("gibbs_delta_ll before gibbs_begin"); return PYGLM_B200_ESTATE; }
+    PYGLM_REQUIRE(M >= 0 && M <= 65535, "gibbs: batch size %d outside [0,65535]", M);
+    PYGLM_REQUIRE(Q >= 1 && Q <= kMaxCand, "gibbs_delta_ll: Q=%d outside [1,%d]", Q, kMaxCand);
+    if (M == 0) return PYGLM_B200_OK;
+    PYGLM_REQUIRE(d_cols && d_pres && d_w_cand && d_out_ll, "gibbs_delta_ll_dev: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ds->T == 0) { PYGLM_CUDA(cudaMemsetAsync(d_out_ll, 0, (size_t)M * Q * sizeof(double), st)); return PYGLM_B200_OK; }
+    GibbsArgs g = gibbs_args(ds);
+    TRY(ds->partial.ensure((size_t)M * g.nchunks * Q));
+    g.partial = ds->partial.p;
+    return launch_gibbs_delta(g, M, d_cols, d_pres, Q, d_w_cand, d_out_ll, st);
 }
 
 int pyglm_b200_gibbs_commit(pyglm_b200_dataset* ds, int32_t M, const int32_t* cols, const int32_t* pres,

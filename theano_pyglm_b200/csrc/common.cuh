@@ -72,7 +72,7 @@ int simt_choose_splits(int64_t T, int N, int B, int Np);
 int launch_simt_ll_grad(const SimtArgs& a, cudaStream_t stream);
 
 struct GibbsArgs {
-    const void* X; int64_t ldx; int x_dtype;
+    const void* X; int64_t ldx; int x_dtype;     // X here is the feature-major copy Xt[j][t]
     const uint8_t* St; int64_t T; int N; int B;
     double dt; int nlin;
     int n_lo, ncols;
@@ -84,6 +84,7 @@ struct GibbsArgs {
     int nchunks;
 };
 int gibbs_num_chunks(int64_t T);
+int launch_transpose_X(const void* X, int64_t T, int64_t NB, int64_t ldx, int x_dtype, void* Xt, cudaStream_t stream);
 int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const int32_t* d_pres, int Q,
                        const double* d_wcand, double* d_out, cudaStream_t stream);
 int launch_gibbs_commit(const GibbsArgs& g, int M, const int32_t* d_cols, const int32_t* d_pres,

@@ -22,13 +22,36 @@ constexpr int kGibbsChunk = 8192;     // bins per block
 
 int gibbs_num_chunks(int64_t T) { return (int)ceil_div(T, kGibbsChunk); }
 
-template <typename XT, int QMAX>
+// exp(-x) for x >= 16 to ~1e-7 relative: an FP32 exp of the rounded argument times the first-order
+// correction for the rounding.  It only feeds lam = x + log1p(e^-x), where it is worth < 1.2e-7, so the
+// error in lam is below one FP64 ulp.
+__device__ __forceinline__ double exp_neg_large(double x)
+{
+    const float hi = (float)x;
+    const double lo = x - (double)hi;
+    return (double)expf(-hi) * (1.0 - lo);
+}
+
+// log(1+e^x) in FP64 for any x (the derivative and log(lam) are not needed per bin here)
+__device__ __forceinline__ double softplus_f64(double x)
+{
+    const double e = exp(-fabs(x));
+    const double l1p = e < 1e-16 ? e : log1p(e);
+    return x > 0.0 ? x + l1p : l1p;
+}
+
+// Softplus fast path: when every candidate of every lane of the warp sits at x >= 16 (a population firing
+// at tens of Hz: bias ~ 20), lam = x + e - e^2/2 with e = e^-x needs no FP64 transcendental, and the
+// log(lam) of the Poisson term is needed only in the ~2% of bins that hold a spike.  Those bins are
+// handed to the whole warp: lane q evaluates candidate q, so one FP64 log serves all candidates.
+template <typename XT, int QMAX, int NLIN>
 __global__ void __launch_bounds__(kGibbsThreads)
 gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t* __restrict__ pres,
                    int Q, const double* __restrict__ wcand)
 {
     __shared__ double sW[kMaxBasis];
     __shared__ double sRed[QMAX][kGibbsThreads / 32];
+    __shared__ double sRedSp[kGibbsThreads / 32][32];
 
     const XT* __restrict__ X = static_cast<const XT*>(g.X);
     const int m = blockIdx.y;
@@ -43,35 +66,75 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     const double aw_old = (double)g.A[(int64_t)pre * g.N + col] * g.W[(int64_t)pre * g.N + col];
     const double bias = g.bias[col];
     double wq[QMAX], acc[QMAX];
+    double wmin = 0.0, wmax = 0.0;                       // range of the candidate weights (with 0 for safety)
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) {
         wq[q] = (q < Q) ? wcand[(int64_t)m * Q + q] : 0.0;
         acc[q] = 0.0;
+        wmin = fmin(wmin, wq[q]);
+        wmax = fmax(wmax, wq[q]);
     }
+    const double w_lane = (lane < Q) ? wcand[(int64_t)m * Q + lane] : 0.0;   // candidate `lane` (spike path)
+    double acc_sp = 0.0;
 
     const int64_t tbeg = (int64_t)blockIdx.x * kGibbsChunk;
     const int64_t tend = min(g.T, tbeg + kGibbsChunk);
     const double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
     const uint8_t* __restrict__ st = g.St + (int64_t)col * g.T;
-    const XT* __restrict__ xcol = X + (int64_t)pre * g.B;
+    const XT* __restrict__ xcol = X + (int64_t)pre * g.B * g.T;      // feature-major copy: Xt[j][t]
 
-    for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) {
-        const XT* xr = xcol + t * g.ldx;
-        double u = 0.0;
-        for (int b = 0; b < g.B; ++b) u += (double)xr[b] * sW[b];
-        const double base = inet[t] - aw_old * u;
-        const double s = (double)st[t];
+    for (int64_t t0 = tbeg; t0 < tend; t0 += kGibbsThreads) {        // warp-uniform trip count
+        const int64_t t = t0 + tid;
+        const bool live = t < tend;
+        double u = 0.0, base = 0.0, s = 0.0;
+        if (live) {
+            for (int b = 0; b < g.B; ++b) u += (double)xcol[(int64_t)b * g.T + t] * sW[b];
+            base = bias + (inet[t] - aw_old * u);
+            s = (double)st[t];
+        }
+        bool fast = false;
+        if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
+            const double xlow = base + fmin(wmin * u, wmax * u);     // smallest activation over the candidates
+            fast = __all_sync(0xffffffffu, !live || xlow >= 16.0);
+        }
+        if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
+            if (live) {
+                if (fast) {
 #pragma unroll
-        for (int q = 0; q < QMAX; ++q) {
-            if (q < Q) {
-                const double x = bias + (base + wq[q] * u);
-                double lam, dlam, loglam;
-                nlin_eval(x, g.nlin, lam, dlam, loglam);
-                acc[q] += -g.dt * lam + loglam * s;
+                    for (int q = 0; q < QMAX; ++q) {
+                        if (q < Q) {
+                            const double x = base + wq[q] * u;
+                            const double e = exp_neg_large(x);
+                            acc[q] -= g.dt * (x + e * (1.0 - 0.5 * e));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < QMAX; ++q)
+                        if (q < Q) acc[q] -= g.dt * softplus_f64(base + wq[q] * u);
+                }
+            }
+            // spike bins (~2%): one lane per candidate evaluates log(lam) for the whole warp
+            unsigned mask = __ballot_sync(0xffffffffu, live && s != 0.0);
+            while (mask) {
+                const int src = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const double bs = __shfl_sync(0xffffffffu, base, src);
+                const double us = __shfl_sync(0xffffffffu, u, src);
+                const double ss = __shfl_sync(0xffffffffu, s, src);
+                if (lane < Q) acc_sp += ss * log(softplus_f64(bs + w_lane * us));
+            }
+        } else if (live) {
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {
+                if (q < Q) {
+                    const double x = base + wq[q] * u;
+                    acc[q] += -g.dt * exp(x) + x * s;                // exp nonlinearity: log(lam) = x
+                }
             }
         }
     }
-    // block reduction, fixed order: lanes (xor tree), then warps 0..7
+    // block reduction, fixed order: lanes (xor tree), then warps 0..7; the spike sums live in lane q
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) {
         double v = acc[q];
@@ -79,11 +142,12 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) sRed[q][warp] = v;
     }
+    sRedSp[warp][lane] = acc_sp;
     __syncthreads();
     if (tid < Q) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < kGibbsThreads / 32; ++w) v += sRed[tid][w];
+        for (int w = 0; w < kGibbsThreads / 32; ++w) v += sRed[tid][w] + sRedSp[w][tid];
         g.partial[((int64_t)m * g.nchunks + blockIdx.x) * Q + tid] = v;
     }
 }
@@ -120,11 +184,10 @@ gibbs_commit_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t
     const int64_t tbeg = (int64_t)blockIdx.x * kGibbsChunk;
     const int64_t tend = min(g.T, tbeg + kGibbsChunk);
     double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
-    const XT* __restrict__ xcol = X + (int64_t)pre * g.B;
+    const XT* __restrict__ xcol = X + (int64_t)pre * g.B * g.T;
     for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) {
-        const XT* xr = xcol + t * g.ldx;
         double u = 0.0;
-        for (int b = 0; b < g.B; ++b) u += (double)xr[b] * sW[b];
+        for (int b = 0; b < g.B; ++b) u += (double)xcol[(int64_t)b * g.T + t] * sW[b];
         inet[t] += delta * u;
     }
 }
@@ -139,6 +202,38 @@ __global__ void gibbs_store_state_kernel(int8_t* A, double* W, int N, int M, con
     W[idx] = wnew[m];
 }
 
+// Xt[j][t] = X[t][j]: feature-major copy so that the B streams an edge reads are contiguous in time
+template <typename XT>
+__global__ void __launch_bounds__(256)
+transpose_X_kernel(const XT* __restrict__ X, int64_t T, int64_t NB, int64_t ldx, XT* __restrict__ Xt)
+{
+    __shared__ XT tile[32][33];
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int64_t j0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t t = t0 + r, j = j0 + tx;
+        tile[r][tx] = (t < T && j < NB) ? X[t * ldx + j] : (XT)0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t j = j0 + r, t = t0 + tx;
+        if (j < NB && t < T) Xt[j * T + t] = tile[tx][r];
+    }
+}
+
+int launch_transpose_X(const void* X, int64_t T, int64_t NB, int64_t ldx, int x_dtype, void* Xt, cudaStream_t stream)
+{
+    if (T <= 0) return PYGLM_B200_OK;
+    dim3 grid((unsigned)ceil_div(T, 32), (unsigned)ceil_div(NB, 32));
+    if (x_dtype == PYGLM_B200_X_F32)
+        transpose_X_kernel<float><<<grid, 256, 0, stream>>>((const float*)X, T, NB, ldx, (float*)Xt);
+    else
+        transpose_X_kernel<double><<<grid, 256, 0, stream>>>((const double*)X, T, NB, ldx, (double*)Xt);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
 int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const int32_t* d_pres, int Q,
                        const double* d_wcand, double* d_out, cudaStream_t stream)
 {
@@ -149,19 +244,19 @@ int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const i
     }
     dim3 grid((unsigned)g.nchunks, (unsigned)M);
     const bool f32 = g.x_dtype == PYGLM_B200_X_F32;
-    if (Q <= 1) {
-        if (f32) gibbs_delta_kernel<float, 1><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-        else     gibbs_delta_kernel<double, 1><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-    } else if (Q <= 4) {
-        if (f32) gibbs_delta_kernel<float, 4><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-        else     gibbs_delta_kernel<double, 4><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-    } else if (Q <= 11) {
-        if (f32) gibbs_delta_kernel<float, 11><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-        else     gibbs_delta_kernel<double, 11><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-    } else {
-        if (f32) gibbs_delta_kernel<float, 16><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-        else     gibbs_delta_kernel<double, 16><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);
-    }
+    const bool sp = g.nlin == PYGLM_B200_NLIN_SOFTPLUS;
+#define PYGLM_GIBBS_LAUNCH(QM)                                                                                         \
+    do {                                                                                                               \
+        if (f32 && sp)       gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_SOFTPLUS><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
+        else if (f32)        gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_EXP><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);      \
+        else if (sp)         gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_SOFTPLUS><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
+        else                 gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_EXP><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);     \
+    } while (0)
+    if (Q <= 1) PYGLM_GIBBS_LAUNCH(1);
+    else if (Q <= 4) PYGLM_GIBBS_LAUNCH(4);
+    else if (Q <= 11) PYGLM_GIBBS_LAUNCH(11);
+    else PYGLM_GIBBS_LAUNCH(16);
+#undef PYGLM_GIBBS_LAUNCH
     PYGLM_CUDA(cudaGetLastError());
     gibbs_reduce_kernel<<<(unsigned)ceil_div((int64_t)M * Q, 128), 128, 0, stream>>>(g.partial, M, g.nchunks, Q, d_out);
     PYGLM_CUDA(cudaGetLastError());

@@ -25,7 +25,7 @@ EXPORTS = [
     "pyglm_b200_dataset_get_fS", "pyglm_b200_dataset_device_X", "pyglm_b200_dataset_device_S",
     "pyglm_b200_dataset_refilter",
     "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_firing_rate",
-    "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_commit",
+    "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_delta_ll_dev", "pyglm_b200_gibbs_commit",
     "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
 ]
 
@@ -65,6 +65,7 @@ def load_library():
     lib.pyglm_b200_firing_rate.argtypes = [p, p, p, p, p, i32, i32, i32, p]
     lib.pyglm_b200_gibbs_begin.argtypes = [p, p, p, p, p, i32, i32, i32]
     lib.pyglm_b200_gibbs_delta_ll.argtypes = [p, i32, p, p, i32, p, p]
+    lib.pyglm_b200_gibbs_delta_ll_dev.argtypes = [p, i32, p, p, i32, p, p, p]
     lib.pyglm_b200_gibbs_commit.argtypes = [p, i32, p, p, p, p]
     lib.pyglm_b200_gibbs_get_state.argtypes = [p, p, p]
     lib.pyglm_b200_gibbs_end.argtypes = [p]
@@ -228,6 +229,12 @@ class Dataset:
         out = np.empty((M, Q))
         _check(load_library().pyglm_b200_gibbs_delta_ll(self._h, M, _ptr(cols), _ptr(pres), Q, _ptr(w_cand), _ptr(out)))
         return out
+
+    def gibbs_delta_ll_dev(self, M, d_cols, d_pres, Q, d_w_cand, d_out, stream):
+        """Device-pointer variant (integer addresses); enqueues on `stream`, no synchronisation."""
+        vp = C.c_void_p
+        _check(load_library().pyglm_b200_gibbs_delta_ll_dev(self._h, M, vp(d_cols), vp(d_pres), Q, vp(d_w_cand),
+                                                            vp(d_out), vp(stream)))
 
     def gibbs_commit(self, cols, pres, a_new, w_new):
         cols = np.ascontiguousarray(cols, dtype=np.int32)
