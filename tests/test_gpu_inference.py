@@ -1,0 +1,158 @@
+"""GPU tests of the callers on either side of the hot path: MAP coordinate descent (synth_map) and the
+collapsed Gibbs sweep (synth_mcmc), through the Population interface."""
+import copy
+
+import numpy as np
+import pytest
+import scipy.optimize as opt
+
+from oracle import pyglm_oracle as orc
+from tests.helpers import rel_err
+from theano_pyglm_b200.models.model_factory import make_model, stabilize_sparsity
+from theano_pyglm_b200.population import Population
+
+pytestmark = pytest.mark.gpu
+
+
+def synth_standard_glm(N=4, nT=20000, seed=0):
+    """Restated test/generate_synth_data.py for standard_glm: prior draw, simulate, package."""
+    model = make_model('standard_glm', N=N, dt=0.001)
+    popn = Population(model)
+    np.random.seed(seed)
+    x_true = popn.sample()
+    for n in range(N):                                   # group-lasso draws are O(10); keep the network stable
+        x_true['glms'][n]['imp']['w_ir'] *= 0.02
+    rng = np.random.default_rng(seed)
+    bias, w, A, W = popn.glm.engine_params(x_true)
+    ib = popn.glm.imp_model.ibasis
+    imps = np.einsum('npb,rb->pnr', w.reshape(N, N, -1), ib)
+    S, X = orc.simulate(bias, imps, np.ones((N, N), np.int8), np.ones((N, N)), nT, 0.001, orc.NLIN_SOFTPLUS, rng)
+    data = {'S': S, 'X': X, 'N': N, 'dt': 0.001, 'T': nT * 0.001, 'stim': None, 'dt_stim': 0.1, 'vars': x_true}
+    return model, popn, data, x_true
+
+
+def test_population_ll_matches_oracle_and_reference_assertion():
+    model, popn, data, x_true = synth_standard_glm()
+    popn.add_data(data)
+    N = model['N']
+    bias, w, A, W = popn.glm.engine_params(x_true)
+    fS = orc.convolve_with_basis(data['S'], popn.glm.imp_model.ibasis)
+    ll, gb, gw = orc.population_ll_grad(fS, data['S'], 0.001, bias, w.reshape(N, N, -1), np.ones((N, N), np.int8),
+                                        np.ones((N, N)), orc.NLIN_SOFTPLUS)
+    assert abs(popn.compute_ll(x_true) - ll.sum()) < 1e-6 * abs(ll.sum())
+    lp = popn.compute_log_p(x_true)
+    assert abs(lp - (popn.compute_log_prior(x_true) + ll.sum())) < 1e-6 * abs(lp)
+    state = popn.eval_state(x_true)                      # generate_synth_data.py:124-129
+    for n in range(N):
+        assert np.allclose(state['glms'][n]['lam'], orc.nlin(data['X'][:, n], orc.NLIN_SOFTPLUS))
+    # per-neuron log posterior + gradient vector in sorted-key order (bias, w_ir)
+    lp1, g1 = popn.glm_log_p_grad(x_true, 1)
+    ref_lp = ll[1] + popn.glm.log_prior(x_true['glms'][1])
+    gp = popn.glm.grad_log_prior(x_true['glms'][1])
+    ref_g = np.concatenate([[gb[1] + gp['bias']['bias'][0]], gw[1].ravel() + gp['imp']['w_ir']])
+    assert abs(lp1 - ref_lp) < 1e-6 * abs(ref_lp) and rel_err(g1, ref_g) < 1e-5
+    lps, gs = popn.glms_log_p_grad(x_true)
+    assert abs(lps[1] - lp1) < 1e-9 * abs(lp1) and np.allclose(gs[1], g1, rtol=1e-9, atol=1e-9)
+
+
+def test_map_coordinate_descent_batched_and_per_neuron_agree_with_cpu_optimum():
+    from theano_pyglm_b200.inference.coord_descent import coord_descent, fit_glm
+    model, popn, data, x_true = synth_standard_glm(N=3, nT=15000, seed=2)
+    popn.add_data(data)
+    N = 3
+    np.random.seed(11)
+    x0 = popn.sample()
+    for n in range(N):
+        x0['glms'][n]['imp']['w_ir'] *= 0.01
+    lp0 = popn.compute_log_p(x0)
+    xa = coord_descent(popn, x0=copy.deepcopy(x0), maxiter=1, batched=True)
+    lpa = popn.compute_log_p(xa)
+    assert lpa > lp0
+    xb = copy.deepcopy(x0)
+    for n in range(N):
+        fit_glm(popn, xb, n)
+    lpb = popn.compute_log_p(xb)
+    # same optimum from the CPU oracle objective with scipy BFGS (the reference's optimiser)
+    fS = orc.convolve_with_basis(data['S'], popn.glm.imp_model.ibasis)
+    A, W = np.ones((N, N), np.int8), np.ones((N, N))
+    lpc = popn.network.log_p(x0['net'])
+    for n in range(N):
+        def nll(v):
+            ll, gb, gw = orc.glm_ll_grad(fS, data['S'], 0.001, n, v[0], v[1:].reshape(N, -1), A, W, orc.NLIN_SOFTPLUS)
+            lp = ll + orc.bias_log_prior(v[0], 20, 0.1) + orc.group_lasso_log_p(v[1:].reshape(N, -1), 0.0, 10.0, 1.0)
+            g = np.concatenate([[gb + orc.bias_log_prior_grad(v[0], 20, 0.1)],
+                                (gw + orc.group_lasso_log_p_grad(v[1:].reshape(N, -1), 0.0, 10.0, 1.0)).ravel()])
+            return -lp, -g
+        v0 = popn.glm_param_vector(x0['glms'][n])
+        res = opt.minimize(nll, v0, jac=True, method="bfgs", options={'maxiter': 225})
+        lpc += -res.fun
+    assert abs(lpa - lpc) < 2e-6 * abs(lpc)
+    assert abs(lpb - lpc) < 2e-6 * abs(lpc)
+    # and the fit moved toward the truth: higher likelihood than the generating parameters' prior draw
+    assert lpa >= popn.compute_log_p(x_true) - 1e-3 * abs(lpa)
+
+
+def synth_network_glm(N=5, nT=6000, seed=3):
+    model = make_model('sparse_weighted_model', N=N, dt=0.001)
+    stabilize_sparsity(model)
+    popn = Population(model)
+    np.random.seed(seed)
+    x = popn.sample()
+    rng = np.random.default_rng(seed)
+    S = (rng.random((nT, N)) < 0.02).astype(np.float64)
+    data = {'S': S, 'N': N, 'dt': 0.001, 'T': nT * 0.001, 'stim': None, 'dt_stim': 0.1}
+    popn.add_data(data)
+    return model, popn, data, x
+
+
+def test_collapsed_column_update_reproduces_reference_decisions_for_the_same_random_stream():
+    """`update(x, n)` consumes np.random where the reference does (shuffle, one rand per edge, one randn
+    when W comes from the prior).  Replaying the same stream through the CPU restatement of
+    gibbs.py:1229-1250 must give identical A decisions and the same W."""
+    from theano_pyglm_b200.inference.gibbs import CollapsedGibbsNetworkColumnUpdate
+    model, popn, data, x = synth_network_glm()
+    N = model['N']
+    upd = CollapsedGibbsNetworkColumnUpdate()
+    upd.preprocess(popn)
+    upd.sample_w_with_ars = False                         # ARS comes from the un-vendored hips: parity unpinned
+    x_ref = copy.deepcopy(x)
+    bias, w, A0, W0 = popn.glm.engine_params(x_ref)
+    fS = orc.convolve_with_basis(data['S'], popn.glm.imp_model.ibasis)
+    p_A = popn.network.graph.pA.get_value()
+    A_ref, W_ref = A0.copy(), W0.copy()
+    upd.begin(x)
+    for n_post in (0, 3):
+        np.random.seed(100 + n_post)
+        upd.update(x, n_post)
+        np.random.seed(100 + n_post)                      # replay
+        order = np.arange(N)
+        np.random.shuffle(order)
+        us, zs = np.zeros(N), np.zeros(N)
+        for i in range(N):
+            us[i] = np.random.rand()
+            zs[i] = np.random.randn()
+        zmap = {int(p): zs[i] for i, p in enumerate(order)}
+        orc.collapsed_column_sweep(fS, data['S'], 0.001, n_post, bias[n_post], w[n_post].reshape(N, -1), A_ref, W_ref,
+                                   p_A, orc.NLIN_SOFTPLUS, 0.0, 1.0, -0.2, 0.5, order, us,
+                                   lambda n_pre, a, mu, sig, ws, lL: mu + sig * zmap[int(n_pre)])
+        assert np.array_equal(x['net']['graph']['A'], A_ref)
+        assert np.allclose(x['net']['weights']['W'].reshape(N, N), W_ref, rtol=0, atol=1e-12)
+    A_dev, W_dev = popn._handle().gibbs_state()
+    assert np.array_equal(A_dev, A_ref) and np.allclose(W_dev, W_ref, atol=1e-12)
+    upd.end()
+
+
+def test_gibbs_sample_runs_and_keeps_a_valid_state():
+    from theano_pyglm_b200.inference.gibbs import gibbs_sample
+    model, popn, data, x = synth_network_glm(N=4, nT=4000, seed=5)
+    np.random.seed(7)
+    for batched in (True, False):
+        smpls = gibbs_sample(popn, N_samples=2, x0=copy.deepcopy(x), batched=batched)
+        assert len(smpls) == 3
+        last = smpls[-1]
+        A = last['net']['graph']['A']
+        assert A.dtype == np.int8 and set(np.unique(A)) <= {0, 1} and np.all(np.diag(A) == 1)
+        assert np.isfinite(popn.compute_log_p(last))
+        assert any(not np.array_equal(smpls[0]['net']['weights']['W'], s['net']['weights']['W']) for s in smpls[1:])
+        # engine state and host state stayed in sync through the sweep
+        assert np.all(np.isfinite(last['net']['weights']['W']))

@@ -1,0 +1,290 @@
+"""MCMC over the network GLM (interface of pyglm/inference/gibbs.py for the accelerated path).
+
+`gibbs_sample(population, N_samples, x0, init_from_mle, callback)` keeps the reference's loop
+(:2475-2571): every sweep applies, for each neuron, HMC on the bias, HMC on the impulse
+responses and the collapsed spike-and-slab Gibbs update of one column of A/W.
+
+The column update is `CollapsedGibbsNetworkColumnUpdate` (:775-1250).  Its likelihood work --
+`_precompute_other_current` + 11 `_glm_ll` passes per edge + ARS probes -- is the engine's K4:
+`gibbs_begin` once per sweep makes I_net resident, every edge is one `gibbs_delta_ll` call and
+one rank-1 `gibbs_commit`.  Two schedules:
+  * `update(x, n)`            one column at a time, edges in np.random.shuffle order, consuming
+                              np.random exactly where the reference does (:1236-1237, log_sum_exp.py:26,
+                              :1063) -- drop-in for seeded runs up to the ARS draws (hips is not vendored);
+  * `sweep_batched(x)`        all columns in lock-step, one batched kernel launch per step of N edges --
+                              columns are conditionally independent (gibbs.py:53-61), so this is the
+                              same Markov kernel the reference runs in parallel over IPython engines.
+"""
+import copy
+
+import numpy as np
+from scipy.special import logsumexp
+
+from ..components.impulse import DirichletImpulses
+from .ars import adaptive_rejection_sample
+from .hmc import hmc
+from .log_sum_exp import log_sum_exp_sample
+
+
+class MetropolisHastingsUpdate(object):
+    def preprocess(self, population):
+        self.population = population
+
+    def update(self, x):
+        return x
+
+
+class ParallelMetropolisHastingsUpdate(MetropolisHastingsUpdate):
+    """Updates that act on one neuron given the rest; conditionally independent across n (gibbs.py:53-61)."""
+
+    def update(self, x, n):
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+# HMC updates of the GLM parameters (gibbs.py:164-321, :449-772); likelihood + gradient from the engine
+# ------------------------------------------------------------------------------------------------
+class _HmcGlmBlockUpdate(ParallelMetropolisHastingsUpdate):
+    n_steps = 10
+
+    def __init__(self):
+        self.avg_accept_rate = 0.9
+        self.step_sz = 0.1
+
+    def _logp_and_grad(self, x, n):
+        return self.population.glm_log_p_grad(x, n)
+
+    def _run(self, x, n, get, put, sl):
+        """HMC on the slice `sl` of neuron n's parameter vector."""
+        popn = self.population
+        xn = x['glms'][n]
+        full0 = popn.glm_param_vector(xn)
+
+        def with_block(q):
+            v = full0.copy()
+            v[sl] = q
+            popn.set_glm_param_vector(xn, v)
+
+        def U(q):
+            with_block(q)
+            return -self._logp_and_grad(x, n)[0]
+
+        def grad_U(q):
+            with_block(q)
+            return -self._logp_and_grad(x, n)[1][sl]
+
+        q, self.step_sz, self.avg_accept_rate = hmc(U, grad_U, self.step_sz, self.n_steps, full0[sl],
+                                                    adaptive_step_sz=True, avg_accept_rate=self.avg_accept_rate)
+        with_block(q)
+        return x
+
+
+class HmcBiasUpdate(_HmcGlmBlockUpdate):
+    """gibbs.py:164-321: 10 leapfrog steps on the scalar bias."""
+    n_steps = 10
+
+    def update(self, x, n):
+        return self._run(x, n, None, None, slice(0, 1))
+
+
+class HmcBkgdUpdate(ParallelMetropolisHastingsUpdate):
+    """gibbs.py:324-446; nothing to sample for the `none` background model."""
+
+
+class HmcImpulseUpdate(_HmcGlmBlockUpdate):
+    """gibbs.py:449-566: HMC on w_ir of a LinearBasisImpulses model."""
+    n_steps = 10
+
+    def update(self, x, n):
+        D = 1 + self.population.N * self.population.glm.imp_model.B
+        return self._run(x, n, None, None, slice(1, D))
+
+
+class HmcDirichletImpulseUpdate(_HmcGlmBlockUpdate):
+    """gibbs.py:569-772: per presynaptic neuron, 2 leapfrog steps on g_{n_pre} where an edge exists,
+    a Gamma(alpha, 1) prior draw where it does not (:764-767)."""
+    n_steps = 2
+
+    def update(self, x, n_post):
+        popn = self.population
+        imp = popn.glm.imp_model
+        A = x['net']['graph']['A']
+        names = sorted(imp.get_variables())                   # vector order of the g blocks
+        for n_pre in range(popn.N):
+            key = 'g_%d' % n_pre
+            if A[n_pre, n_post]:
+                k = names.index(key)
+                self._run(x, n_post, None, None, slice(1 + k * imp.B, 1 + (k + 1) * imp.B))
+            else:
+                x['glms'][n_post]['imp'][key] = np.random.gamma(imp.alpha, np.ones(imp.B))
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+# Collapsed Gibbs over one column of A / W
+# ------------------------------------------------------------------------------------------------
+class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
+    def __init__(self):
+        self.DEG_GAUSS_HERMITE = 10
+        self.GAUSS_HERMITE_ABSCISSAE, self.GAUSS_HERMITE_WEIGHTS = \
+            np.polynomial.hermite.hermgauss(self.DEG_GAUSS_HERMITE)        # gibbs.py:787-789
+        self.sample_w_with_ars = True
+        self._resident = None
+
+    def preprocess(self, population):
+        self.population = population
+        self.network = population.network
+        w = self.network.weights
+        self.mu_w, self.sigma_w = w.prior.mu.get_value(), w.prior.sigma.get_value()
+        if hasattr(w, 'refractory_prior'):
+            self.mu_w_ref = w.refractory_prior.mu.get_value()
+            self.sigma_w_ref = w.refractory_prior.sigma.get_value()
+        else:
+            self.mu_w_ref, self.sigma_w_ref = self.mu_w, self.sigma_w
+
+    # -- engine residency ------------------------------------------------------------------------
+    def begin(self, x):
+        """Upload the state and build I_net for every column (seval(glm.I_net), gibbs.py:812-864)."""
+        popn = self.population
+        bias, w, A, W = popn.glm.engine_params(x)
+        ds = popn._handle()
+        ds.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code)
+        self._resident = ds
+        return ds
+
+    def end(self):
+        if self._resident is not None:
+            self._resident.gibbs_end()
+        self._resident = None
+
+    def _prior(self, n_pre, n_post):
+        if n_pre == n_post:
+            return self.mu_w_ref, self.sigma_w_ref                             # :984-989
+        return self.mu_w, self.sigma_w
+
+    def _log_odds(self, log_L, ll_noA, p_A):
+        """(log_pr_noA, log_pr_A) from the 10 quadrature lls and the w=0 ll (:1002-1035)."""
+        log_L = np.array(log_L, dtype=np.float64)
+        log_L[np.isnan(log_L)] = -np.inf
+        with np.errstate(divide='ignore'):
+            weighted = log_L + np.log(self.GAUSS_HERMITE_WEIGHTS / np.sqrt(np.pi))
+        weighted[np.isnan(weighted)] = -np.inf
+        log_G = logsumexp(weighted)
+        if not np.isfinite(log_G):
+            raise Exception("log_G not finie")
+        with np.errstate(divide='ignore'):
+            log_pr_A = np.log(p_A) + log_G
+            log_pr_noA = np.log(1.0 - p_A) + ll_noA
+        if np.isnan(log_pr_noA):
+            log_pr_noA = -np.inf
+        return log_pr_noA, log_pr_A
+
+    def _sample_w(self, ds, n_pre, n_post, mu_w, sigma_w, W_nns, log_L):
+        """W | A=1 by adaptive rejection sampling on the exact conditional (:1087-1126); every probe of
+        the log posterior is a Q=1 delta-ll call."""
+        log_post = -0.5 / sigma_w ** 2 * (W_nns - mu_w) ** 2 + log_L
+        Z = np.amax(log_post)
+
+        def _log_posterior(w):
+            ll = ds.gibbs_delta_ll([n_post], [n_pre], np.array([[float(w)]]))[0, 0]
+            return -0.5 / sigma_w ** 2 * (w - mu_w) ** 2 + ll - Z
+
+        valid = np.isfinite(log_post) & (log_post > -1e8)                       # effective behaviour of :1118-1120
+        return adaptive_rejection_sample(_log_posterior, W_nns[valid], log_post[valid] - Z, (-np.inf, np.inf),
+                                         stepsz=sigma_w / 2.0, debug=False)
+
+    def _resample_edge(self, ds, x, n_pre, n_post, ll, p_A):
+        """Given the 11 candidate lls of one edge, draw A then W and commit (gibbs.py:1036-1066)."""
+        A = x['net']['graph']['A']
+        N = A.shape[0]
+        W = x['net']['weights']['W'].reshape(N, N)
+        mu_w, sigma_w = self._prior(n_pre, n_post)
+        W_nns = np.sqrt(2) * sigma_w * self.GAUSS_HERMITE_ABSCISSAE + mu_w
+        lp_noA, lp_A = self._log_odds(ll[:10], ll[10], p_A[n_pre, n_post])
+        A[n_pre, n_post] = log_sum_exp_sample([lp_noA, lp_A])                   # one np.random.rand()
+        if np.allclose(p_A[n_pre, n_post], 1.0) and not A[n_pre, n_post]:
+            raise Exception("Sampled no self edge")
+        if A[n_pre, n_post] == 1 and self.sample_w_with_ars:
+            W[n_pre, n_post] = self._sample_w(ds, n_pre, n_post, mu_w, sigma_w, W_nns, np.asarray(ll[:10]))
+        else:
+            W[n_pre, n_post] = mu_w + sigma_w * np.random.randn()               # :1063
+        x['net']['weights']['W'] = W.ravel()
+        ds.gibbs_commit([n_post], [n_pre], [A[n_pre, n_post]], [W[n_pre, n_post]])
+
+    def _candidates(self, n_pre, n_post):
+        mu_w, sigma_w = self._prior(n_pre, n_post)
+        return np.concatenate([np.sqrt(2) * sigma_w * self.GAUSS_HERMITE_ABSCISSAE + mu_w, [0.0]])
+
+    # -- reference schedule: one column ----------------------------------------------------------
+    def update(self, x, n):
+        ds = self._resident or self.begin(x)
+        N = x['net']['graph']['A'].shape[0]
+        p_A = self.network.graph.pA.get_value()
+        order = np.arange(N)
+        np.random.shuffle(order)                                                # :1236-1237
+        for n_pre in order:
+            ll = ds.gibbs_delta_ll([n], [n_pre], self._candidates(n_pre, n)[None, :])[0]
+            self._resample_edge(ds, x, n_pre, n, ll, p_A)
+        return x
+
+    # -- B200 schedule: all columns in lock-step ---------------------------------------------------
+    def sweep_batched(self, x):
+        ds = self._resident or self.begin(x)
+        N = x['net']['graph']['A'].shape[0]
+        p_A = self.network.graph.pA.get_value()
+        orders = np.stack([np.random.permutation(N) for _ in range(N)])        # one shuffled order per column
+        cols = np.arange(N, dtype=np.int32)
+        for s in range(N):
+            pres = orders[:, s].astype(np.int32)
+            cand = np.stack([self._candidates(pres[n], n) for n in range(N)])
+            ll = ds.gibbs_delta_ll(cols, pres, cand)                            # N edges x 11 candidates, one launch
+            for n in range(N):
+                self._resample_edge(ds, x, int(pres[n]), n, ll[n], p_A)
+        return x
+
+
+# ------------------------------------------------------------------------------------------------
+def initialize_updates(population):
+    """gibbs.py:2413-2473 restricted to the samplers the accelerated path supports (no latent variables)."""
+    serial_updates = []
+    parallel_updates = [HmcBiasUpdate(), HmcBkgdUpdate()]
+    parallel_updates.append(HmcDirichletImpulseUpdate() if isinstance(population.glm.imp_model, DirichletImpulses)
+                            else HmcImpulseUpdate())
+    parallel_updates.append(CollapsedGibbsNetworkColumnUpdate())
+    for u in parallel_updates:
+        u.preprocess(population)
+    return serial_updates, parallel_updates
+
+
+def gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=False, callback=None, batched=True,
+                 verbose=False):
+    """Sample the posterior over parameters (gibbs.py:2475-2571).  `init_from_mle` needs convert_model
+    (models/model_factory.py:187-268, a 'next' row) and is not available yet."""
+    if init_from_mle:
+        raise NotImplementedError("init_from_mle needs convert_model, which is outside the built scope")
+    N = population.model['N']
+    if x0 is None:
+        x0 = population.sample()
+    serial_updates, parallel_updates = initialize_updates(population)
+    net_update = parallel_updates[-1]
+    x = x0
+    x_smpls = [copy.deepcopy(x0)]
+    for smpl in range(N_samples):
+        if callback is not None:
+            callback(x)
+        if verbose:
+            print("Gibbs iteration %d. Log prob: %.3f" % (smpl, population.compute_log_p(x)))
+        for upd in parallel_updates[:-1]:
+            for n in range(N):
+                upd.update(x, n)
+        net_update.begin(x)                                   # GLM parameters changed: rebuild the resident currents
+        if batched:
+            net_update.sweep_batched(x)
+        else:
+            for n in range(N):
+                net_update.update(x, n)
+        net_update.end()
+        for upd in serial_updates:
+            upd.update(x)
+        x_smpls.append(copy.deepcopy(x))
+    return x_smpls

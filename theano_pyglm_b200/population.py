@@ -152,6 +152,40 @@ class Population:
             parts.append(gp['imp'][k] + g_imp[k])
         return float(lp), np.concatenate([np.ravel(p) for p in parts])
 
+    def glm_param_vector(self, xn):
+        """Differentiable GLM variables of one neuron as a flat vector, sorted-key order (bias < imp)."""
+        parts = [np.ravel(xn['bias']['bias'])]
+        for k in sorted(self.glm.imp_model.get_variables()):
+            parts.append(np.ravel(xn['imp'][k]))
+        return np.concatenate(parts).astype(np.float64)
+
+    def set_glm_param_vector(self, xn, vec):
+        xn['bias']['bias'] = np.array(vec[:1], dtype=np.float64)
+        off = 1
+        for k, shp in sorted(self.glm.imp_model.get_variables().items()):
+            sz = int(np.prod(shp))
+            xn['imp'][k] = np.array(vec[off:off + sz], dtype=np.float64).reshape(shp)
+            off += sz
+
+    def glms_log_p_grad(self, x):
+        """The per-neuron log posteriors of coord_descent.nlp/grad_nlp for ALL neurons from one engine call
+        per data sequence: lp (N,), grad (N, D) in the order of `glm_param_vector`."""
+        bias, w, A, W = self.glm.engine_params(x)
+        scale = self.glm.lkhd_scale.get_value()
+        ll, gb, gw = 0.0, 0.0, 0.0
+        for data in self.data_sequences:
+            l, b, g = data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, path=self.path)
+            ll, gb, gw = ll + scale * l, gb + scale * b, gw + scale * g
+        lps, grads = [], []
+        for n in range(self.N):
+            xn = x['glms'][n]
+            gp = self.glm.grad_log_prior(xn)
+            g_imp = self.glm.imp_model.chain_rule(xn['imp'], gw[n])
+            parts = [gp['bias']['bias'] + gb[n]] + [np.ravel(gp['imp'][k] + g_imp[k]) for k in sorted(g_imp)]
+            lps.append(self.glm.log_prior(xn) + ll[n])
+            grads.append(np.concatenate(parts))
+        return np.array(lps), np.stack(grads)
+
     def eval_state(self, vars):
         """Firing rates and currents for the current state (population.py:88-123), engine-side lam."""
         bias, w, A, W = self.glm.engine_params(vars)
