@@ -30,14 +30,15 @@ static FiltSmemLayout filt_layout(int R, int B, int tt, int pc) {
     L.off_basis = o; o += (size_t)R * B * sizeof(double);
     L.off_out = o;   o += (size_t)kFiltSub * (pc * B + 1) * sizeof(XT);
     o = (o + 7) & ~(size_t)7;
-    L.off_ent = o;   o += (size_t)rows * pc * sizeof(uint32_t);
+    L.off_ent = o;   o += (size_t)rows * pc * sizeof(uint16_t);
     L.off_idx = o;   o += (size_t)(rows + 1) * pc * sizeof(uint16_t);
     L.off_s = o;     o += (size_t)rows * (pc + 4);
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
 
-template <typename XT, int BMAX>
+// BEXACT: B is exactly BMAX (no per-basis predicates in the inner loop)
+template <typename XT, int BMAX, bool BEXACT>
 __global__ void __launch_bounds__(kFiltThreads)
 filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
               const double* __restrict__ ibasis, int R, int B,
@@ -46,7 +47,7 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
     extern __shared__ __align__(16) unsigned char smem[];
     double*   sB   = reinterpret_cast<double*>(smem + L.off_basis);   // [R][B]
     XT*       sOut = reinterpret_cast<XT*>(smem + L.off_out);         // [kFiltSub][pc*B+1]
-    uint32_t* sEnt = reinterpret_cast<uint32_t*>(smem + L.off_ent);   // [rows][pc]  (row<<8 | count)
+    uint16_t* sEnt = reinterpret_cast<uint16_t*>(smem + L.off_ent);   // [rows][pc]  tile row of the e-th spike of a column
     uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.off_idx);   // [rows+1][pc] #spikes in tile rows [0,i)
     uint8_t*  sS   = smem + L.off_s;                                  // [rows][pc+4]
 
@@ -63,19 +64,20 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
     const int64_t gmax = (int64_t)halo + T;
     for (int c = lane; c < pc; c += 32) {
         const bool col_ok = c0 + c < N;
-        for (int i = warp; i < rows; i += 8 * kFiltWarps) {
-            uint8_t v[8];
+        const uint8_t* src = S + (g0 + warp) * N + c0 + c;            // row `warp` of the tile, this lane's column
+        uint8_t* dsts = sS + warp * sstride + c;
+        for (int i = warp; i < rows; i += 4 * kFiltWarps) {
+            uint8_t v[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int ii = i + u * kFiltWarps;
-                const int64_t g = g0 + ii;
-                v[u] = (col_ok && ii < rows && g >= 0 && g < gmax) ? S[g * N + c0 + c] : (uint8_t)0;
+            for (int u = 0; u < 4; ++u) {
+                const int64_t g = g0 + i + u * kFiltWarps;
+                v[u] = (col_ok && i + u * kFiltWarps < rows && g >= 0 && g < gmax) ? src[(int64_t)u * kFiltWarps * N] : (uint8_t)0;
             }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int ii = i + u * kFiltWarps;
-                if (ii < rows) sS[ii * sstride + c] = v[u];
-            }
+            for (int u = 0; u < 4; ++u)
+                if (i + u * kFiltWarps < rows) dsts[u * kFiltWarps * sstride] = v[u];
+            src += (int64_t)4 * kFiltWarps * N;
+            dsts += 4 * kFiltWarps * sstride;
         }
     }
     for (int e = tid; e < R * B; e += kFiltThreads) sB[e] = ibasis[e];
@@ -90,7 +92,7 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
             const uint32_t m = __ballot_sync(0xffffffffu, v != 0u);
             const int pos = count + __popc(m & ((1u << lane) - 1u));
             if (i < rows) sIdx[i * pc + c] = (uint16_t)pos;
-            if (v) sEnt[pos * pc + c] = ((uint32_t)i << 8) | v;
+            if (v) sEnt[pos * pc + c] = (uint16_t)i;
             count += __popc(m);
         }
         if (lane == 0) sIdx[rows * pc + c] = (uint16_t)count;
@@ -112,45 +114,59 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
             double acc[BMAX];
 #pragma unroll
             for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
+#pragma unroll 1
             for (int e = e0; e < e1; ++e) {
-                const uint32_t ent = sEnt[e * pc + c];        // warp-uniform broadcast
-                const int k = i - (int)(ent >> 8);            // lag
+                const int srow = sEnt[e * pc + c];            // warp-uniform broadcast
+                const int k = i - srow;                       // lag
+                const uint32_t cnt = sS[srow * sstride + c];  // warp-uniform: spike count of that bin
                 if (k >= 1 && k <= R) {
-                    const double cnt = (double)(ent & 0xffu);
                     const double* row = sB + (size_t)(k - 1) * B;
+                    if (cnt == 1u) {                          // the usual case: no multiply
 #pragma unroll
-                    for (int b = 0; b < BMAX; ++b)
-                        if (b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(cnt, row[b]));
+                        for (int b = 0; b < BMAX; ++b)
+                            if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], row[b]);
+                    } else {
+                        const double dc = (double)cnt;
+#pragma unroll
+                        for (int b = 0; b < BMAX; ++b)
+                            if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(dc, row[b]));
+                    }
                 }
             }
 #pragma unroll
             for (int b = 0; b < BMAX; ++b)
-                if (b < B) sOut[ts * ostride + c * B + b] = (XT)acc[b];
+                if (BEXACT || b < B) sOut[ts * ostride + c * B + b] = (XT)acc[b];
         }
         __syncthreads();
         // ---- coalesced copy-out of the valid part of the sub-tile
         const int nrow = (int)min((int64_t)kFiltSub, T - (t0 + sub));
         XT* dst = X + (t0 + sub) * ldx + (int64_t)c0 * B;
-        for (int ts = warp; ts < nrow; ts += kFiltWarps) {
-            const XT* src = sOut + ts * ostride;
-            XT* drow = dst + (int64_t)ts * ldx;
-            for (int j = lane; j < width; j += 32) drow[j] = src[j];
+        {
+            const XT* src = sOut + warp * ostride + lane;
+            XT* drow = dst + (int64_t)warp * ldx + lane;
+            for (int ts = warp; ts < nrow; ts += kFiltWarps) {
+#pragma unroll
+                for (int j = 0; j < (32 * BMAX + 31) / 32; ++j)              // pc <= 32 columns: at most BMAX chunks of 32
+                    if (lane + 32 * j < width) drow[32 * j] = src[32 * j];
+                src += kFiltWarps * ostride;
+                drow += (int64_t)kFiltWarps * ldx;
+            }
         }
         __syncthreads();
     }
 }
 
-template <typename XT, int BMAX>
+template <typename XT, int BMAX, bool BEXACT>
 static int launch_filter_t(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
                            XT* dX, int64_t ldx, cudaStream_t stream)
 {
     // pick the largest tile whose shared memory fits (<= 200 KB: one resident block per SM at worst)
-    const int cand[][2] = {{256, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {64, 4}};
+    const int cand[][2] = {{192, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {64, 4}};
     int tt = 0, pc = 0;
     FiltSmemLayout L{};
     for (auto& c : cand) {
         L = filt_layout<XT>(R, B, c[0], c[1]);
-        if (L.total <= 200 * 1024) { tt = c[0]; pc = c[1]; break; }
+        if (L.total <= 113 * 1024) { tt = c[0]; pc = c[1]; break; }     // two resident blocks per SM
     }
     if (tt == 0) {
         set_error("filter: R=%d B=%d needs more shared memory than one SM has", R, B);
@@ -160,7 +176,7 @@ static int launch_filter_t(const uint8_t* dS, int64_t T, int N, int halo, const 
         set_error("filter: R=%d too long", R);
         return PYGLM_B200_EUNSUPPORTED;
     }
-    auto kern = filter_kernel<XT, BMAX>;
+    auto kern = filter_kernel<XT, BMAX, BEXACT>;
     PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
     dim3 grid((unsigned)ceil_div(T, tt), (unsigned)ceil_div(N, pc));
     kern<<<grid, kFiltThreads, L.total, stream>>>(dS, T, N, halo, d_ibasis, R, B, dX, ldx, tt, pc, L);
@@ -178,14 +194,16 @@ int launch_filter(const uint8_t* dS, int64_t T, int N, int halo, const double* d
     if (T <= 0) return PYGLM_B200_OK;
     if (x_dtype == PYGLM_B200_X_F32) {
         float* x = static_cast<float*>(dX);
-        if (B <= 5)  return launch_filter_t<float, 5>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        if (B <= 10) return launch_filter_t<float, 10>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        return launch_filter_t<float, 16>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B == 5)  return launch_filter_t<float, 5, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B == 10) return launch_filter_t<float, 10, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B <= 8)  return launch_filter_t<float, 8, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        return launch_filter_t<float, 16, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
     } else {
         double* x = static_cast<double*>(dX);
-        if (B <= 5)  return launch_filter_t<double, 5>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        if (B <= 10) return launch_filter_t<double, 10>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        return launch_filter_t<double, 16>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B == 5)  return launch_filter_t<double, 5, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B == 10) return launch_filter_t<double, 10, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        if (B <= 8)  return launch_filter_t<double, 8, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+        return launch_filter_t<double, 16, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
     }
 }
 
