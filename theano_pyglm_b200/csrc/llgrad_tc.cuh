@@ -24,6 +24,7 @@ struct TcWorkspace {
     size_t part_elems = 0;
     void* tmaps = nullptr;        // host copy of the two CUtensorMap descriptors
     int num_sms = 0;
+    void* gemm = nullptr;         // large-population GEMM path workspace (llgrad_tc_gemm.cu)
     void release();
 };
 
@@ -37,6 +38,12 @@ struct TcArgs {
 };
 
 bool tc_supported(int64_t T, int N, int B, int x_dtype);
+bool tc_uses_fused_kernel(int N, int B);
+// shared with the GEMM path
+int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
+int tc_make_map_2d(void* map, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1);
+int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
+void tc_gemm_release(void* w);
 int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 
 }  // namespace pyglm

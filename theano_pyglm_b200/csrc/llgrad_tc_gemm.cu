@@ -1,0 +1,537 @@
+// K2 (tensor-core path, large populations): two tcgen05 GEMM kernels for N*B > 160 features.
+//
+// When the X tile of all features no longer fits in shared memory next to its pipeline (the fused
+// kernel in llgrad_tc.cu), the two contractions become two kernels, each a classic TMA -> tcgen05 ->
+// TMEM -> epilogue pipeline over the same FP16 split planes:
+//
+//   tc_gemm_fwd_kernel   act tile [128 bins x 128 neurons] = X[128 x K] M[K x 128], K = N*B streamed in
+//                        32-feature chunks through a 6-stage ring; the epilogue (FP32) turns the TMEM
+//                        accumulators into Poisson terms and residuals r, writes r to HBM as split FP16
+//                        planes and keeps per-column ll / g_bias sums in FP64.          glm.py:39-52
+//   tc_gemm_bwd_kernel   G tile [128 features x 128 neurons] = sum_t X[t]^T r[t] over this CTA's share of
+//                        the recording (split-K over time); both operands MN-major straight from TMA;
+//                        every 128 bins the TMEM block is folded into FP64 registers (TMEM FP32
+//                        accumulation is not clean over long sums, see llgrad_tc.cu).   T.grad(glm.ll)
+//
+// Same operand splitting as the fused kernel: x1 m1 in one accumulator, x2 m1 + x1 m2 (carrying 2^-11) in
+// a second one.  A 128x128x16 FP16 MMA reads 8 KB of operands for 64 cycles of tensor pipe, so these tiles
+// are tensor-bound rather than shared-memory-bound.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "llgrad_tc.cuh"
+#include "tc_common.cuh"
+
+namespace pyglm {
+
+constexpr int kGT = 128;                     // bins per tile (UMMA M of the forward, K block of the gradient)
+constexpr int kGN = 128;                     // neurons per tile (UMMA N)
+constexpr int kGF = 128;                     // features per gradient tile (UMMA M of the gradient)
+constexpr int kGEpiWarps = 16;
+constexpr int kGFirstEpi = 3;
+constexpr int kGThreads = 32 * (kGFirstEpi + kGEpiWarps);
+constexpr int kGColsPerWarp = kGN / 4;       // 32 columns per epilogue warp (4 column groups x 4 lane quarters)
+constexpr int kFwdStages = 6;
+constexpr int kFwdStageBytes = 4 * kGT * 64; // X1, X2, M1, M2 chunks of [128 rows][32 halves]
+constexpr int kBwdStages = 3;
+constexpr int kBwdRows = 64;                 // bins per gradient stage
+constexpr int kBwdChunkBytes = kBwdRows * 64;
+constexpr int kBwdStageBytes = 16 * kBwdChunkBytes;   // X1, X2, r1, r2: 4 chunks each
+
+struct GemmWorkspace {
+    __half* Mp = nullptr; size_t Mp_elems = 0;         // [2][Npr][Kp]
+    float* colpar = nullptr; size_t colpar_elems = 0;  // [2][Npr]
+    __half* R = nullptr; size_t R_elems = 0;           // [2][T][Npr]
+    double* part = nullptr; size_t part_elems = 0;     // forward: [nctas][4][Npr][2]
+    double* Gp = nullptr; size_t Gp_elems = 0;         // gradient: [splits][NBp][Npr]
+    CUtensorMap mapX64[2];                             // X planes with 64-row boxes (gradient kernel)
+    bool mapX64_ready = false;
+};
+
+static int ensure(void** p, size_t* have, size_t want, size_t esz)
+{
+    if (*have >= want) return PYGLM_B200_OK;
+    cudaFree(*p);
+    *p = nullptr; *have = 0;
+    PYGLM_CUDA(cudaMalloc(p, want * esz));
+    *have = want;
+    return PYGLM_B200_OK;
+}
+
+void tc_gemm_release(void* w)
+{
+    GemmWorkspace* g = static_cast<GemmWorkspace*>(w);
+    if (!g) return;
+    cudaFree(g->Mp); cudaFree(g->colpar); cudaFree(g->R); cudaFree(g->part); cudaFree(g->Gp);
+    delete g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scaled weight planes for all requested columns: block = one column
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_gemm_prep_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A, const double* __restrict__ W,
+                      const double* __restrict__ bias, const float* __restrict__ sx,
+                      int N, int B, int n_lo, int ncols, int Npr, int Kp, __half* __restrict__ Mp, float* __restrict__ colpar)
+{
+    __shared__ float smax[256];
+    const int nl = blockIdx.x;
+    const int NB = N * B;
+    const bool live = nl < ncols;
+    const int n = n_lo + nl;
+    float mx = 0.f;
+    if (live) {
+        for (int j = threadIdx.x; j < NB; j += 256) {
+            const int pre = j / B;
+            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
+            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+            mx = fmaxf(mx, fabsf((float)((a * ww) * w[(int64_t)n * NB + j] / (double)sx[j])));
+        }
+    }
+    smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + off]);
+        __syncthreads();
+    }
+    const float sm = pow2_scale(smax[0] * 1.0001f);
+    __half* M1 = Mp + (int64_t)nl * Kp;
+    __half* M2 = Mp + ((int64_t)Npr + nl) * Kp;
+    for (int j = threadIdx.x; j < Kp; j += 256) {
+        __half h1 = __float2half_rn(0.f), h2 = h1;
+        if (live && j < NB) {
+            const int pre = j / B;
+            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
+            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+            const double v = (a * ww) * w[(int64_t)n * NB + j] / (double)sx[j] * (double)sm;
+            h1 = __double2half(v);
+            h2 = __double2half((v - (double)__half2float(h1)) * (double)kLoScale);
+        }
+        M1[j] = h1;
+        M2[j] = h2;
+    }
+    if (threadIdx.x == 0) {
+        colpar[nl] = live ? 1.0f / sm : 0.f;
+        colpar[Npr + nl] = live ? (float)bias[n] : 0.f;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward GEMM + epilogue
+// ---------------------------------------------------------------------------------------------
+struct GemmFwdArgs {
+    const uint8_t* Sp; int Nps;        // padded spikes [T][Nps]
+    int64_t T; int n_lo, ncols, Npr;
+    int nkc;                           // 32-feature chunks
+    int64_t ntt; int ncb;              // time tiles, column blocks
+    const float* colpar;               // [2][Npr]
+    __half* R; int64_t plane;          // residual planes: R1 at R, R2 at R + plane; row pitch Npr
+    double* part;                      // [nctas][4 quarters][Npr][2]
+    float dt;
+};
+
+template <int NLIN>
+__global__ void __launch_bounds__(kGThreads, 1)
+tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
+                   const __grid_constant__ CUtensorMap mapM1, const __grid_constant__ CUtensorMap mapM2, GemmFwdArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdStages * kFwdStageBytes);
+    uint64_t* bar_full = bars;                       // [6]
+    uint64_t* bar_empty = bars + kFwdStages;         // [6]
+    uint64_t* bar_acc_full = bars + 2 * kFwdStages;  // [2]
+    uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kFwdStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kGEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int64_t ntiles = a.ntt * a.ncb;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t chunk = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int row0 = (int)((tile / a.ncb) * kGT);
+                const int col0 = (int)((tile % a.ncb) * kGN);
+                for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
+                    const int s = chunk % kFwdStages;
+                    mbar_wait(&bar_empty[s], ((chunk / kFwdStages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[s], kFwdStageBytes);
+                    unsigned char* st = smem + s * kFwdStageBytes;
+                    tma_load_2d(st, &mapX1, &bar_full[s], kc * 32, row0);
+                    tma_load_2d(st + kGT * 64, &mapX2, &bar_full[s], kc * 32, row0);
+                    tma_load_2d(st + 2 * kGT * 64, &mapM1, &bar_full[s], kc * 32, col0);
+                    tma_load_2d(st + 3 * kGT * 64, &mapM2, &bar_full[s], kc * 32, col0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kGT, kGN, 0, 0);
+            uint32_t chunk = 0, it = 0;
+            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int ab = it & 1;
+                const uint32_t t_a = tmem_base + ab * 256, t_b = t_a + 128;
+                mbar_wait(&bar_acc_empty[ab], ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
+                    const int s = chunk % kFwdStages;
+                    mbar_wait(&bar_full[s], (chunk / kFwdStages) & 1);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + s * kFwdStageBytes);
+                    const uint64_t dx1 = umma_desc(base, 16, 512), dx2 = umma_desc(base + kGT * 64, 16, 512);
+                    const uint64_t dm1 = umma_desc(base + 2 * kGT * 64, 16, 512), dm2 = umma_desc(base + 3 * kGT * 64, 16, 512);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                        const uint32_t acc = (kc | ks) ? 1u : 0u;
+                        umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc, acc);     // X1 M1
+                        umma_f16(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc, acc);     // X2 M1
+                        umma_f16(t_b, dx1 + 2 * ks, dm2 + 2 * ks, idesc, 1u);      // X1 M2
+                    }
+                    umma_commit(&bar_empty[s]);
+                }
+                umma_commit(&bar_acc_full[ab]);
+            }
+        }
+    } else if (warp >= kGFirstEpi) {
+        // ================================ epilogue warps ==============================
+        const int q = warp & 3;
+        const int cg = (warp - kGFirstEpi) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + cg * kGColsPerWarp;
+        double* my_part = a.part + ((int64_t)blockIdx.x * 4 + q) * a.Npr * 2;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int64_t t = (tile / a.ncb) * kGT + row;
+            const int col0 = (int)((tile % a.ncb) * kGN) + cg * kGColsPerWarp;      // first of this warp's 32 columns
+            const float lv = t < a.T ? 1.0f : 0.0f;
+            // column parameters: lane l holds column col0 + l
+            const float ism_l = a.colpar[col0 + lane], bias_l = a.colpar[a.Npr + col0 + lane];
+            uint32_t sp[8];
+            if (t < a.T) {
+                const uint4* src = reinterpret_cast<const uint4*>(a.Sp + t * a.Nps + a.n_lo + col0);
+                if (((a.n_lo + col0) & 15) == 0) {
+                    const uint4 v0 = src[0], v1 = src[1];
+                    sp[0] = v0.x; sp[1] = v0.y; sp[2] = v0.z; sp[3] = v0.w; sp[4] = v1.x; sp[5] = v1.y; sp[6] = v1.z; sp[7] = v1.w;
+                } else {
+                    const uint8_t* sb = a.Sp + t * a.Nps + a.n_lo + col0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sp[i] = sb[4 * i] | (sb[4 * i + 1] << 8) | (sb[4 * i + 2] << 16) | ((uint32_t)sb[4 * i + 3] << 24);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sp[i] = 0;
+            }
+            mbar_wait(&bar_acc_full[ab], (it >> 1) & 1);
+            tc_fence_after();
+            __half* r1row = a.R + (t < a.T ? t : 0) * a.Npr + col0;
+            __half* r2row = r1row + a.plane;
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {                                      // 8 columns at a time
+                float da[8], db[8];
+                tmem_ld8(t_lane + ab * 256 + sub * 8, da);
+                tmem_ld8(t_lane + ab * 256 + 128 + sub * 8, db);
+                tmem_ld_wait();
+                if (sub == 3) {                                                      // accumulators drained
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
+                }
+                uint32_t h1[4], h2[4];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int cc = sub * 8 + c;
+                    const float ism = __shfl_sync(0xffffffffu, ism_l, cc), bc = __shfl_sync(0xffffffffu, bias_l, cc);
+                    float term = 0.f, r = 0.f;
+                    if (col0 + cc < a.ncols) {                                       // warp-uniform
+                        const float x = fmaf(fmaf(db[c], 1.0f / kLoScale, da[c]), ism, bc);
+                        poisson_terms<NLIN>(x, (float)((sp[cc >> 2] >> ((cc & 3) * 8)) & 0xffu), a.dt, term, r);
+                        term *= lv;
+                        r *= lv;
+                    }
+                    da[c] = term;
+                    db[c] = r;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float ra = db[2 * k] * kRScale, rb = db[2 * k + 1] * kRScale;
+                    const __half2 hi = __floats2half2_rn(ra, rb);
+                    const float2 back = __half22float2(hi);
+                    const __half2 lo = __floats2half2_rn((ra - back.x) * kLoScale, (rb - back.y) * kLoScale);
+                    h1[k] = *reinterpret_cast<const uint32_t*>(&hi);
+                    h2[k] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                if (t < a.T) {
+                    *reinterpret_cast<uint4*>(r1row + sub * 8) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                    *reinterpret_cast<uint4*>(r2row + sub * 8) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+                }
+                // column sums over this warp's 32 bins: lane l ends with column sub*8 + (l & 7)
+                const float sl = warp_column_sums<8>(da, lane);
+                const float sg = warp_column_sums<8>(db, lane);
+                if (lane < 8) {                                                  // slot owned by this (CTA, quarter, lane); zeroed by the host
+                    double* slot = my_part + (int64_t)(col0 + sub * 8 + lane) * 2;
+                    slot[0] += (double)sl;
+                    slot[1] += (double)sg;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gradient GEMM, split over time
+// ---------------------------------------------------------------------------------------------
+struct GemmBwdArgs {
+    int64_t ntt;                       // 128-bin tiles in the recording
+    int64_t tiles_per_split;
+    int Npr; int64_t NBp;              // padded neurons / features (multiples of 128)
+    double* Gp;                        // [splits][NBp][Npr]
+};
+
+__global__ void __launch_bounds__(kGThreads, 1)
+tc_gemm_bwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
+                   const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2, GemmBwdArgs a)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdStages * kBwdStageBytes);
+    uint64_t* bar_full = bars;                       // [3]
+    uint64_t* bar_empty = bars + kBwdStages;         // [3]
+    uint64_t* bar_g_full = bars + 2 * kBwdStages;    // [2]
+    uint64_t* bar_g_empty = bar_g_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_g_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int fb = blockIdx.x, cb = blockIdx.y, split = blockIdx.z;
+    const int64_t tile_lo = (int64_t)split * a.tiles_per_split;
+    const int64_t tile_hi = min(a.ntt, tile_lo + a.tiles_per_split);
+    const int nt = tile_hi > tile_lo ? (int)(tile_hi - tile_lo) : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kBwdStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_g_full[i], 1); mbar_init(&bar_g_empty[i], kGEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int h = 0; h < 2 * nt; ++h) {                       // 64-bin half tiles
+                const int s = h % kBwdStages;
+                mbar_wait(&bar_empty[s], ((h / kBwdStages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&bar_full[s], kBwdStageBytes);
+                unsigned char* st = smem + s * kBwdStageBytes;
+                const int row0 = (int)(tile_lo * kGT) + h * kBwdRows;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    tma_load_2d(st + (0 + c) * kBwdChunkBytes, &mapX1, &bar_full[s], fb * kGF + c * 32, row0);
+                    tma_load_2d(st + (4 + c) * kBwdChunkBytes, &mapX2, &bar_full[s], fb * kGF + c * 32, row0);
+                    tma_load_2d(st + (8 + c) * kBwdChunkBytes, &mapR1, &bar_full[s], cb * kGN + c * 32, row0);
+                    tma_load_2d(st + (12 + c) * kBwdChunkBytes, &mapR2, &bar_full[s], cb * kGN + c * 32, row0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kGF, kGN, 1, 1);   // both operands MN-major
+            for (int i = 0; i < nt; ++i) {
+                const int gb = i & 1;
+                const uint32_t t_a = tmem_base + gb * 256, t_b = t_a + 128;
+                mbar_wait(&bar_g_empty[gb], ((i >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int h = 2 * i + hh, s = h % kBwdStages;
+                    mbar_wait(&bar_full[s], (h / kBwdStages) & 1);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(smem + s * kBwdStageBytes);
+                    const uint64_t dx1 = umma_desc(base, kBwdChunkBytes, 512);
+                    const uint64_t dx2 = umma_desc(base + 4 * kBwdChunkBytes, kBwdChunkBytes, 512);
+                    const uint64_t dr1 = umma_desc(base + 8 * kBwdChunkBytes, kBwdChunkBytes, 512);
+                    const uint64_t dr2 = umma_desc(base + 12 * kBwdChunkBytes, kBwdChunkBytes, 512);
+#pragma unroll
+                    for (int ks = 0; ks < kBwdRows / 16; ++ks) {
+                        const uint32_t acc = (hh | ks) ? 1u : 0u;
+                        const uint64_t off = (uint64_t)(ks * 1024 >> 4);
+                        umma_f16(t_a, dx1 + off, dr1 + off, idesc, acc);          // X1^T r1
+                        umma_f16(t_b, dx2 + off, dr1 + off, idesc, acc);          // X2^T r1
+                        umma_f16(t_b, dx1 + off, dr2 + off, idesc, 1u);           // X1^T r2
+                    }
+                    umma_commit(&bar_empty[s]);
+                }
+                umma_commit(&bar_g_full[gb]);
+            }
+        }
+    } else if (warp >= kGFirstEpi) {
+        const int q = warp & 3;
+        const int cg = (warp - kGFirstEpi) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + cg * kGColsPerWarp;
+        double gacc[kGColsPerWarp];
+#pragma unroll
+        for (int c = 0; c < kGColsPerWarp; ++c) gacc[c] = 0.0;
+        for (int i = 0; i < nt; ++i) {
+            const int gb = i & 1;
+            mbar_wait(&bar_g_full[gb], (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int sub = 0; sub < 4; ++sub) {
+                float ga[8], gbv[8];
+                tmem_ld8(t_lane + gb * 256 + sub * 8, ga);
+                tmem_ld8(t_lane + gb * 256 + 128 + sub * 8, gbv);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 8; ++c) gacc[sub * 8 + c] += (double)fmaf(gbv[c], 1.0f / kLoScale, ga[c]);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_g_empty[gb]);
+        }
+        double* dst = a.Gp + ((int64_t)split * a.NBp + (int64_t)fb * kGF + row) * a.Npr + cb * kGN + cg * kGColsPerWarp;
+#pragma unroll
+        for (int c = 0; c < kGColsPerWarp; ++c) dst[c] = gacc[c];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// final reductions (fixed order)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tc_gemm_final_ll_kernel(const double* __restrict__ part, int nctas, int Npr, int ncols,
+                        double* __restrict__ out_ll, double* __restrict__ out_gb)
+{
+    const int nl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nl >= ncols) return;
+    double l = 0.0, g = 0.0;
+    for (int c = 0; c < nctas * 4; ++c) {
+        l += part[((int64_t)c * Npr + nl) * 2];
+        g += part[((int64_t)c * Npr + nl) * 2 + 1];
+    }
+    out_ll[nl] = l;
+    if (out_gb) out_gb[nl] = g;
+}
+
+__global__ void __launch_bounds__(256)
+tc_gemm_final_G_kernel(const double* __restrict__ Gp, int splits, int64_t NBp, int Npr, int N, int B, int n_lo, int ncols,
+                       const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
+                       double* __restrict__ out_gw)
+{
+    const int64_t NB = (int64_t)N * B;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (j, nl), nl fastest: coalesced partial reads
+    if (idx >= NB * ncols) return;
+    const int64_t j = idx / ncols;
+    const int nl = (int)(idx - j * ncols);
+    double s = 0.0;
+    for (int z = 0; z < splits; ++z) s += Gp[((int64_t)z * NBp + j) * Npr + nl];
+    const int n = n_lo + nl, pre = (int)(j / B);
+    const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
+    const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+    out_gw[(int64_t)nl * NB + j] = (a * ww) * s / ((double)sx[j] * (double)kRScale);
+}
+
+// ---------------------------------------------------------------------------------------------
+int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
+{
+    if (a.T <= 0 || a.ncols <= 0) return PYGLM_B200_OK;
+    int rc = tc_ensure_planes(a, ws, stream);
+    if (rc) return rc;
+    if (!ws.gemm) ws.gemm = new GemmWorkspace();
+    GemmWorkspace& g = *static_cast<GemmWorkspace*>(ws.gemm);
+    const int NB = a.N * a.B;
+    const int nkc = (int)ceil_div(NB, 32);
+    const int Kp = nkc * 32;
+    const int Npr = (int)round_up(a.ncols, kGN);
+    const int ncb = Npr / kGN;
+    const int64_t ntt = ceil_div(a.T, kGT);
+    const int64_t NBp = round_up(NB, kGF);
+    const int nfb = (int)(NBp / kGF);
+    const bool grad = a.out_gw != nullptr;
+
+    if ((rc = ensure((void**)&g.Mp, &g.Mp_elems, (size_t)2 * Npr * Kp, sizeof(__half)))) return rc;
+    if ((rc = ensure((void**)&g.colpar, &g.colpar_elems, (size_t)2 * Npr, sizeof(float)))) return rc;
+    if ((rc = ensure((void**)&g.R, &g.R_elems, (size_t)2 * a.T * Npr, sizeof(__half)))) return rc;
+    const int nctas = (int)std::min<int64_t>(ntt * ncb, ws.num_sms);
+    if ((rc = ensure((void**)&g.part, &g.part_elems, (size_t)nctas * 4 * Npr * 2, sizeof(double)))) return rc;
+
+    PYGLM_CUDA(cudaMemsetAsync(g.part, 0, (size_t)nctas * 4 * Npr * 2 * sizeof(double), stream));
+    tc_gemm_prep_M_kernel<<<Npr, 256, 0, stream>>>(a.w, a.A, a.W, a.bias, ws.sx, a.N, a.B, a.n_lo, a.ncols, Npr, Kp, g.Mp, g.colpar);
+    PYGLM_CUDA(cudaGetLastError());
+
+    const CUtensorMap* xmaps = static_cast<const CUtensorMap*>(ws.tmaps);
+    CUtensorMap mM1, mM2, mR1, mR2;
+    if ((rc = tc_make_map_2d(&mM1, g.Mp, Kp, Npr, Kp, 32, kGN))) return rc;
+    if ((rc = tc_make_map_2d(&mM2, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, 32, kGN))) return rc;
+
+    GemmFwdArgs f{};
+    f.Sp = ws.Sp; f.Nps = ws.Np; f.T = a.T; f.n_lo = a.n_lo; f.ncols = a.ncols; f.Npr = Npr; f.nkc = nkc;
+    f.ntt = ntt; f.ncb = ncb; f.colpar = g.colpar; f.R = g.R; f.plane = (int64_t)a.T * Npr; f.part = g.part; f.dt = (float)a.dt;
+    const int smem_f = kFwdStages * kFwdStageBytes + 256 + 1024;
+    auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP> : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS>;
+    PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    kf<<<nctas, kGThreads, smem_f, stream>>>(xmaps[0], xmaps[1], mM1, mM2, f);
+    PYGLM_CUDA(cudaGetLastError());
+    tc_gemm_final_ll_kernel<<<(unsigned)ceil_div(a.ncols, 256), 256, 0, stream>>>(g.part, nctas, Npr, a.ncols, a.out_ll, a.out_gb);
+    PYGLM_CUDA(cudaGetLastError());
+    if (!grad) return PYGLM_B200_OK;
+
+    if (!g.mapX64_ready) {
+        if ((rc = tc_make_map_2d(&g.mapX64[0], ws.X1, ws.ldp, a.T, ws.ldp, 32, kBwdRows))) return rc;
+        if ((rc = tc_make_map_2d(&g.mapX64[1], ws.X2, ws.ldp, a.T, ws.ldp, 32, kBwdRows))) return rc;
+        g.mapX64_ready = true;
+    }
+    if ((rc = tc_make_map_2d(&mR1, g.R, Npr, a.T, Npr, 32, kBwdRows))) return rc;
+    if ((rc = tc_make_map_2d(&mR2, g.R + (size_t)a.T * Npr, Npr, a.T, Npr, 32, kBwdRows))) return rc;
+    int64_t splits = std::max<int64_t>(1, (int64_t)ws.num_sms / ((int64_t)nfb * ncb));
+    splits = std::min<int64_t>(splits, ntt);
+    const int64_t tps = ceil_div(ntt, splits);
+    splits = ceil_div(ntt, tps);
+    if ((rc = ensure((void**)&g.Gp, &g.Gp_elems, (size_t)splits * NBp * Npr, sizeof(double)))) return rc;
+    GemmBwdArgs b{};
+    b.ntt = ntt; b.tiles_per_split = tps; b.Npr = Npr; b.NBp = NBp; b.Gp = g.Gp;
+    const int smem_b = kBwdStages * kBwdStageBytes + 256 + 1024;
+    PYGLM_CUDA(cudaFuncSetAttribute(tc_gemm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+    dim3 gridb((unsigned)nfb, (unsigned)ncb, (unsigned)splits);
+    tc_gemm_bwd_kernel<<<gridb, kGThreads, smem_b, stream>>>(g.mapX64[0], g.mapX64[1], mR1, mR2, b);
+    PYGLM_CUDA(cudaGetLastError());
+    tc_gemm_final_G_kernel<<<(unsigned)ceil_div((int64_t)NB * a.ncols, 256), 256, 0, stream>>>(
+        g.Gp, (int)splits, NBp, Npr, a.N, a.B, a.n_lo, a.ncols, ws.sx, a.A, a.W, a.out_gw);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
+}  // namespace pyglm

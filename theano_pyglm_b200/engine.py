@@ -196,6 +196,9 @@ class Dataset:
     def path_info(self, path="auto"):
         """What a call with `path` runs on this dataset (used by bench.py's roofline bookkeeping)."""
         use = load_library().pyglm_b200_resolve_path(self._h, _PATHS.get(path, path))
+        if use == PATH_TC and self.N * self.B > 160:
+            return dict(name="tcgen05-gemm-f16split", dtype="f16x2-split/f32-acc/f64-sum", x_passes=2,
+                        launches_per_eval=5, bound="tensor", kernel="tc_gemm_fwd_kernel+tc_gemm_bwd_kernel")
         if use == PATH_TC:
             return dict(name="tcgen05-fused-f16split", dtype="f16x2-split/f32-acc/f64-sum", x_passes=1,
                         launches_per_eval=3, bound="hbm", kernel="tc_fused_kernel")
