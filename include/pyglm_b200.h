@@ -57,6 +57,10 @@ extern "C" {
 /* storage type of the filtered spike train X (reference: float64 `fS`) */
 #define PYGLM_B200_X_F32  0
 #define PYGLM_B200_X_F64  1
+/* planes only: keep just the FP16 split planes of X that the tensor-core path streams (4 bytes per
+ * element); the FP64 path, firing_rate, get_fS and the Gibbs entry points are unavailable.  For
+ * recordings whose FP32 X would not fit next to the planes (configs C4/C5 shards). */
+#define PYGLM_B200_X_PLANES 2
 
 /* arithmetic path for ll / gradient */
 #define PYGLM_B200_PATH_AUTO   0

@@ -141,6 +141,32 @@ def test_tensor_core_path_at_benchmark_size(eng):
     assert rel_err(acc[1], gb_x) < GRAD_RTOL and rel_err(acc[2], gw_x) < GRAD_RTOL
 
 
+@pytest.mark.parametrize("T,N,B", [(3000, 27, 5), (2500, 70, 5)])
+def test_planes_only_dataset(eng, T, N, B, monkeypatch):
+    """x_dtype="planes": only the FP16 split planes are resident (built by a chunked two-pass filter);
+    results equal the regular dataset's bit for bit, and the FP64-side entry points refuse."""
+    p = make_problem(T, N, B, network=True)
+    _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)
+    full = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+    ref = full.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="tc")
+    full.close()
+    for chunk in (None, "1000"):                          # one chunk, then several (chunk boundaries need filter context)
+        if chunk:
+            monkeypatch.setenv("PYGLM_PLANES_CHUNK", chunk)
+        ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="planes")
+        out = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="auto")
+        for o, r in zip(out, ref):
+            assert np.array_equal(o, r)
+        assert np.max(np.abs(out[0] - ll) / np.abs(ll)) < LL_RTOL and rel_err(out[2], gw) < GRAD_RTOL
+        with pytest.raises(eng.EngineError):
+            ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="fp64")
+        with pytest.raises(eng.EngineError):
+            ds.fS()
+        with pytest.raises(eng.EngineError):
+            ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'])
+        ds.close()
+
+
 def test_ll_grad_null_network_is_complete_graph(eng):
     p = make_problem(2000, 6, 5)
     _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)

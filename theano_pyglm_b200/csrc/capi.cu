@@ -94,7 +94,8 @@ int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t
     PYGLM_REQUIRE(R >= 1 && B >= 1 && B <= kMaxBasis, "dataset_create: bad basis shape R=%d B=%d (B<=%d)", R, B, kMaxBasis);
     PYGLM_REQUIRE(S != nullptr || (T + halo) == 0, "dataset_create: S is null");
     PYGLM_REQUIRE(ibasis != nullptr, "dataset_create: ibasis is null");
-    PYGLM_REQUIRE(x_dtype == PYGLM_B200_X_F32 || x_dtype == PYGLM_B200_X_F64, "dataset_create: bad x_dtype %d", x_dtype);
+    PYGLM_REQUIRE(x_dtype == PYGLM_B200_X_F32 || x_dtype == PYGLM_B200_X_F64 || x_dtype == PYGLM_B200_X_PLANES,
+                  "dataset_create: bad x_dtype %d", x_dtype);
     PYGLM_REQUIRE(dt > 0.0, "dataset_create: dt must be positive");
     PYGLM_CUDA(cudaSetDevice(device));
 
@@ -109,18 +110,21 @@ int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return fail(PYGLM_B200_ECUDA); }
 
     const size_t nS = (size_t)(T + halo) * N;
-    const size_t esz = x_dtype == PYGLM_B200_X_F32 ? 4 : 8;
+    const size_t esz = x_dtype == PYGLM_B200_X_F64 ? 8 : 4;
+    const bool planes_only = x_dtype == PYGLM_B200_X_PLANES;
     int rc;
-    if ((rc = ds->S.ensure(nS ? nS : 1)) || (rc = ds->St.ensure((size_t)T * N ? (size_t)T * N : 1)) ||
-        (rc = ds->X.ensure((size_t)T * ds->ldx * esz ? (size_t)T * ds->ldx * esz : 1)) ||
+    if ((rc = ds->S.ensure(nS ? nS : 1)) || (rc = ds->St.ensure(planes_only || (size_t)T * N == 0 ? 1 : (size_t)T * N)) ||
+        (rc = ds->X.ensure(planes_only || (size_t)T * ds->ldx * esz == 0 ? 1 : (size_t)T * ds->ldx * esz)) ||
         (rc = ds->ibasis.ensure((size_t)R * B)))
         return fail(rc);
 #define CK(call) do { cudaError_t e2 = (call); if (e2 != cudaSuccess) { set_error("%s -> %s", #call, cudaGetErrorString(e2)); return fail(PYGLM_B200_ECUDA); } } while (0)
     if (nS) CK(cudaMemcpyAsync(ds->S.p, S, nS, cudaMemcpyHostToDevice, ds->stream));
     CK(cudaMemcpyAsync(ds->ibasis.p, ibasis, (size_t)R * B * sizeof(double), cudaMemcpyHostToDevice, ds->stream));
     CK(cudaMemsetAsync(ds->X.p, 0, ds->X.n, ds->stream));
-    if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->X.p, ds->ldx, x_dtype, ds->stream))) return fail(rc);
-    if ((rc = launch_transpose_spikes(ds->S.p, T, N, halo, ds->St.p, ds->stream))) return fail(rc);
+    if (planes_only) {
+        if (T > 0 && (rc = tc_build_planes_streaming(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->stream))) return fail(rc);
+    } else if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->X.p, ds->ldx, x_dtype, ds->stream))) return fail(rc);
+    if (!planes_only && (rc = launch_transpose_spikes(ds->S.p, T, N, halo, ds->St.p, ds->stream))) return fail(rc);
     CK(cudaStreamSynchronize(ds->stream));
 #undef CK
     *out = ds;
@@ -166,6 +170,7 @@ int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
 {
     DS_GUARD(ds);
     PYGLM_REQUIRE(out != nullptr, "get_fS: out is null");
+    if (ds->x_dtype == PYGLM_B200_X_PLANES) { set_error("get_fS: planes-only dataset keeps no filtered spike train"); return PYGLM_B200_EUNSUPPORTED; }
     const int64_t NB = (int64_t)ds->N * ds->B;
     if (ds->T == 0) return PYGLM_B200_OK;
     PYGLM_CUDA(cudaStreamSynchronize(ds->stream));
@@ -191,6 +196,7 @@ int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
 int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
 {
     DS_GUARD(ds);
+    if (ds->x_dtype == PYGLM_B200_X_PLANES) { set_error("refilter: planes-only dataset"); return PYGLM_B200_EUNSUPPORTED; }
     ds->xt_ready = false;
     return launch_filter(ds->S.p, ds->T, ds->N, ds->halo, ds->ibasis.p, ds->R, ds->B, ds->X.p, ds->ldx,
                          ds->x_dtype, (cudaStream_t)stream);
@@ -199,8 +205,10 @@ int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
 // ------------------------------------------------------------------------------------
 static int resolve_path(const pyglm_b200_dataset* ds, int path, bool need_aux)
 {
-    if (path == PYGLM_B200_PATH_FP64) return PYGLM_B200_PATH_FP64;
-    const bool tc_ok = tc_supported(ds->T, ds->N, ds->B, ds->x_dtype) && !need_aux;
+    const bool planes_only = ds->x_dtype == PYGLM_B200_X_PLANES;
+    if (path == PYGLM_B200_PATH_FP64) return planes_only ? -1 : PYGLM_B200_PATH_FP64;
+    const bool tc_ok = (planes_only || tc_supported(ds->T, ds->N, ds->B, ds->x_dtype)) && !need_aux;
+    if (planes_only) return tc_ok ? PYGLM_B200_PATH_TC : -1;
     if (path == PYGLM_B200_PATH_TC) return tc_ok ? PYGLM_B200_PATH_TC : -1;
     return tc_ok ? PYGLM_B200_PATH_TC : PYGLM_B200_PATH_FP64;
 }
@@ -226,12 +234,12 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     }
     const int use = resolve_path(ds, path, d_act != nullptr || d_lam != nullptr);
     if (use < 0) {
-        set_error("ll_grad: tensor-core path does not support this shape (N=%d B=%d x_dtype=%d)", ds->N, ds->B, ds->x_dtype);
+        set_error("ll_grad: requested path is not available for this dataset (N=%d B=%d x_dtype=%d)", ds->N, ds->B, ds->x_dtype);
         return PYGLM_B200_EUNSUPPORTED;
     }
     if (use == PYGLM_B200_PATH_TC) {
         TcArgs t{};
-        t.X = (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
+        t.X = ds->x_dtype == PYGLM_B200_X_PLANES ? nullptr : (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
         t.B = ds->B; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
         t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
         t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
@@ -372,6 +380,7 @@ int pyglm_b200_gibbs_begin(pyglm_b200_dataset* ds,
     PYGLM_REQUIRE(nlin == PYGLM_B200_NLIN_EXP || nlin == PYGLM_B200_NLIN_SOFTPLUS, "bad nlin %d", nlin);
     PYGLM_REQUIRE(0 <= n_lo && n_lo < n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
     PYGLM_REQUIRE(A && W, "gibbs_begin needs explicit A and W");
+    if (ds->x_dtype == PYGLM_B200_X_PLANES) { set_error("gibbs_begin: planes-only dataset"); return PYGLM_B200_EUNSUPPORTED; }
     cudaStream_t st = ds->stream;
     ds->gibbs_active = false;
     TRY(stage_params(ds, bias, w, A, W, ds->g_bias, ds->g_w, ds->g_A, ds->g_W, st));

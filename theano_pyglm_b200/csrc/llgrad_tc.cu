@@ -606,39 +606,87 @@ int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, 
     return PYGLM_B200_OK;
 }
 
-int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
+// allocate everything the tensor-core path keeps per dataset (planes, scales, padded spikes, maps)
+static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, int B, cudaStream_t stream)
 {
-    if (ws.planes_ready) return PYGLM_B200_OK;
-    const int NB = a.N * a.B;
+    const int NB = N * B;
     ws.ldp = round_up(NB, 8);
     int dev = 0;
     PYGLM_CUDA(cudaGetDevice(&dev));
     PYGLM_CUDA(cudaDeviceGetAttribute(&ws.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t plane = (size_t)a.T * ws.ldp;
+    const size_t plane = (size_t)T * ws.ldp;
     PYGLM_CUDA(cudaMalloc(&ws.X1, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.X2, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.sx, NB * sizeof(float)));
     PYGLM_CUDA(cudaMalloc(&ws.colmax, NB * sizeof(unsigned)));
     PYGLM_CUDA(cudaMalloc(&ws.Mp, (size_t)2 * kNcol * kMaxChunks * kChunkF * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.colpar, 2 * kNcol * sizeof(float)));
-    ws.Np = (int)round_up(a.N, 32) + 32;          // slack: a column group may start anywhere below N
-    PYGLM_CUDA(cudaMalloc(&ws.Sp, (size_t)a.T * ws.Np));
-    PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)a.T * ws.Np, stream));
-    PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, a.S + (size_t)a.halo * a.N, a.N, a.N, a.T, cudaMemcpyDeviceToDevice, stream));
+    ws.Np = (int)round_up(N, 32) + 32;            // slack: a column group may start anywhere below N
+    PYGLM_CUDA(cudaMalloc(&ws.Sp, (size_t)T * ws.Np));
+    PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)T * ws.Np, stream));
+    PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
     PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, NB * sizeof(unsigned), stream));
+    ws.tmaps = malloc(2 * sizeof(CUtensorMap));
+    if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
+    CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
+    int rc;
+    if ((rc = tc_make_map_2d(&maps[0], ws.X1, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
+    if ((rc = tc_make_map_2d(&maps[1], ws.X2, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
+    return PYGLM_B200_OK;
+}
+
+int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
+{
+    if (ws.planes_ready) return PYGLM_B200_OK;
+    if (a.X == nullptr) { set_error("tensor-core planes were not built for this dataset"); return PYGLM_B200_ESTATE; }
+    const int NB = a.N * a.B;
+    int rc = alloc_planes(ws, a.S, a.T, a.N, a.halo, a.B, stream);
+    if (rc) return rc;
     dim3 gmax((unsigned)std::min<int64_t>(a.T, 148 * 16), (unsigned)ceil_div(NB, 128));
     tc_colmax_kernel<<<gmax, 128, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.colmax);
     PYGLM_CUDA(cudaGetLastError());
     tc_scales_kernel<<<(unsigned)ceil_div(NB, 128), 128, 0, stream>>>(ws.colmax, NB, ws.sx);
     PYGLM_CUDA(cudaGetLastError());
-    tc_split_X_kernel<<<(unsigned)ceil_div((int64_t)plane, 256), 256, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.sx, ws.X1, ws.X2, ws.ldp);
+    tc_split_X_kernel<<<(unsigned)ceil_div((int64_t)a.T * ws.ldp, 256), 256, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.sx, ws.X1, ws.X2, ws.ldp);
     PYGLM_CUDA(cudaGetLastError());
-    ws.tmaps = malloc(2 * sizeof(CUtensorMap));
-    if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
-    CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
-    int rc;
-    if ((rc = tc_make_map_2d(&maps[0], ws.X1, ws.ldp, a.T, ws.ldp, kChunkF, kTileT))) return rc;
-    if ((rc = tc_make_map_2d(&maps[1], ws.X2, ws.ldp, a.T, ws.ldp, kChunkF, kTileT))) return rc;
+    ws.planes_ready = true;
+    return PYGLM_B200_OK;
+}
+
+// Planes-only ingest (PYGLM_B200_X_PLANES): the FP32 filtered spike train is never resident.  The filter runs
+// twice over time chunks through one scratch buffer: pass 1 finds the per-feature scales, pass 2 splits.
+int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
+                              int R, int B, cudaStream_t stream)
+{
+    const int NB = N * B;
+    const int64_t ldx = round_up(NB, 4);
+    int rc = alloc_planes(ws, S, T, N, halo, B, stream);
+    if (rc) return rc;
+    int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(T, ((int64_t)256 << 20) / (ldx * 4)));   // ~256 MB scratch
+    if (const char* env = getenv("PYGLM_PLANES_CHUNK")) chunk = std::max<int64_t>(1, atoll(env));          // tests: force several chunks
+    float* scratch = nullptr;
+    PYGLM_CUDA(cudaMalloc(&scratch, (size_t)chunk * ldx * sizeof(float)));
+    PYGLM_CUDA(cudaMemsetAsync(scratch, 0, (size_t)chunk * ldx * sizeof(float), stream));
+    for (int pass = 0; pass < 2 && rc == PYGLM_B200_OK; ++pass) {
+        for (int64_t r0 = 0; r0 < T && rc == PYGLM_B200_OK; r0 += chunk) {
+            const int64_t nt = std::min(chunk, T - r0);
+            const int64_t h = std::min<int64_t>(R, halo + r0);                 // left context available for this chunk
+            rc = launch_filter(S + (halo + r0 - h) * N, nt, N, (int)h, d_ibasis, R, B, scratch, ldx, PYGLM_B200_X_F32, stream);
+            if (rc) break;
+            if (pass == 0) {
+                dim3 gmax((unsigned)std::min<int64_t>(nt, 148 * 16), (unsigned)ceil_div(NB, 128));
+                tc_colmax_kernel<<<gmax, 128, 0, stream>>>(scratch, nt, NB, ldx, ws.colmax);
+            } else {
+                tc_split_X_kernel<<<(unsigned)ceil_div(nt * ws.ldp, 256), 256, 0, stream>>>(
+                    scratch, nt, NB, ldx, ws.sx, ws.X1 + r0 * ws.ldp, ws.X2 + r0 * ws.ldp, ws.ldp);
+            }
+            if (cudaGetLastError() != cudaSuccess) { set_error("planes-only ingest: kernel launch failed"); rc = PYGLM_B200_ECUDA; }
+        }
+        if (pass == 0 && rc == PYGLM_B200_OK) tc_scales_kernel<<<(unsigned)ceil_div(NB, 128), 128, 0, stream>>>(ws.colmax, NB, ws.sx);
+    }
+    cudaStreamSynchronize(stream);
+    cudaFree(scratch);
+    if (rc) return rc;
     ws.planes_ready = true;
     return PYGLM_B200_OK;
 }

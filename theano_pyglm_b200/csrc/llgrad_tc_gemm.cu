@@ -435,15 +435,24 @@ __global__ void __launch_bounds__(256)
 tc_gemm_final_ll_kernel(const double* __restrict__ part, int nctas, int Npr, int ncols,
                         double* __restrict__ out_ll, double* __restrict__ out_gb)
 {
-    const int nl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (nl >= ncols) return;
+    // one block per column: 256 threads stride over the (CTA, quarter) slots, then a fixed-order tree
+    __shared__ double sl[256], sg[256];
+    const int nl = blockIdx.x;
     double l = 0.0, g = 0.0;
-    for (int c = 0; c < nctas * 4; ++c) {
+    for (int c = threadIdx.x; c < nctas * 4; c += 256) {
         l += part[((int64_t)c * Npr + nl) * 2];
         g += part[((int64_t)c * Npr + nl) * 2 + 1];
     }
-    out_ll[nl] = l;
-    if (out_gb) out_gb[nl] = g;
+    sl[threadIdx.x] = l; sg[threadIdx.x] = g;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) { sl[threadIdx.x] += sl[threadIdx.x + off]; sg[threadIdx.x] += sg[threadIdx.x + off]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out_ll[nl] = sl[0];
+        if (out_gb) out_gb[nl] = sg[0];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -505,7 +514,7 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
     kf<<<nctas, kGThreads, smem_f, stream>>>(xmaps[0], xmaps[1], mM1, mM2, f);
     PYGLM_CUDA(cudaGetLastError());
-    tc_gemm_final_ll_kernel<<<(unsigned)ceil_div(a.ncols, 256), 256, 0, stream>>>(g.part, nctas, Npr, a.ncols, a.out_ll, a.out_gb);
+    tc_gemm_final_ll_kernel<<<(unsigned)a.ncols, 256, 0, stream>>>(g.part, nctas, Npr, a.ncols, a.out_ll, a.out_gb);
     PYGLM_CUDA(cudaGetLastError());
     if (!grad) return PYGLM_B200_OK;
 

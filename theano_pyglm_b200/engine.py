@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libpyglm_b200.so")
 
 NLIN_EXP, NLIN_SOFTPLUS = 0, 1
-X_F32, X_F64 = 0, 1
+X_F32, X_F64, X_PLANES = 0, 1, 2
 PATH_AUTO, PATH_FP64, PATH_TC = 0, 1, 2
 _PATHS = {"auto": PATH_AUTO, "fp64": PATH_FP64, "tc": PATH_TC}
 _NLINS = {"exp": NLIN_EXP, "explinear": NLIN_SOFTPLUS, "softplus": NLIN_SOFTPLUS}
@@ -126,7 +126,8 @@ class Dataset:
         self.dt = float(dt)
         self.halo = int(halo)
         self.device = int(device)
-        self.x_dtype = X_F64 if x_dtype in ("f64", X_F64, np.float64) else X_F32
+        self.x_dtype = (X_F64 if x_dtype in ("f64", X_F64, np.float64) else
+                        X_PLANES if x_dtype in ("planes", X_PLANES) else X_F32)
         self.h2d_bytes = S.nbytes + ibasis.nbytes
         h = C.c_void_p()
         _check(lib.pyglm_b200_dataset_create(_ptr(S), self.T, self.halo, self.N, self.dt, _ptr(ibasis),
