@@ -449,18 +449,45 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             if (lane == 0) mbar_arrive(bar_fwd_empty);
 
             // act, Poisson term, residual (padded columns have M = 0, bias = 0 and are ignored later)
+            float xs[kColsPerWarp];
+            float xmin = 3.0e38f;
 #pragma unroll
             for (int c = 0; c < kColsPerWarp; ++c) {
                 const float2 cp = cpar[c0 + c];
-                float term = 0.f, r = 0.f;
-                if (c0 + c < a.ncols) {                  // warp-uniform: padded columns cost nothing
-                    const float x = fmaf(fmaf(d1[c] + d2[c], 1.0f / kLoScale, d0[c]), cp.x, cp.y);
-                    poisson_terms<NLIN>(x, (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu), a.dt, term, r);
-                    r *= lv;                             // bins past the end of the recording contribute nothing
-                    pll[c] = fmaf(lv, term, pll[c]);
-                    pgb[c] += r;
+                xs[c] = fmaf(fmaf(d1[c] + d2[c], 1.0f / kLoScale, d0[c]), cp.x, cp.y);
+                if (c0 + c < a.ncols) xmin = fminf(xmin, xs[c]);
+            }
+            const float dtl = a.dt * lv;                 // bins past the end of the recording contribute nothing
+            if (NLIN == PYGLM_B200_NLIN_SOFTPLUS && __all_sync(0xffffffffu, xmin > 17.5f)) {
+                // every activation of this warp's block is in the regime where log(1+e^x) rounds to x and
+                // sigmoid(x) to 1 in FP32 (e^-17.5 < 2^-25): straight-line code, no divergence, two MUFU per bin
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) {
+                    float r = 0.f;
+                    if (c0 + c < a.ncols) {              // warp-uniform: padded columns cost nothing
+                        const float x = xs[c];
+                        const float sv = (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu);     // 0 past the end of the recording
+                        float lg, rc;
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(x));
+                        pll[c] += fmaf(sv * 0.69314718f, lg, -dtl * x);                        // -dt*lam + s*log(lam)
+                        r = fmaf(sv, rc, -dtl);                                                 // (s/lam - dt) * 1
+                        pgb[c] += r;
+                    }
+                    d1[c] = r;
                 }
-                d1[c] = r;
+            } else {
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) {
+                    float term = 0.f, r = 0.f;
+                    if (c0 + c < a.ncols) {
+                        poisson_terms<NLIN>(xs[c], (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu), a.dt, term, r);
+                        r *= lv;
+                        pll[c] = fmaf(lv, term, pll[c]);
+                        pgb[c] += r;
+                    }
+                    d1[c] = r;
+                }
             }
             // residual planes back to smem as the gradient MMA's B operand (MN-major, 64B swizzle)
             mbar_wait(&bar_r_free[b], ph ^ 1);
@@ -535,20 +562,21 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
 }
 
 // Sum the per-CTA partials in a fixed order and undo the scales.  One block per feature row j
-// (plus one for ll / g_bias): 32 columns x 8 slices of the CTA range, combined slice 0..7.
-__global__ void __launch_bounds__(256)
+// (plus one for ll / g_bias): 32 columns x 32 slices of the CTA range, combined slice 0..31.
+constexpr int kFinalSlices = 32;
+__global__ void __launch_bounds__(32 * kFinalSlices)
 tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int B, int n_lo, int ncols,
                 const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
                 double* __restrict__ out_ll, double* __restrict__ out_gb, double* __restrict__ out_gw)
 {
-    __shared__ double sh[8][2 * kNcol];
+    __shared__ double sh[kFinalSlices][2 * kNcol];
     const int64_t NB = (int64_t)N * B;
     const int64_t per_cta = (int64_t)nmt * 128 * kNcol + 2 * kNcol;
     const int nl = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const bool tail = blockIdx.x == NB;                      // the ll / g_bias block
     const int64_t off = tail ? (int64_t)nmt * 128 * kNcol : (int64_t)blockIdx.x * kNcol;
     double s0 = 0.0, s1 = 0.0;
-    for (int c = slice; c < nctas; c += 8) {
+    for (int c = slice; c < nctas; c += kFinalSlices) {
         s0 += part[c * per_cta + off + nl];
         if (tail) s1 += part[c * per_cta + off + kNcol + nl];
     }
@@ -557,7 +585,7 @@ tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int 
     __syncthreads();
     if (slice != 0 || nl >= ncols) return;
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { s0 += sh[k][nl]; s1 += sh[k][kNcol + nl]; }
+    for (int k = 1; k < kFinalSlices; ++k) { s0 += sh[k][nl]; s1 += sh[k][kNcol + nl]; }
     if (tail) {
         out_ll[nl] = s0;
         if (out_gb) out_gb[nl] = s1;                         // residual column sums are carried unscaled
@@ -753,7 +781,7 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
                 }
             }
         }
-        tc_final_kernel<<<(unsigned)(NB + 1), 256, 0, stream>>>(
+        tc_final_kernel<<<(unsigned)(NB + 1), 32 * kFinalSlices, 0, stream>>>(
             ws.part, nctas, nmt, a.N, a.B, n_lo, nc, ws.sx, a.A, a.W,
             a.out_ll + c0, a.out_gb ? a.out_gb + c0 : nullptr, a.out_gw ? a.out_gw + (int64_t)c0 * NB : nullptr);
         PYGLM_CUDA(cudaGetLastError());
