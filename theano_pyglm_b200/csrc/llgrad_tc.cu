@@ -172,6 +172,7 @@ struct TcKernelArgs {
     int nfeat;                     // N*B real features
     int flush;                     // fold the TMEM gradient accumulators into FP64 every `flush` tiles
     int debug;                     // timing experiments only (PYGLM_TC_DEBUG): skip phases
+    unsigned producer_sleep_ns;
     long long* trace;              // optional [3][32][4] clock64 stamps of CTA 0 (PYGLM_TC_TRACE)
 };
 
@@ -211,23 +212,24 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
     unsigned char* sM = smem + L.off_M;               // per chunk: [M1 rows 0..31][M2 rows 0..31], 64 B rows
     unsigned char* sR = smem + L.off_R;               // buffer b: [r1 plane][r2 plane]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* bar_full = bars;            // [2] TMA landed
-    uint64_t* bar_empty = bars + 2;       // [2] X stage consumed by the gradient MMA
-    uint64_t* bar_fwd_full = bars + 4;    // activation accumulators ready
-    uint64_t* bar_fwd_empty = bars + 6;   // ... drained by the epilogue
-    uint64_t* bar_r_ready = bars + 8;     // [2] residual planes written
-    uint64_t* bar_r_free = bars + 10;     // [2] ... consumed by the gradient MMA
-    uint64_t* bar_g_full = bars + 12;     // [2] gradient accumulators of a tile complete
-    uint64_t* bar_g_empty = bars + 14;    // [2] ... folded into FP64
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-    float* sPar = reinterpret_cast<float*>(bars + 18);   // [32] x (1/sm, bias)
+    uint64_t* bar_full = bars;            // [2 stages][5 chunks] TMA landed, per 32-feature chunk (both planes)
+    uint64_t* bar_empty = bars + 10;      // [2 stages][2 groups] chunks 0-3 / chunk 4 consumed by the gradient MMA
+    uint64_t* bar_fwd_full = bars + 14;   // activation accumulators ready
+    uint64_t* bar_fwd_empty = bars + 15;  // ... drained by the epilogue
+    uint64_t* bar_r_ready = bars + 16;    // [2] residual planes written
+    uint64_t* bar_r_free = bars + 18;     // [2] ... consumed by the gradient MMA
+    uint64_t* bar_g_full = bars + 20;     // [2] gradient accumulators of a tile complete
+    uint64_t* bar_g_empty = bars + 22;    // [2] ... folded into FP64
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    float* sPar = reinterpret_cast<float*>(bars + 26);   // [32] x (1/sm, bias)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nch = a.nch;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1);
+            for (int c = 0; c < kMaxChunks; ++c) mbar_init(&bar_full[i * kMaxChunks + c], 1);
+            mbar_init(&bar_empty[2 * i], 1); mbar_init(&bar_empty[2 * i + 1], 1);
             mbar_init(&bar_g_full[i], 1); mbar_init(&bar_g_empty[i], kEpiWarps);
             mbar_init(&bar_r_ready[i], kEpiWarps); mbar_init(&bar_r_free[i], 1);
         }
@@ -273,15 +275,20 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
         if (lane == 0) {
             for (int it = 0; it < ntl; ++it) {
                 const int s = it & 1;
-                mbar_wait(&bar_empty[s], ((it >> 1) & 1) ^ 1);
-                if ((a.debug & 16) && it >= 2) { mbar_arrive(&bar_full[s]); continue; }
-                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
-                mbar_arrive_expect_tx(&bar_full[s], (uint32_t)L.stage_bytes);
+                // Chunks land on their own barriers so the forward MMA starts on chunk 0 while chunk 4 is still in
+                // flight, and chunks 0-3 are refilled as soon as the first gradient tile has consumed them.
                 unsigned char* st = smem + s * L.stage_bytes;
                 const int row0 = (int)((first + (int64_t)it * step) * kTileT);
+                const uint32_t par = ((it >> 1) & 1) ^ 1;
                 for (int c = 0; c < nch; ++c) {
-                    tma_load_2d(st + c * kChunkBytes, &tmap1, &bar_full[s], c * kChunkF, row0);
-                    tma_load_2d(st + (nch + c) * kChunkBytes, &tmap2, &bar_full[s], c * kChunkF, row0);
+                    if (c == 0) mbar_wait_relaxed(&bar_empty[2 * s], par, a.producer_sleep_ns);
+                    if (c == 4) mbar_wait_relaxed(&bar_empty[2 * s + 1], par, a.producer_sleep_ns);
+                    uint64_t* fb = &bar_full[s * kMaxChunks + c];
+                    if ((a.debug & 16) && it >= 2) { mbar_arrive(fb); continue; }
+                    if (c == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
+                    mbar_arrive_expect_tx(fb, 2 * kChunkBytes);
+                    tma_load_2d(st + c * kChunkBytes, &tmap1, fb, c * kChunkF, row0);
+                    tma_load_2d(st + (nch + c) * kChunkBytes, &tmap2, fb, c * kChunkF, row0);
                 }
             }
         }
@@ -295,12 +302,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             for (int it = 0; it < ntl; ++it) {
                 const int s = it & 1;
                 const uint32_t sX1 = smem_u32(smem + s * L.stage_bytes), sX2 = sX1 + nch * kChunkBytes;
-                mbar_wait(&bar_full[s], (it >> 1) & 1);
                 mbar_wait(bar_fwd_empty, (it & 1) ^ 1);
-                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
-                tc_fence_after();
                 uint64_t dx1 = umma_desc(sX1, 16, 512), dx2 = umma_desc(sX2, 16, 512), dm = umma_desc(sMb, 16, 512);
-                for (int c = 0; c < ((a.debug & 1) ? 0 : nch); ++c) {
+                for (int c = 0; c < nch; ++c) {
+                    mbar_wait(&bar_full[s * kMaxChunks + c], (it >> 1) & 1);
+                    if (c == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
+                    tc_fence_after();
+                    if (a.debug & 1) continue;
                     umma_f16(t_f, dx1, dm, idesc_f64, c ? 1u : 0u);            // X1 [M1 | M2], features 0..15 of the chunk
                     umma_f16(t_f + 64, dx2, dm, idesc_f32, c ? 1u : 0u);       // X2 M1
                     umma_f16(t_f, dx1 + 2, dm + 2, idesc_f64, 1u);             // features 16..31 (+32 bytes)
@@ -324,6 +332,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 const int s = j & 1, b = j & 1, gb = j & 1;
                 const uint32_t sX1 = smem_u32(smem + s * L.stage_bytes), sX2 = sX1 + nch * kChunkBytes;
                 const uint32_t sR1 = smem_u32(sR + b * 2 * kRBytes);
+                for (int c = 0; c < nch; ++c) mbar_wait(&bar_full[s * kMaxChunks + c], (j >> 1) & 1);   // landed long ago
                 mbar_wait(&bar_r_ready[b], (j >> 1) & 1);
                 mbar_wait(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
                 if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
@@ -341,8 +350,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                         umma_f16(t_g, dx1_0 + off, dr0 + off, idesc_b64, acc);       // X1^T [r1 | r2]
                         umma_f16(t_g + 64, dx2_0 + off, dr0 + off, idesc_b32, acc);  // X2^T r1
                     }
+                    if (mt == 0) umma_commit(&bar_empty[2 * s]);                 // chunks 0-3 can be refilled
                 }
-                umma_commit(&bar_empty[s]);
+                if (a.debug & 2) umma_commit(&bar_empty[2 * s]);
+                umma_commit(&bar_empty[2 * s + 1]);
                 umma_commit(&bar_r_free[b]);
                 umma_commit(&bar_g_full[gb]);
                 if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 3] = clock64();
@@ -369,16 +380,21 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             float g0[kColsPerWarp], g1[kColsPerWarp], g2[kColsPerWarp];
             const int gb = j & 1;
             const uint32_t t_g = t_lane + kGradBase + gb * kGradBuf;
+            const bool trf = a.trace && blockIdx.x == 0 && warp == kFirstEpiWarp + (a.debug >> 8) && lane == 0 && j < 31;
+            if (trf) a.trace[1536 + j * 4 + 0] = clock64();
             mbar_wait(&bar_g_full[gb], (j >> 1) & 1);
+            if (trf) a.trace[1536 + j * 4 + 1] = clock64();
             tc_fence_after();
             if (!(a.debug & 8)) {
+                const bool tile1 = a.nmt > 1 && 128 + q * 32 < NBreal;         // warp-uniform: rows with real features
                 tmem_ld<kColsPerWarp>(t_g + 0, g0);
                 tmem_ld<kColsPerWarp>(t_g + 32, g1);
                 tmem_ld<kColsPerWarp>(t_g + 64, g2);
                 tmem_ld_wait();
+                if (trf) a.trace[1536 + j * 4 + 2] = clock64();
 #pragma unroll
                 for (int c = 0; c < kColsPerWarp; ++c) gacc[c] += (double)fmaf(g1[c] + g2[c], 1.0f / kLoScale, g0[c]);
-                if (a.nmt > 1 && 128 + q * 32 < NBreal) {                    // warp-uniform
+                if (tile1) {
                     tmem_ld<kColsPerWarp>(t_g + kFwdCols + 0, g0);
                     tmem_ld<kColsPerWarp>(t_g + kFwdCols + 32, g1);
                     tmem_ld<kColsPerWarp>(t_g + kFwdCols + 64, g2);
@@ -390,6 +406,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_g_empty[gb]);
+            if (trf) a.trace[1536 + j * 4 + 3] = clock64();
         };
         double ll_acc = 0.0, gb_acc = 0.0;               // lane l accumulates column c0 + (l % kColsPerWarp)
         const int sw = (row >> 1) & 3;
@@ -434,7 +451,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
 #pragma unroll
             for (int i = 0; i < kSpWords; ++i) sb[i] = sb_next[i];
             load_spikes(it + 1, sb_next);
-            const bool tr = a.trace && blockIdx.x == 0 && warp == kFirstEpiWarp && lane == 0 && it < 32;
+            const bool tr = a.trace && blockIdx.x == 0 && warp == kFirstEpiWarp + (a.debug >> 8) && lane == 0 && it < 32;
             if (tr) a.trace[(2 * 32 + it) * 4 + 0] = clock64();
             mbar_wait(bar_fwd_full, it & 1);
             if (tr) a.trace[(2 * 32 + it) * 4 + 1] = clock64();
@@ -444,6 +461,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             tmem_ld<kColsPerWarp>(t_lane + 32, d1);
             tmem_ld<kColsPerWarp>(t_lane + 64, d2);
             tmem_ld_wait();
+            if (tr) a.trace[1408 + it * 4 + 0] = clock64();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_fwd_empty);
@@ -490,7 +508,9 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 }
             }
             // residual planes back to smem as the gradient MMA's B operand (MN-major, 64B swizzle)
+            if (tr) a.trace[1408 + it * 4 + 1] = clock64();
             mbar_wait(&bar_r_free[b], ph ^ 1);
+            if (tr) a.trace[1408 + it * 4 + 2] = clock64();
             {
                 unsigned char* p1 = sR + b * 2 * kRBytes + row * 64;
                 unsigned char* p2 = p1 + kRBytes;
@@ -754,17 +774,18 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         k.Sp = ws.Sp; k.Np = ws.Np;
         k.Mp = ws.Mp; k.Kp = Kp; k.colpar = ws.colpar; k.part = ws.part;
         { const char* dbg = getenv("PYGLM_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
+        { const char* sl = getenv("PYGLM_TC_SLEEP"); k.producer_sleep_ns = sl ? (unsigned)atoi(sl) : 0u; }
         { const char* fl = getenv("PYGLM_TC_FLUSH"); k.flush = fl ? std::max(1, atoi(fl)) : kFlushTiles; }
         static long long* d_trace = nullptr;
         const bool want_trace = getenv("PYGLM_TC_TRACE") != nullptr;
-        if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, (384 + 32 * 32) * sizeof(long long)));
+        if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, (384 + 32 * 32 + 32 * 16) * sizeof(long long)));
         k.trace = want_trace ? d_trace : nullptr;
         kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], k);
         PYGLM_CUDA(cudaGetLastError());
         if (want_trace) {
             static int dumped = 0;
             if (dumped++ == 5) {
-                long long h[384 + 32 * 32];
+                long long h[384 + 32 * 32 + 32 * 16];
                 PYGLM_CUDA(cudaStreamSynchronize(stream));
                 PYGLM_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
                 const long long t0 = h[0];
@@ -774,6 +795,13 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
                             h[(32 + i) * 4 + 0] - t0, h[(32 + i) * 4 + 1] - t0, h[(32 + i) * 4 + 2] - t0, h[(32 + i) * 4 + 3] - t0,
                             h[(64 + i) * 4 + 0] - t0, h[(64 + i) * 4 + 1] - t0, h[(64 + i) * 4 + 2] - t0, h[(64 + i) * 4 + 3] - t0);
                 }
+                for (int i = 8; i < 14; ++i)
+                    fprintf(stderr, "epi tile %d: fwd_full %lld ld_done +%lld math_done +%lld r_free +%lld r_ready +%lld iter_end +%lld\n", i,
+                            h[(64 + i) * 4 + 1] - t0, h[1408 + i * 4 + 0] - h[(64 + i) * 4 + 1], h[1408 + i * 4 + 1] - h[1408 + i * 4 + 0],
+                            h[1408 + i * 4 + 2] - h[1408 + i * 4 + 1], h[(64 + i) * 4 + 2] - h[1408 + i * 4 + 2], h[(64 + i) * 4 + 3] - h[(64 + i) * 4 + 2]);
+                for (int i = 8; i < 12; ++i)
+                    fprintf(stderr, "fold tile %d: start %lld wait +%lld ld +%lld rest +%lld\n", i, h[1536 + i * 4] - t0,
+                            h[1536 + i * 4 + 1] - h[1536 + i * 4], h[1536 + i * 4 + 2] - h[1536 + i * 4 + 1], h[1536 + i * 4 + 3] - h[1536 + i * 4 + 2]);
                 for (int i = 10; i < 13; ++i) {
                     fprintf(stderr, "r_ready arrivals tile %d:", i);
                     for (int w = kFirstEpiWarp; w < kFirstEpiWarp + kEpiWarps; ++w) fprintf(stderr, " %lld", h[384 + w * 32 + i] - t0);

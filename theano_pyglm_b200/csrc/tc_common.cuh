@@ -79,6 +79,18 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)kSw64 << 61;
     return d;
 }
+// Wait used by warps whose waits are long (TMA producer): back off between polls so the spinning lane
+// does not compete with the epilogue warps of its scheduler for issue / MIO slots.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D=F32 [4,6)=1, A/B=F16 (0),
 // a_major [15], b_major [16] (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N, int a_mn, int b_mn)
