@@ -48,8 +48,19 @@ constexpr int kStages = 2;
 constexpr int kColGroups = PYGLM_TC_COLGROUPS;  // column groups: the epilogue runs 4 * kColGroups warps
 constexpr int kColsPerWarp = kNcol / kColGroups;
 constexpr int kEpiWarps = 4 * kColGroups;
-constexpr int kFirstEpiWarp = 3;                // warp 0: TMA, warp 1: forward MMA, warp 2: gradient MMA
+#ifndef PYGLM_TC_ROLE_BASE
+#define PYGLM_TC_ROLE_BASE 1
+#endif
+// Warp roles.  Default: epilogue warps 0..15 first, then an idle warp and the TMA producer / forward-MMA / gradient-MMA
+// issuers on schedulers 1..3, so no spinning role warp shares a scheduler slot pattern with lane quarter 0 (measured:
+// with the role warps first, the quarter-0 epilogue warps trailed the others by ~1.3k cycles per tile).
+#if PYGLM_TC_ROLE_BASE == 0
+constexpr int kFirstEpiWarp = 3, kProducerWarp = 0, kFwdWarp = 1, kBwdWarp = 2;
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+#else
+constexpr int kFirstEpiWarp = 0, kProducerWarp = kEpiWarps + 1, kFwdWarp = kEpiWarps + 2, kBwdWarp = kEpiWarps + 3;
+constexpr int kThreads = 32 * (kEpiWarps + 4);
+#endif
 constexpr int kFlushTiles = 8;              // TMEM gradient accumulators are folded into FP64 every 8 tiles
 
 void TcWorkspace::release()
@@ -236,7 +247,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
         mbar_init(bar_fwd_full, 1); mbar_init(bar_fwd_empty, kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemAlloc) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -270,7 +281,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
     const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;   // tiles of this CTA
     const int F = a.flush;
 
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             for (int it = 0; it < ntl; ++it) {
@@ -292,7 +303,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kFwdWarp) {
         // ================================ forward MMA issuer ==========================
         if (lane == 0) {
             constexpr uint32_t idesc_f64 = umma_idesc(128, 64, 0, 0);     // A: X K-major,  B: [M1|M2] K-major
@@ -319,7 +330,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 1] = clock64();
             }
         }
-    } else if (warp == 2) {
+    } else if (warp == kBwdWarp) {
         // ================================ gradient MMA issuer =========================
         // Its own warp, so a forward MMA waiting for data never delays a gradient MMA (or the reverse).
         // The TMEM accumulators do not keep full FP32 precision over long sums (measured: the gradient
@@ -359,7 +370,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 3] = clock64();
             }
         }
-    } else {
+    } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
         // ================================ epilogue warps ==============================
         // kEpiWarps warps; warp w owns TMEM lane quarter q = w & 3 (hardware restriction) and the
         // column group cg of kColsPerWarp postsynaptic columns.
@@ -576,7 +587,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == kProducerWarp) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemAlloc) : "memory");
     }
 }
