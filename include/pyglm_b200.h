@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PYGLM_B200_ABI_VERSION 1
+#define PYGLM_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PYGLM_B200_API __attribute__((visibility("default")))
@@ -90,7 +90,31 @@ PYGLM_B200_API int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_
                               const double* ibasis, int32_t R, int32_t B,
                               int32_t x_dtype, int32_t device,
                               pyglm_b200_dataset** out);
+
+/* Same, with F = D_stim*B_stim filtered-stimulus features appended behind the N*B spike-history
+ * features of X (F = 0, fstim = NULL: identical to dataset_create).
+ * Replaces BasisStimulus.preprocess_data / set_data (components/bkgd.py:122-157): fstim is
+ * data['fstim'], host float64 [T][F] (no halo rows), I_stim = fstim @ w_stim (bkgd.py:81).
+ * With F > 0 every parameter row `w` and gradient row `out_g_w` below has N*B + F entries: the
+ * N*B impulse weights followed by x['glms'][n]['bkgd']['w_stim']; stimulus features are not
+ * masked by A / W.  Not available for PYGLM_B200_X_PLANES datasets. */
+PYGLM_B200_API int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, int32_t N, double dt,
+                              const double* ibasis, int32_t R, int32_t B,
+                              const double* fstim, int32_t F,
+                              int32_t x_dtype, int32_t device,
+                              pyglm_b200_dataset** out);
 PYGLM_B200_API int pyglm_b200_dataset_destroy(pyglm_b200_dataset* ds);
+
+/* number of stimulus features F of a dataset (0 for dataset_create) */
+PYGLM_B200_API int32_t pyglm_b200_dataset_num_stim(const pyglm_b200_dataset* ds);
+
+/* Dense causal basis projection of a real-valued signal (the stimulus):
+ *   out[t][d*B+b] = sum_{k=1..R} ibasis[k-1][b] * stim[t-k][d]
+ * == convolve_with_basis(stim, ibasis) flattened as in bkgd.py:145-154 (utils/basis.py:201-236).
+ * stim host float64 [T][D], ibasis host float64 [R][B], out host float64 [T][D*B]. */
+PYGLM_B200_API int pyglm_b200_filter_dense(const double* stim, int64_t T, int32_t D,
+                            const double* ibasis, int32_t R, int32_t B,
+                            int32_t device, double* out);
 
 /* shape query: any pointer may be NULL */
 PYGLM_B200_API int pyglm_b200_dataset_info(const pyglm_b200_dataset* ds, int64_t* T, int32_t* N, int32_t* B,
@@ -117,13 +141,14 @@ PYGLM_B200_API int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* str
  *      I_imp = sum_b ir[t,pre,b] * w[pre,b]                   (impulse.py:58 / :308).
  *
  * bias  float64 [N]              x['glms'][n]['bias']['bias'][0]
- * w     float64 [N][N*B]         row n = x['glms'][n]['imp']['w_ir'] (pre-major, basis fastest);
+ * w     float64 [N][N*B+F]       row n = x['glms'][n]['imp']['w_ir'] (pre-major, basis fastest), then
+ *                                the F stimulus weights w_stim (dataset_create_stim; F = 0 otherwise);
  *                                for DirichletImpulses pass beta = |g|/sum|g| (impulse.py:286-291)
  * A     int8    [N][N] or NULL   x['net']['graph']['A'] (row = presynaptic); NULL = complete graph
  * W     float64 [N][N] or NULL   x['net']['weights']['W'] reshaped (N,N); NULL = ones (weights.py:32)
  * out_ll      float64 [n_hi-n_lo]
  * out_g_bias  float64 [n_hi-n_lo]          d ll_n / d bias_n            (may be NULL => ll only)
- * out_g_w     float64 [n_hi-n_lo][N*B]     d ll_n / d w[n][pre*B+b]     (may be NULL => ll only)
+ * out_g_w     float64 [n_hi-n_lo][N*B+F]   d ll_n / d w[n][j]           (may be NULL => ll only)
  * ---------------------------------------------------------------------------------- */
 PYGLM_B200_API int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
                        const double* bias, const double* w, const int8_t* A, const double* W,

@@ -230,12 +230,16 @@ def population_activation(fS, bias, w, A, W):
     return bias[None, :] + fS.reshape(T, N * B) @ M
 
 
-def population_ll_grad(fS, S, dt, bias, w, A, W, nlin_type):
+def population_ll_grad(fS, S, dt, bias, w, A, W, nlin_type, fstim=None, w_stim=None):
     """Best-effort CPU form (multithreaded BLAS): two GEMMs for all N neurons.
-    bias (N,), w (N_post, N_pre, B).  Returns ll (N,), g_bias (N,), g_w (N_post,N_pre,B)."""
+    bias (N,), w (N_post, N_pre, B).  Returns ll (N,), g_bias (N,), g_w (N_post,N_pre,B).
+    With a filtered stimulus fstim (T, F) and weights w_stim (N, F) the activation gains
+    I_stim = fstim @ w_stim[n] (bkgd.py:81) and a fourth output g_w_stim (N, F) = (fstim^T r)^T."""
     T, N, B = fS.shape
     X = fS.reshape(T, N * B)
     x = population_activation(fS, bias, w, A, W)
+    if fstim is not None:
+        x = x + fstim @ w_stim.T
     lam, dlam, loglam = nlin_and_derivative(x, nlin_type)
     Sf = S.astype(np.float64)
     ll = np.sum(-dt * lam + loglam * Sf, axis=0)
@@ -244,7 +248,45 @@ def population_ll_grad(fS, S, dt, bias, w, A, W, nlin_type):
     G = (X.T @ r).reshape(N, B, N)                        # [(pre,b), post]
     Weff = A.astype(np.float64) * W
     g_w = np.transpose(G, (2, 0, 1)) * Weff.T[:, :, None]
+    if fstim is not None:
+        return ll, g_bias, g_w, (fstim.T @ r).T
     return ll, g_bias, g_w
+
+
+# --------------------------------------------------------------------------------------
+# Stimulus features  (components/bkgd.py:45-157, BasisStimulus)
+# --------------------------------------------------------------------------------------
+def interpolate_stim_basis(basis, dt, dt_max, norm):
+    """bkgd.py:102-121: resample the basis on np.linspace(0,1,dt_max/dt); if norm, each column is
+    divided by its SUM (not trapz, unlike impulse.py:372)."""
+    L, B = basis.shape
+    Lt_int = int(round(dt_max / dt))
+    t_int = np.linspace(0, 1, Lt_int)
+    t_bas = np.linspace(0, 1, L)
+    ibasis = np.zeros((Lt_int, B))
+    for b in range(B):
+        ibasis[:, b] = np.interp(t_int, t_bas, basis[:, b])
+    if norm:
+        ibasis = ibasis / np.sum(ibasis, axis=0)[None, :]
+    return ibasis
+
+
+def filter_stimulus(stim, dt_stim, nT, dt, ibasis):
+    """bkgd.py:134-154: interpolate the stimulus onto the spike bins, project it on the basis
+    (utils/basis.py:201-236) and flatten to fstim[t, d*B+b]."""
+    D = stim.shape[1]
+    t = dt * np.arange(nT)
+    t_stim = dt_stim * np.arange(stim.shape[0])
+    istim = np.zeros((nT, D))
+    for d in range(D):
+        istim[:, d] = np.interp(t, t_stim, stim[:, d])
+    cstim = convolve_with_basis(istim, ibasis)             # (nT, D, B)
+    return istim, cstim.reshape(nT, D * cstim.shape[2])
+
+
+def stim_log_prior(w_stim):
+    """bkgd.py:76: spherical Gaussian with the hard-coded sigma 0.01."""
+    return np.sum(-0.5 / (0.01 ** 2) * (w_stim - 0.0) ** 2)
 
 
 def dirichlet_chain_rule(g, g_beta):

@@ -281,3 +281,103 @@ def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
         assert np.array_equal(batch[m], one[0])
     ds.gibbs_end()
     ds.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# Stimulus features (BasisStimulus, bkgd.py:45-172)
+# ----------------------------------------------------------------------------------------------
+def make_stimulus(T, D, Bs, seed, dt=0.001):
+    """A slowly varying D-dimensional stimulus sampled at 10 ms, filtered the way bkgd.py:122-154 does."""
+    rng = np.random.default_rng(seed)
+    dt_stim = 0.01
+    stim = np.cumsum(rng.standard_normal((int(np.ceil(T * dt / dt_stim)) + 1, D)), axis=0) * 0.1
+    prms = dict(type='cosine', n_eye=0, n_cos=Bs, a=1.0 / 120, b=0.5, orth=False, norm=True)
+    ib = orc.interpolate_stim_basis(orc.create_basis(prms), dt, 0.3, True)
+    istim, fstim = orc.filter_stimulus(stim, dt_stim, T, dt, ib)
+    return istim, ib, fstim
+
+
+def test_dense_filter_matches_oracle(eng):
+    """engine.filter_dense vs convolve_with_basis (utils/basis.py:201-236) on a real-valued signal."""
+    istim, ib, fstim = make_stimulus(5000, 2, 4, seed=3)
+    out = eng.engine.filter_dense(istim, ib)
+    assert out.shape == (5000, 2, 4)
+    scale = np.max(np.abs(fstim))
+    assert np.max(np.abs(out.reshape(5000, -1) - fstim)) < 1e-12 * scale
+    # first bin has no past: exactly zero (zero row prepended, basis.py:220)
+    assert np.all(out[0] == 0.0)
+
+
+@pytest.mark.parametrize("nlin", [orc.NLIN_SOFTPLUS, orc.NLIN_EXP])
+@pytest.mark.parametrize("T,N,B,D,Bs,network", [(3000, 6, 5, 2, 4, False),      # 38 features: fused kernel
+                                                (4000, 27, 5, 1, 3, True),      # 138 features: fused kernel
+                                                (2500, 40, 5, 2, 3, True)])     # 206 features: GEMM path
+def test_ll_grad_with_stimulus(eng, T, N, B, D, Bs, network, nlin):
+    """I_stim = fstim @ w_stim (bkgd.py:81) rides in the feature matrix: ll, d/d bias, d/d w_ir and
+    d/d w_stim on the FP64 path and the tensor-core path against the oracle."""
+    p = make_problem(T, N, B, network=network, seed=21)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 17.0
+    _, _, fstim = make_stimulus(T, D, Bs, seed=8)
+    F = D * Bs
+    w_stim = 0.05 * np.random.default_rng(4).standard_normal((N, F))
+    fS = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    ll, gb, gw, gs = orc.population_ll_grad(fS, p['S'], p['dt'], p['bias'], p['w'], p['A'], p['W'], nlin,
+                                            fstim=fstim, w_stim=w_stim)
+    ll0 = orc.population_ll_grad(fS, p['S'], p['dt'], p['bias'], p['w'], p['A'], p['W'], nlin)[0]
+    assert np.max(np.abs(ll - ll0) / np.abs(ll0)) > 1e-4        # the stimulus term matters in this problem
+    gw = gw.reshape(N, -1)
+    for x_dtype, path, lt, gt in (("f64", "fp64", 1e-11, 1e-9), ("f32", "fp64", LL_RTOL, GRAD_RTOL),
+                                  ("f32", "tc", LL_RTOL, GRAD_RTOL)):
+        ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype, fstim=fstim)
+        assert ds.F == F
+        ll_g, gb_g, gw_g, gs_g = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path=path, w_stim=w_stim)
+        assert np.max(np.abs(ll_g - ll) / np.abs(ll)) < lt, (x_dtype, path)
+        assert rel_err(gb_g, gb) < gt and rel_err(gw_g, gw) < gt and rel_err(gs_g, gs) < gt, (x_dtype, path)
+        # neuron sub-range and ll-only
+        ll_s, _, gw_s, gs_s = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, n_lo=2, n_hi=N - 1, path=path,
+                                         w_stim=w_stim)
+        assert np.max(np.abs(ll_s - ll[2:N - 1]) / np.abs(ll[2:N - 1])) < lt
+        assert rel_err(gs_s, gs[2:N - 1]) < gt and rel_err(gw_s, gw[2:N - 1]) < gt
+        assert np.max(np.abs(ds.ll(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path=path, w_stim=w_stim) - ll)
+                      / np.abs(ll)) < lt
+        with pytest.raises(ValueError):
+            ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)          # w_stim is required
+        assert np.array_equal(ds.fS().reshape(T, -1), eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype).fS().reshape(T, -1))
+        ds.close()
+
+
+def test_gibbs_delta_ll_with_stimulus_and_extreme_activations(eng):
+    """K4 with a stimulus current in the base activation (gibbs.py:914: I_bias + I_stim + I_net), and with
+    weights large enough that candidates land in every branch of the tabulated softplus (|x| > 37 on both
+    sides, spike bins at negative activation)."""
+    T, N, B = 6000, 5, 5
+    p = make_problem(T, N, B, network=True, dirichlet=True, seed=31)
+    p['W'] = p['W'] * 0.3
+    _, _, fstim = make_stimulus(T, 1, 3, seed=12)
+    w_stim = 2.0 * np.random.default_rng(2).standard_normal((N, 3))
+    fS = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f64", fstim=fstim)
+    ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'], nlin="explinear", w_stim=w_stim)
+    rng = np.random.default_rng(0)
+    seen_lo = seen_hi = False
+    for n_post, n_pre in ((0, 3), (2, 2), (4, 1)):
+        I_imp = orc.impulse_current(fS, p['w'][n_post])
+        Weff = orc.effective_weights(p['A'], p['W'], n_post).copy()
+        Weff[n_pre] = 0.0
+        I_other = I_imp @ Weff
+        I_stim = fstim @ w_stim[n_post]
+        cand = np.concatenate([orc.gh_candidates(0.0, 0.5), [0.0]])
+        out = ds.gibbs_delta_ll([n_post], [n_pre], cand[None, :])[0]
+        for q, wq in enumerate(cand):
+            ref = orc.gibbs_glm_ll(p['bias'][n_post], I_stim, I_other, I_imp[:, n_pre], wq, p['S'][:, n_post], p['dt'],
+                                   orc.NLIN_SOFTPLUS)
+            assert abs(out[q] - ref) <= 1e-10 * abs(ref) + 1e-9, (n_post, n_pre, q, out[q], ref)
+            x = p['bias'][n_post] + I_stim + I_other + wq * I_imp[:, n_pre]
+            seen_lo |= bool(np.any(x < -37.0)); seen_hi |= bool(np.any(x > 37.0))
+        ds.gibbs_commit([n_post], [n_pre], [1], [rng.standard_normal() * 0.5])
+        p['A'][n_pre, n_post] = 1
+        p['W'][n_pre, n_post] = ds.gibbs_state()[1][n_pre, n_post]
+    assert seen_lo and seen_hi                                   # the test really visited both tails
+    ds.gibbs_end()
+    ds.close()

@@ -49,6 +49,8 @@ struct pyglm_b200_dataset {
     int device = 0;
     int64_t T = 0;
     int N = 0, B = 0, R = 0, halo = 0;
+    int F = 0;                        // stimulus features behind the N*B spike-history features of X
+    int64_t NF() const { return (int64_t)N * B + F; }
     double dt = 0.0;
     int x_dtype = PYGLM_B200_X_F32;
     int64_t ldx = 0;
@@ -88,6 +90,45 @@ int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t
                               const double* ibasis, int32_t R, int32_t B,
                               int32_t x_dtype, int32_t device, pyglm_b200_dataset** out)
 {
+    return pyglm_b200_dataset_create_stim(S, T, halo, N, dt, ibasis, R, B, nullptr, 0, x_dtype, device, out);
+}
+
+int32_t pyglm_b200_dataset_num_stim(const pyglm_b200_dataset* ds) { return ds ? ds->F : 0; }
+
+int pyglm_b200_filter_dense(const double* stim, int64_t T, int32_t D, const double* ibasis, int32_t R, int32_t B,
+                            int32_t device, double* out)
+{
+    PYGLM_REQUIRE(T >= 0 && D >= 1, "filter_dense: bad shape T=%lld D=%d", (long long)T, D);
+    PYGLM_REQUIRE(R >= 1 && B >= 1 && B <= kMaxBasis, "filter_dense: bad basis shape R=%d B=%d (B<=%d)", R, B, kMaxBasis);
+    PYGLM_REQUIRE(ibasis != nullptr && (T == 0 || (stim != nullptr && out != nullptr)), "filter_dense: null argument");
+    if (T == 0) return PYGLM_B200_OK;
+    PYGLM_CUDA(cudaSetDevice(device));
+    DevBuf<double> d_stim, d_ib, d_out;
+    int rc;
+    if ((rc = d_stim.ensure((size_t)T * D)) || (rc = d_ib.ensure((size_t)R * B)) || (rc = d_out.ensure((size_t)T * D * B))) {
+        d_stim.release(); d_ib.release(); d_out.release();
+        return rc;
+    }
+    auto done = [&](int r) { d_stim.release(); d_ib.release(); d_out.release(); return r; };
+    cudaError_t e;
+    if ((e = cudaMemcpy(d_stim.p, stim, (size_t)T * D * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(d_ib.p, ibasis, (size_t)R * B * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        set_error("filter_dense: upload failed: %s", cudaGetErrorString(e));
+        return done(PYGLM_B200_ECUDA);
+    }
+    if ((rc = launch_filter_dense(d_stim.p, T, D, d_ib.p, R, B, d_out.p, nullptr))) return done(rc);
+    if ((e = cudaMemcpy(out, d_out.p, (size_t)T * D * B * sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+        set_error("filter_dense: download failed: %s", cudaGetErrorString(e));
+        return done(PYGLM_B200_ECUDA);
+    }
+    return done(PYGLM_B200_OK);
+}
+
+int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, int32_t N, double dt,
+                                   const double* ibasis, int32_t R, int32_t B,
+                                   const double* fstim, int32_t F,
+                                   int32_t x_dtype, int32_t device, pyglm_b200_dataset** out)
+{
     PYGLM_REQUIRE(out != nullptr, "dataset_create: out is null");
     *out = nullptr;
     PYGLM_REQUIRE(T >= 0 && N >= 1 && halo >= 0, "dataset_create: bad shape T=%lld N=%d halo=%d", (long long)T, N, halo);
@@ -97,13 +138,18 @@ int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t
     PYGLM_REQUIRE(x_dtype == PYGLM_B200_X_F32 || x_dtype == PYGLM_B200_X_F64 || x_dtype == PYGLM_B200_X_PLANES,
                   "dataset_create: bad x_dtype %d", x_dtype);
     PYGLM_REQUIRE(dt > 0.0, "dataset_create: dt must be positive");
+    PYGLM_REQUIRE(F >= 0 && (F == 0 || fstim != nullptr || T == 0), "dataset_create: bad stimulus block F=%d", F);
+    if (F > 0 && x_dtype == PYGLM_B200_X_PLANES) {
+        set_error("dataset_create: stimulus features are not available for planes-only datasets");
+        return PYGLM_B200_EUNSUPPORTED;
+    }
     PYGLM_CUDA(cudaSetDevice(device));
 
     pyglm_b200_dataset* ds = new (std::nothrow) pyglm_b200_dataset();
     PYGLM_REQUIRE(ds != nullptr, "dataset_create: host allocation failed");
     ds->device = device; ds->T = T; ds->N = N; ds->B = B; ds->R = R; ds->halo = halo; ds->dt = dt;
-    ds->x_dtype = x_dtype;
-    ds->ldx = round_up((int64_t)N * B, 4);
+    ds->x_dtype = x_dtype; ds->F = F;
+    ds->ldx = round_up(ds->NF(), 4);
     auto fail = [&](int rc) { pyglm_b200_dataset_destroy(ds); return rc; };
 
     cudaError_t e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking);
@@ -125,6 +171,16 @@ int pyglm_b200_dataset_create(const uint8_t* S, int64_t T, int32_t halo, int32_t
         if (T > 0 && (rc = tc_build_planes_streaming(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->stream))) return fail(rc);
     } else if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->X.p, ds->ldx, x_dtype, ds->stream))) return fail(rc);
     if (!planes_only && (rc = launch_transpose_spikes(ds->S.p, T, N, halo, ds->St.p, ds->stream))) return fail(rc);
+    if (F > 0 && T > 0) {
+        DevBuf<double> d_fs;
+        if ((rc = d_fs.ensure((size_t)T * F))) return fail(rc);
+        cudaError_t e3 = cudaMemcpyAsync(d_fs.p, fstim, (size_t)T * F * sizeof(double), cudaMemcpyHostToDevice, ds->stream);
+        if (e3 == cudaSuccess) rc = launch_fill_stim(d_fs.p, T, F, ds->X.p, ds->ldx, (int64_t)N * B, x_dtype, ds->stream);
+        cudaStreamSynchronize(ds->stream);
+        d_fs.release();
+        if (e3 != cudaSuccess) { set_error("dataset_create: stimulus upload failed: %s", cudaGetErrorString(e3)); return fail(PYGLM_B200_ECUDA); }
+        if (rc) return fail(rc);
+    }
     CK(cudaStreamSynchronize(ds->stream));
 #undef CK
     *out = ds;
@@ -225,7 +281,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     PYGLM_REQUIRE((d_gb == nullptr) == (d_gw == nullptr), "ll_grad: pass both gradient outputs or neither");
     const int ncols = n_hi - n_lo;
     if (ncols == 0) return PYGLM_B200_OK;
-    const int64_t NB = (int64_t)ds->N * ds->B;
+    const int64_t NB = ds->NF();
     if (ds->T == 0) {   // empty recording: ll = 0, gradients = 0
         PYGLM_CUDA(cudaMemsetAsync(d_ll, 0, ncols * sizeof(double), stream));
         if (d_gb) PYGLM_CUDA(cudaMemsetAsync(d_gb, 0, ncols * sizeof(double), stream));
@@ -240,7 +296,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     if (use == PYGLM_B200_PATH_TC) {
         TcArgs t{};
         t.X = ds->x_dtype == PYGLM_B200_X_PLANES ? nullptr : (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
-        t.B = ds->B; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
+        t.B = ds->B; t.F = ds->F; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
         t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
         t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
         return launch_tc_ll_grad(t, ds->tc, stream);
@@ -255,7 +311,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     TRY(ds->gbp.ensure((size_t)ntiles * Np));
     SimtArgs a{};
     a.X = ds->X.p; a.ldx = ds->ldx; a.x_dtype = ds->x_dtype;
-    a.S = ds->S.p; a.T = ds->T; a.N = ds->N; a.halo = ds->halo; a.B = ds->B;
+    a.S = ds->S.p; a.T = ds->T; a.N = ds->N; a.halo = ds->halo; a.B = ds->B; a.F = ds->F;
     a.dt = ds->dt; a.nlin = nlin; a.n_lo = n_lo; a.ncols = ncols; a.Np = Np;
     a.bias = d_bias; a.M = ds->M.p; a.Weff = ds->Weff.p;
     a.llp = ds->llp.p; a.gbp = ds->gbp.p;
@@ -264,11 +320,11 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     if (d_gw) {
         TRY(ds->Rres.ensure((size_t)ds->T * Np));
         a.R = ds->Rres.p;
-        a.splits = simt_choose_splits(ds->T, ds->N, ds->B, Np);
+        a.splits = simt_choose_splits(ds->T, NB, Np);
         TRY(ds->Gp.ensure((size_t)a.splits * round_up(NB, 64) * Np));
         a.Gp = ds->Gp.p;
     }
-    TRY(launch_build_M(d_w, d_A, d_W, ds->N, ds->B, n_lo, ncols, ds->M.p, Np, NBp, ds->Weff.p, stream));
+    TRY(launch_build_M(d_w, d_A, d_W, ds->N, ds->B, ds->F, n_lo, ncols, ds->M.p, Np, NBp, ds->Weff.p, stream));
     return launch_simt_ll_grad(a, stream);
 }
 
@@ -295,7 +351,7 @@ static int stage_params(pyglm_b200_dataset* ds, const double* bias, const double
                         cudaStream_t stream)
 {
     PYGLM_REQUIRE(bias && w, "null bias / w");
-    const size_t N = ds->N, NB = (size_t)ds->N * ds->B;
+    const size_t N = ds->N, NB = (size_t)ds->NF();
     TRY(b_bias.ensure(N));
     TRY(b_w.ensure(N * NB));
     PYGLM_CUDA(cudaMemcpyAsync(b_bias.p, bias, N * sizeof(double), cudaMemcpyHostToDevice, stream));
@@ -321,7 +377,7 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
     PYGLM_REQUIRE(0 <= n_lo && n_lo <= n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
     const int ncols = n_hi - n_lo;
     if (ncols == 0) return PYGLM_B200_OK;
-    const size_t NB = (size_t)ds->N * ds->B;
+    const size_t NB = (size_t)ds->NF();
     cudaStream_t st = ds->stream;
     TRY(stage_params(ds, bias, w, A, W, ds->p_bias, ds->p_w, ds->p_A, ds->p_W, st));
     const bool grad = out_g_bias != nullptr || out_g_w != nullptr;
@@ -365,7 +421,7 @@ static GibbsArgs gibbs_args(pyglm_b200_dataset* ds)
 {
     GibbsArgs g{};
     g.X = ds->Xt.p; g.ldx = ds->ldx; g.x_dtype = ds->x_dtype;
-    g.St = ds->St.p; g.T = ds->T; g.N = ds->N; g.B = ds->B;
+    g.St = ds->St.p; g.T = ds->T; g.N = ds->N; g.B = ds->B; g.F = ds->F;
     g.dt = ds->dt; g.nlin = ds->g_nlin; g.n_lo = ds->g_nlo; g.ncols = ds->g_ncols;
     g.bias = ds->g_bias.p; g.w = ds->g_w.p; g.A = ds->g_A.p; g.W = ds->g_W.p;
     g.Inet = ds->Inet.p; g.partial = ds->partial.p; g.nchunks = gibbs_num_chunks(ds->T);

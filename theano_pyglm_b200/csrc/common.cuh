@@ -44,17 +44,26 @@ constexpr int kMaxCand = 16;    // Q <= 16 candidate weights per edge (reference
 int launch_filter(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
                   void* dX, int64_t ldx, int x_dtype, cudaStream_t stream);
 
+// dense FP64 causal filter of a real-valued stimulus (device pointers): out[t][d*B+b]
+int launch_filter_dense(const double* d_stim, int64_t T, int D, const double* d_ibasis, int R, int B, double* d_out,
+                        cudaStream_t stream);
+// X[t][col0+f] = fstim[t][f]
+int launch_fill_stim(const double* d_fstim, int64_t T, int F, void* dX, int64_t ldx, int64_t col0, int x_dtype,
+                     cudaStream_t stream);
+
 // St[n][t] = S[halo+t][n]
 int launch_transpose_spikes(const uint8_t* dS, int64_t T, int N, int halo, uint8_t* dSt, cudaStream_t stream);
 
-// M[j][n'] = A[pre][n] W[pre][n] w[n][j]   (n = n_lo+n', pre = j/B), zero padded to [NBp][Np];
-// Weff[n'][pre] = A[pre][n] W[pre][n]
-int launch_build_M(const double* d_w, const int8_t* d_A, const double* d_W, int N, int B, int n_lo, int ncols,
+// Feature layout everywhere: NF = N*B + F columns; j < N*B is spike-history feature (pre = j/B, b = j%B),
+// j >= N*B is stimulus feature j - N*B.  Parameter rows w[n][NF] and gradient rows g_w[n'][NF] share it.
+// M[j][n'] = A[pre][n] W[pre][n] w[n][j]   (n = n_lo+n', pre = j/B; no mask for stimulus rows),
+// zero padded to [NBp][Np];  Weff[n'][pre] = A[pre][n] W[pre][n]
+int launch_build_M(const double* d_w, const int8_t* d_A, const double* d_W, int N, int B, int F, int n_lo, int ncols,
                    double* d_M, int Np, int64_t NBp, double* d_Weff, cudaStream_t stream);
 
 struct SimtArgs {
     const void* X; int64_t ldx; int x_dtype;
-    const uint8_t* S; int64_t T; int N; int halo; int B;
+    const uint8_t* S; int64_t T; int N; int halo; int B; int F;
     double dt; int nlin;
     int n_lo, ncols, Np;
     const double* bias;      // [N]
@@ -63,21 +72,21 @@ struct SimtArgs {
     double* R;               // [T][Np] residuals (nullptr: forward only)
     double* llp; double* gbp;   // [tiles][Np] partials
     double* Gp; int splits;  // [splits][NBp64][Np]
-    double* out_ll; double* out_gb; double* out_gw;   // [ncols], [ncols], [ncols][N*B]
+    double* out_ll; double* out_gb; double* out_gw;   // [ncols], [ncols], [ncols][N*B+F]
     double* act_out;         // optional [ncols][T] activation without bias (Gibbs I_net)
     double* lam_out;         // optional [T][ncols] firing rate
 };
 int simt_workspace_tiles(int64_t T);
-int simt_choose_splits(int64_t T, int N, int B, int Np);
+int simt_choose_splits(int64_t T, int64_t NF, int Np);
 int launch_simt_ll_grad(const SimtArgs& a, cudaStream_t stream);
 
 struct GibbsArgs {
     const void* X; int64_t ldx; int x_dtype;     // X here is the feature-major copy Xt[j][t]
-    const uint8_t* St; int64_t T; int N; int B;
+    const uint8_t* St; int64_t T; int N; int B; int F;
     double dt; int nlin;
     int n_lo, ncols;
     const double* bias;      // [N]
-    const double* w;         // [N][N*B]
+    const double* w;         // [N][N*B+F]
     int8_t* A; double* W;    // device state [N][N]
     double* Inet;            // [ncols][T]
     double* partial;         // [M][nchunks][Q]

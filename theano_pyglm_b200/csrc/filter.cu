@@ -240,4 +240,82 @@ int launch_transpose_spikes(const uint8_t* dS, int64_t T, int N, int halo, uint8
     return PYGLM_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// Stimulus features (BasisStimulus, pyglm/components/bkgd.py:122-154): the interpolated stimulus is real
+// valued, so its basis projection is a dense causal convolution in FP64,
+//   out[t][d*B+b] = sum_{k=1..R} ibasis[k-1][b] * stim[t-k][d]          (utils/basis.py:212-236)
+// summed in increasing lag.  One block = 256 bins of one stimulus dimension; window and basis in smem.
+// ---------------------------------------------------------------------------------
+constexpr int kDenseBins = 256;
+
+__global__ void __launch_bounds__(kDenseBins)
+filter_dense_kernel(const double* __restrict__ stim, int64_t T, int D, const double* __restrict__ ibasis, int R, int B,
+                    double* __restrict__ out)
+{
+    extern __shared__ double dsm[];
+    double* sIb = dsm;                       // [R][B]
+    double* sS = dsm + (size_t)R * B;        // [R + kDenseBins]: stim[t0-R .. t0+255][d]
+    const int d = blockIdx.y;
+    const int64_t t0 = (int64_t)blockIdx.x * kDenseBins;
+    for (int i = threadIdx.x; i < R * B; i += kDenseBins) sIb[i] = ibasis[i];
+    for (int i = threadIdx.x; i < R + kDenseBins; i += kDenseBins) {
+        const int64_t t = t0 - R + i;
+        sS[i] = (t >= 0 && t < T) ? stim[t * D + d] : 0.0;
+    }
+    __syncthreads();
+    const int64_t t = t0 + threadIdx.x;
+    if (t >= T) return;
+    double acc[kMaxBasis];
+#pragma unroll
+    for (int b = 0; b < kMaxBasis; ++b) acc[b] = 0.0;
+    for (int k = 1; k <= R; ++k) {
+        const double v = sS[R + threadIdx.x - k];
+#pragma unroll
+        for (int b = 0; b < kMaxBasis; ++b)
+            if (b < B) acc[b] = fma(sIb[(k - 1) * B + b], v, acc[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < kMaxBasis; ++b)
+        if (b < B) out[t * ((int64_t)D * B) + (int64_t)d * B + b] = acc[b];
+}
+
+int launch_filter_dense(const double* d_stim, int64_t T, int D, const double* d_ibasis, int R, int B, double* d_out,
+                        cudaStream_t stream)
+{
+    if (T <= 0 || D <= 0) return PYGLM_B200_OK;
+    const size_t smem = ((size_t)R * B + R + kDenseBins) * sizeof(double);
+    if (smem > 200 * 1024) {
+        set_error("filter_dense: R=%d x B=%d basis does not fit in shared memory", R, B);
+        return PYGLM_B200_EUNSUPPORTED;
+    }
+    PYGLM_CUDA(cudaFuncSetAttribute(filter_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(T, kDenseBins), (unsigned)D);
+    filter_dense_kernel<<<grid, kDenseBins, smem, stream>>>(d_stim, T, D, d_ibasis, R, B, d_out);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
+// X[t][col0 + f] = fstim[t][f]: the stimulus features ride behind the spike-history features of X
+template <typename XT>
+__global__ void __launch_bounds__(256)
+fill_stim_kernel(const double* __restrict__ fstim, int64_t T, int F, XT* __restrict__ X, int64_t ldx, int64_t col0)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * F) return;
+    const int64_t t = idx / F;
+    const int f = (int)(idx - t * F);
+    X[t * ldx + col0 + f] = (XT)fstim[idx];
+}
+
+int launch_fill_stim(const double* d_fstim, int64_t T, int F, void* dX, int64_t ldx, int64_t col0, int x_dtype,
+                     cudaStream_t stream)
+{
+    if (T <= 0 || F <= 0) return PYGLM_B200_OK;
+    const unsigned blocks = (unsigned)ceil_div(T * F, 256);
+    if (x_dtype == PYGLM_B200_X_F32) fill_stim_kernel<float><<<blocks, 256, 0, stream>>>(d_fstim, T, F, (float*)dX, ldx, col0);
+    else fill_stim_kernel<double><<<blocks, 256, 0, stream>>>(d_fstim, T, F, (double*)dX, ldx, col0);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
 }  // namespace pyglm

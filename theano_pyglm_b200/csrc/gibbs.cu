@@ -22,17 +22,8 @@ constexpr int kGibbsChunk = 8192;     // bins per block
 
 int gibbs_num_chunks(int64_t T) { return (int)ceil_div(T, kGibbsChunk); }
 
-// exp(-x) for x >= 16 to ~1e-7 relative: an FP32 exp of the rounded argument times the first-order
-// correction for the rounding.  It only feeds lam = x + log1p(e^-x), where it is worth < 1.2e-7, so the
-// error in lam is below one FP64 ulp.
-__device__ __forceinline__ double exp_neg_large(double x)
-{
-    const float hi = (float)x;
-    const double lo = x - (double)hi;
-    return (double)expf(-hi) * (1.0 - lo);
-}
-
-// log(1+e^x) in FP64 for any x (the derivative and log(lam) are not needed per bin here)
+// log(1+e^x) in FP64 for any x through the library functions (spike bins with x < 0, where log(lam) needs
+// lam to full RELATIVE accuracy)
 __device__ __forceinline__ double softplus_f64(double x)
 {
     const double e = exp(-fabs(x));
@@ -40,10 +31,71 @@ __device__ __forceinline__ double softplus_f64(double x)
     return x > 0.0 ? x + l1p : l1p;
 }
 
-// Softplus fast path: when every candidate of every lane of the warp sits at x >= 16 (a population firing
-// at tens of Hz: bias ~ 20), lam = x + e - e^2/2 with e = e^-x needs no FP64 transcendental, and the
-// log(lam) of the Poisson term is needed only in the ~2% of bins that hold a spike.  Those bins are
-// handed to the whole warp: lane q evaluates candidate q, so one FP64 log serves all candidates.
+// The per-bin rate of the softplus model is lam = max(x,0) + L(|x|), L(a) = log1p(e^-a).  The sampler evaluates
+// it (Q+1) T times per edge and the library exp + log1p pair costs ~95 instructions, so L is tabulated
+// instead: 149 intervals of width 1/4 centred on a = i/4, a degree-9 polynomial in z = 8(a - i/4) on each
+// (Chebyshev interpolant expanded in monomials, built once on the host in long double).  Absolute error
+// < 1e-16 on [0, 37]; beyond 37, L < 8.6e-17 and only matters (to 1e-19 per bin) when x < 0.
+constexpr int kSpDeg = 9;
+constexpr int kSpRows = 149;
+constexpr double kSpMax = 37.0;
+constexpr double kSpMagic = 6755399441055744.0;          // 1.5 * 2^52: adding it rounds to the nearest integer
+__device__ double g_softplus_tab[kSpRows * (kSpDeg + 1)];
+
+__device__ __forceinline__ double softplus_tab(double x, const double* __restrict__ tab)
+{
+    const double a = fabs(x);
+    double l1p;
+    if (a < kSpMax) {
+        const double tm = fma(a, 4.0, kSpMagic);
+        const int i = __double2loint(tm);                 // rint(4a) in 0..148
+        const double fi = tm - kSpMagic;
+        const double z = fma(a, 8.0, -2.0 * fi);          // in [-1, 1]
+        const double* __restrict__ r = tab + i * (kSpDeg + 1);
+        double p = r[kSpDeg];
+#pragma unroll
+        for (int k = kSpDeg - 1; k >= 0; --k) p = fma(p, z, r[k]);
+        l1p = p;
+    } else {
+        l1p = x < 0.0 ? (double)__expf((float)x) : 0.0;
+    }
+    return fmax(x, 0.0) + l1p;
+}
+
+static int ensure_softplus_table()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    PYGLM_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && done[dev]) return PYGLM_B200_OK;
+    constexpr int n = kSpDeg + 1;
+    static double tab[kSpRows * n];
+    long double Tm[n][n] = {};                            // Chebyshev polynomials as monomial coefficient rows
+    Tm[0][0] = 1; Tm[1][1] = 1;
+    for (int k = 2; k < n; ++k)
+        for (int j = 0; j <= k; ++j) Tm[k][j] = (j ? 2 * Tm[k - 1][j - 1] : 0) - Tm[k - 2][j];
+    const long double pi = acosl(-1.0L);
+    for (int i = 0; i < kSpRows; ++i) {
+        long double f[n], cheb[n];
+        for (int k = 0; k < n; ++k) f[k] = log1pl(expl(-(0.25L * i + 0.125L * cosl(pi * (k + 0.5L) / n))));
+        for (int j = 0; j < n; ++j) {
+            long double acc = 0;
+            for (int k = 0; k < n; ++k) acc += f[k] * cosl(pi * j * (k + 0.5L) / n);
+            cheb[j] = acc * (j ? 2.0L : 1.0L) / n;
+        }
+        for (int j = 0; j < n; ++j) {
+            long double m = 0;
+            for (int k = j; k < n; ++k) m += cheb[k] * Tm[k][j];
+            tab[i * n + j] = (double)m;
+        }
+    }
+    PYGLM_CUDA(cudaMemcpyToSymbol(g_softplus_tab, tab, sizeof(tab)));
+    if (dev >= 0 && dev < 64) done[dev] = true;
+    return PYGLM_B200_OK;
+}
+
+// log(lam) of the Poisson term is needed only in the ~2% of bins that hold a spike.  Those bins are handed to
+// the whole warp: lane q evaluates candidate q, so one FP64 log serves all candidates.
 template <typename XT, int QMAX, int NLIN>
 __global__ void __launch_bounds__(kGibbsThreads)
 gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t* __restrict__ pres,
@@ -52,27 +104,27 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     __shared__ double sW[kMaxBasis];
     __shared__ double sRed[QMAX][kGibbsThreads / 32];
     __shared__ double sRedSp[kGibbsThreads / 32][32];
+    __shared__ double sTab[NLIN == PYGLM_B200_NLIN_SOFTPLUS ? kSpRows * (kSpDeg + 1) : 1];
 
     const XT* __restrict__ X = static_cast<const XT*>(g.X);
     const int m = blockIdx.y;
     const int col = cols[m], pre = pres[m];
     const int nl = col - g.n_lo;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t NB = (int64_t)g.N * g.B;
+    const int64_t NB = (int64_t)g.N * g.B + g.F;           // row pitch of w: all features
 
     if (tid < g.B) sW[tid] = g.w[(int64_t)col * NB + (int64_t)pre * g.B + tid];
+    if (NLIN == PYGLM_B200_NLIN_SOFTPLUS)
+        for (int i = tid; i < kSpRows * (kSpDeg + 1); i += kGibbsThreads) sTab[i] = g_softplus_tab[i];
     __syncthreads();
 
     const double aw_old = (double)g.A[(int64_t)pre * g.N + col] * g.W[(int64_t)pre * g.N + col];
     const double bias = g.bias[col];
     double wq[QMAX], acc[QMAX];
-    double wmin = 0.0, wmax = 0.0;                       // range of the candidate weights (with 0 for safety)
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) {
         wq[q] = (q < Q) ? wcand[(int64_t)m * Q + q] : 0.0;
         acc[q] = 0.0;
-        wmin = fmin(wmin, wq[q]);
-        wmax = fmax(wmax, wq[q]);
     }
     const double w_lane = (lane < Q) ? wcand[(int64_t)m * Q + lane] : 0.0;   // candidate `lane` (spike path)
     double acc_sp = 0.0;
@@ -92,27 +144,11 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
             base = bias + (inet[t] - aw_old * u);
             s = (double)st[t];
         }
-        bool fast = false;
-        if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
-            const double xlow = base + fmin(wmin * u, wmax * u);     // smallest activation over the candidates
-            fast = __all_sync(0xffffffffu, !live || xlow >= 16.0);
-        }
         if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
             if (live) {
-                if (fast) {
 #pragma unroll
-                    for (int q = 0; q < QMAX; ++q) {
-                        if (q < Q) {
-                            const double x = base + wq[q] * u;
-                            const double e = exp_neg_large(x);
-                            acc[q] -= g.dt * (x + e * (1.0 - 0.5 * e));
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < QMAX; ++q)
-                        if (q < Q) acc[q] -= g.dt * softplus_f64(base + wq[q] * u);
-                }
+                for (int q = 0; q < QMAX; ++q)
+                    if (q < Q) acc[q] -= g.dt * softplus_tab(base + wq[q] * u, sTab);
             }
             // spike bins (~2%): one lane per candidate evaluates log(lam) for the whole warp
             unsigned mask = __ballot_sync(0xffffffffu, live && s != 0.0);
@@ -122,7 +158,10 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
                 const double bs = __shfl_sync(0xffffffffu, base, src);
                 const double us = __shfl_sync(0xffffffffu, u, src);
                 const double ss = __shfl_sync(0xffffffffu, s, src);
-                if (lane < Q) acc_sp += ss * log(softplus_f64(bs + w_lane * us));
+                if (lane < Q) {
+                    const double x = bs + w_lane * us;
+                    acc_sp += ss * log(x >= 0.0 ? softplus_tab(x, sTab) : softplus_f64(x));
+                }
             }
         } else if (live) {
 #pragma unroll
@@ -174,7 +213,7 @@ gibbs_commit_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t
     const int col = cols[m], pre = pres[m];
     const int nl = col - g.n_lo;
     const int tid = threadIdx.x;
-    const int64_t NB = (int64_t)g.N * g.B;
+    const int64_t NB = (int64_t)g.N * g.B + g.F;           // row pitch of w: all features
     if (tid < g.B) sW[tid] = g.w[(int64_t)col * NB + (int64_t)pre * g.B + tid];
     __syncthreads();
     const double aw_old = (double)g.A[(int64_t)pre * g.N + col] * g.W[(int64_t)pre * g.N + col];
@@ -245,6 +284,7 @@ int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const i
     dim3 grid((unsigned)g.nchunks, (unsigned)M);
     const bool f32 = g.x_dtype == PYGLM_B200_X_F32;
     const bool sp = g.nlin == PYGLM_B200_NLIN_SOFTPLUS;
+    if (sp) { int rc = ensure_softplus_table(); if (rc) return rc; }
 #define PYGLM_GIBBS_LAUNCH(QM)                                                                                         \
     do {                                                                                                               \
         if (f32 && sp)       gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_SOFTPLUS><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \

@@ -24,21 +24,25 @@ constexpr int kBwdTK = 32;       // time bins per backward K step
 
 // ---------------------------------------------------------------------------------
 __global__ void build_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A,
-                               const double* __restrict__ W, int N, int B, int n_lo, int ncols,
+                               const double* __restrict__ W, int N, int B, int F, int n_lo, int ncols,
                                double* __restrict__ M, int Np, int64_t NBp, double* __restrict__ Weff)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t NB = (int64_t)N * B;
+    const int64_t NB = (int64_t)N * B, NF = NB + F;
     if (idx < NBp * Np) {
         const int64_t j = idx / Np;
         const int nl = (int)(idx - j * Np);
         double v = 0.0;
-        if (j < NB && nl < ncols) {
+        if (j < NF && nl < ncols) {
             const int n = n_lo + nl;
-            const int pre = (int)(j / B);
-            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
-            v = (a * ww) * w[(int64_t)n * NB + j];
+            if (j < NB) {
+                const int pre = (int)(j / B);
+                const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
+                const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+                v = (a * ww) * w[(int64_t)n * NF + j];
+            } else {
+                v = w[(int64_t)n * NF + j];              // stimulus weight: no network mask (bkgd.py:81)
+            }
         }
         M[idx] = v;
     }
@@ -52,11 +56,11 @@ __global__ void build_M_kernel(const double* __restrict__ w, const int8_t* __res
     }
 }
 
-int launch_build_M(const double* d_w, const int8_t* d_A, const double* d_W, int N, int B, int n_lo, int ncols,
+int launch_build_M(const double* d_w, const int8_t* d_A, const double* d_W, int N, int B, int F, int n_lo, int ncols,
                    double* d_M, int Np, int64_t NBp, double* d_Weff, cudaStream_t stream)
 {
     const int64_t total = NBp * Np > (int64_t)ncols * N ? NBp * Np : (int64_t)ncols * N;
-    build_M_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(d_w, d_A, d_W, N, B, n_lo, ncols,
+    build_M_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(d_w, d_A, d_W, N, B, F, n_lo, ncols,
                                                                         d_M, Np, NBp, d_Weff);
     PYGLM_CUDA(cudaGetLastError());
     return PYGLM_B200_OK;
@@ -79,7 +83,7 @@ simt_fwd_kernel(SimtArgs a)
     const int tx = tid & 7, ty = tid >> 3;            // 8 x 16
     const int64_t t0 = (int64_t)blockIdx.x * kFwdTT;
     const int nt0 = blockIdx.y * kNT;
-    const int64_t NB = (int64_t)a.N * a.B;
+    const int64_t NB = (int64_t)a.N * a.B + a.F;     // all features: spike history + stimulus
 
     double acc[4][4];
 #pragma unroll
@@ -194,7 +198,7 @@ simt_bwd_kernel(SimtArgs a, int64_t chunk, int64_t NBp64)
     const int nt0 = blockIdx.y * kNT;
     const int64_t tbeg = (int64_t)blockIdx.z * chunk;
     const int64_t tend = min(a.T, tbeg + chunk);
-    const int64_t NB = (int64_t)a.N * a.B;
+    const int64_t NB = (int64_t)a.N * a.B + a.F;     // all features: spike history + stimulus
 
     double acc[4][4];
 #pragma unroll
@@ -236,24 +240,24 @@ simt_bwd_kernel(SimtArgs a, int64_t chunk, int64_t NBp64)
 }
 
 __global__ void __launch_bounds__(256)
-reduce_G_kernel(const double* __restrict__ Gp, int splits, int64_t NBp64, int Np, int N, int B, int ncols,
+reduce_G_kernel(const double* __restrict__ Gp, int splits, int64_t NBp64, int Np, int N, int B, int F, int ncols,
                 const double* __restrict__ Weff, double* __restrict__ out_gw)
 {
-    const int64_t NB = (int64_t)N * B;
+    const int64_t NB = (int64_t)N * B + F;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= NB * ncols) return;
     const int nl = (int)(idx / NB);
     const int64_t j = idx - (int64_t)nl * NB;
     double s = 0.0;
     for (int z = 0; z < splits; ++z) s += Gp[((int64_t)z * NBp64 + j) * Np + nl];
-    out_gw[idx] = Weff[(int64_t)nl * N + (j / B)] * s;
+    out_gw[idx] = j < (int64_t)N * B ? Weff[(int64_t)nl * N + (j / B)] * s : s;
 }
 
 int simt_workspace_tiles(int64_t T) { return (int)ceil_div(T, kFwdTT); }
 
-int simt_choose_splits(int64_t T, int N, int B, int Np)
+int simt_choose_splits(int64_t T, int64_t NF, int Np)
 {
-    const int64_t tiles = ceil_div((int64_t)N * B, kBwdJT) * (Np / kNT);
+    const int64_t tiles = ceil_div(NF, kBwdJT) * (Np / kNT);
     int64_t splits = ceil_div(148 * 8, tiles);
     const int64_t max_splits = ceil_div(T, 4 * kBwdTK);
     if (splits > max_splits) splits = max_splits;
@@ -273,14 +277,14 @@ static int launch_simt_t(const SimtArgs& a, cudaStream_t stream)
     reduce_tiles_kernel<<<gridr, 256, 0, stream>>>(a.llp, a.gbp, ntiles, a.Np, a.ncols, a.out_ll, a.out_gb);
     PYGLM_CUDA(cudaGetLastError());
     if (a.R && a.out_gw) {
-        const int64_t NB = (int64_t)a.N * a.B;
+        const int64_t NB = (int64_t)a.N * a.B + a.F;     // all features: spike history + stimulus
         const int64_t NBp64 = round_up(NB, kBwdJT);
         int64_t chunk = round_up(ceil_div(a.T, a.splits), kBwdTK);
         dim3 gridb((unsigned)(NBp64 / kBwdJT), (unsigned)(a.Np / kNT), (unsigned)a.splits);
         simt_bwd_kernel<XT><<<gridb, kThreads, 0, stream>>>(a, chunk, NBp64);
         PYGLM_CUDA(cudaGetLastError());
         reduce_G_kernel<<<(unsigned)ceil_div(NB * a.ncols, 256), 256, 0, stream>>>(
-            a.Gp, a.splits, NBp64, a.Np, a.N, a.B, a.ncols, a.Weff, a.out_gw);
+            a.Gp, a.splits, NBp64, a.Np, a.N, a.B, a.F, a.ncols, a.Weff, a.out_gw);
         PYGLM_CUDA(cudaGetLastError());
     }
     return PYGLM_B200_OK;

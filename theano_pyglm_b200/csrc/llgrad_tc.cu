@@ -81,7 +81,7 @@ bool tc_supported(int64_t T, int N, int B, int x_dtype)
 }
 
 // N*B <= 160 features: the fused single-pass kernel; larger populations: the two GEMM kernels
-bool tc_uses_fused_kernel(int N, int B) { return (int64_t)N * B <= kMaxChunks * kChunkF; }
+bool tc_uses_fused_kernel(int64_t nfeat) { return nfeat <= kMaxChunks * kChunkF; }
 
 // ---------------------------------------------------------------------------------------------
 // One-time: per-feature scales and the FP16 split planes of X
@@ -125,19 +125,19 @@ __global__ void tc_split_X_kernel(const float* __restrict__ X, int64_t T, int NB
 __global__ void __launch_bounds__(256)
 tc_prep_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A, const double* __restrict__ W,
                  const double* __restrict__ bias, const float* __restrict__ sx,
-                 int N, int B, int n_lo, int ncols, int Kp, __half* __restrict__ Mp, float* __restrict__ colpar)
+                 int N, int B, int F, int n_lo, int ncols, int Kp, __half* __restrict__ Mp, float* __restrict__ colpar)
 {
     __shared__ float smax[256];
     const int nl = blockIdx.x;                 // 0..31
-    const int NB = N * B;
+    const int NS = N * B, NB = NS + F;         // spike-history features, all features
     const bool live = nl < ncols;
     const int n = n_lo + nl;
     float mx = 0.f;
     if (live) {
         for (int j = threadIdx.x; j < NB; j += 256) {
             const int pre = j / B;
-            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+            const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+            const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
             const double m = (a * ww) * w[(int64_t)n * NB + j] / (double)sx[j];
             mx = fmaxf(mx, fabsf((float)m));
         }
@@ -155,8 +155,8 @@ tc_prep_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A, con
         __half h1 = __float2half_rn(0.f), h2 = h1;
         if (live && j < NB) {
             const int pre = j / B;
-            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+            const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+            const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
             const double v = (a * ww) * w[(int64_t)n * NB + j] / (double)sx[j] * (double)sm;
             h1 = __double2half(v);
             h2 = __double2half((v - (double)__half2float(h1)) * (double)kLoScale);
@@ -596,12 +596,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
 // (plus one for ll / g_bias): 32 columns x 32 slices of the CTA range, combined slice 0..31.
 constexpr int kFinalSlices = 32;
 __global__ void __launch_bounds__(32 * kFinalSlices)
-tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int B, int n_lo, int ncols,
+tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int B, int F, int n_lo, int ncols,
                 const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
                 double* __restrict__ out_ll, double* __restrict__ out_gb, double* __restrict__ out_gw)
 {
     __shared__ double sh[kFinalSlices][2 * kNcol];
-    const int64_t NB = (int64_t)N * B;
+    const int64_t NS = (int64_t)N * B, NB = NS + F;
     const int64_t per_cta = (int64_t)nmt * 128 * kNcol + 2 * kNcol;
     const int nl = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const bool tail = blockIdx.x == NB;                      // the ll / g_bias block
@@ -623,8 +623,8 @@ tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int 
     } else if (out_gw) {
         const int64_t j = blockIdx.x;
         const int n = n_lo + nl, pre = (int)(j / B);
-        const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-        const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+        const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+        const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
         out_gw[(int64_t)nl * NB + j] = (a * ww) * s0 / ((double)sx[j] * (double)kRScale);
     }
 }
@@ -666,9 +666,8 @@ int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, 
 }
 
 // allocate everything the tensor-core path keeps per dataset (planes, scales, padded spikes, maps)
-static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, int B, cudaStream_t stream)
+static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, int NB, cudaStream_t stream)
 {
-    const int NB = N * B;
     ws.ldp = round_up(NB, 8);
     int dev = 0;
     PYGLM_CUDA(cudaGetDevice(&dev));
@@ -698,8 +697,8 @@ int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
 {
     if (ws.planes_ready) return PYGLM_B200_OK;
     if (a.X == nullptr) { set_error("tensor-core planes were not built for this dataset"); return PYGLM_B200_ESTATE; }
-    const int NB = a.N * a.B;
-    int rc = alloc_planes(ws, a.S, a.T, a.N, a.halo, a.B, stream);
+    const int NB = a.N * a.B + a.F;
+    int rc = alloc_planes(ws, a.S, a.T, a.N, a.halo, NB, stream);
     if (rc) return rc;
     dim3 gmax((unsigned)std::min<int64_t>(a.T, 148 * 16), (unsigned)ceil_div(NB, 128));
     tc_colmax_kernel<<<gmax, 128, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.colmax);
@@ -719,7 +718,7 @@ int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int 
 {
     const int NB = N * B;
     const int64_t ldx = round_up(NB, 4);
-    int rc = alloc_planes(ws, S, T, N, halo, B, stream);
+    int rc = alloc_planes(ws, S, T, N, halo, NB, stream);
     if (rc) return rc;
     int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(T, ((int64_t)256 << 20) / (ldx * 4)));   // ~256 MB scratch
     if (const char* env = getenv("PYGLM_PLANES_CHUNK")) chunk = std::max<int64_t>(1, atoll(env));          // tests: force several chunks
@@ -753,10 +752,10 @@ int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int 
 int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
 {
     if (a.T <= 0 || a.ncols <= 0) return PYGLM_B200_OK;
-    if (!tc_uses_fused_kernel(a.N, a.B)) return launch_tc_gemm_ll_grad(a, ws, stream);
+    const int NB = a.N * a.B + a.F;
+    if (!tc_uses_fused_kernel(NB)) return launch_tc_gemm_ll_grad(a, ws, stream);
     int rc = tc_ensure_planes(a, ws, stream);
     if (rc) return rc;
-    const int NB = a.N * a.B;
     const int nch = (int)ceil_div(NB, kChunkF);
     const int nmt = (int)ceil_div(nch, 4);
     const int Kp = nch * kChunkF;
@@ -777,7 +776,7 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     for (int c0 = 0; c0 < a.ncols; c0 += kNcol) {
         const int nc = std::min(kNcol, a.ncols - c0);
         const int n_lo = a.n_lo + c0;
-        tc_prep_M_kernel<<<kNcol, 256, 0, stream>>>(a.w, a.A, a.W, a.bias, ws.sx, a.N, a.B, n_lo, nc, Kp, ws.Mp, ws.colpar);
+        tc_prep_M_kernel<<<kNcol, 256, 0, stream>>>(a.w, a.A, a.W, a.bias, ws.sx, a.N, a.B, a.F, n_lo, nc, Kp, ws.Mp, ws.colpar);
         PYGLM_CUDA(cudaGetLastError());
         TcKernelArgs k{};
         k.S = a.S; k.T = a.T; k.N = a.N; k.halo = a.halo; k.dt = (float)a.dt; k.nlin = a.nlin;
@@ -821,7 +820,7 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
             }
         }
         tc_final_kernel<<<(unsigned)(NB + 1), 32 * kFinalSlices, 0, stream>>>(
-            ws.part, nctas, nmt, a.N, a.B, n_lo, nc, ws.sx, a.A, a.W,
+            ws.part, nctas, nmt, a.N, a.B, a.F, n_lo, nc, ws.sx, a.A, a.W,
             a.out_ll + c0, a.out_gb ? a.out_gb + c0 : nullptr, a.out_gw ? a.out_gw + (int64_t)c0 * NB : nullptr);
         PYGLM_CUDA(cudaGetLastError());
     }

@@ -30,7 +30,7 @@ struct TcWorkspace {
 
 struct TcArgs {
     const float* X; int64_t ldx;
-    const uint8_t* S; int64_t T; int N; int halo; int B;
+    const uint8_t* S; int64_t T; int N; int halo; int B; int F;
     double dt; int nlin;
     int n_lo, ncols;
     const double* bias; const double* w; const int8_t* A; const double* W;
@@ -38,7 +38,7 @@ struct TcArgs {
 };
 
 bool tc_supported(int64_t T, int N, int B, int x_dtype);
-bool tc_uses_fused_kernel(int N, int B);
+bool tc_uses_fused_kernel(int64_t nfeat);
 // shared with the GEMM path
 int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,

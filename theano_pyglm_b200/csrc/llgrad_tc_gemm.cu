@@ -75,19 +75,19 @@ void tc_gemm_release(void* w)
 __global__ void __launch_bounds__(256)
 tc_gemm_prep_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A, const double* __restrict__ W,
                       const double* __restrict__ bias, const float* __restrict__ sx,
-                      int N, int B, int n_lo, int ncols, int Npr, int Kp, __half* __restrict__ Mp, float* __restrict__ colpar)
+                      int N, int B, int F, int n_lo, int ncols, int Npr, int Kp, __half* __restrict__ Mp, float* __restrict__ colpar)
 {
     __shared__ float smax[256];
     const int nl = blockIdx.x;
-    const int NB = N * B;
+    const int NS = N * B, NB = NS + F;         // spike-history features, all features
     const bool live = nl < ncols;
     const int n = n_lo + nl;
     float mx = 0.f;
     if (live) {
         for (int j = threadIdx.x; j < NB; j += 256) {
             const int pre = j / B;
-            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+            const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+            const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
             mx = fmaxf(mx, fabsf((float)((a * ww) * w[(int64_t)n * NB + j] / (double)sx[j])));
         }
     }
@@ -104,8 +104,8 @@ tc_gemm_prep_M_kernel(const double* __restrict__ w, const int8_t* __restrict__ A
         __half h1 = __float2half_rn(0.f), h2 = h1;
         if (live && j < NB) {
             const int pre = j / B;
-            const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-            const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+            const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+            const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
             const double v = (a * ww) * w[(int64_t)n * NB + j] / (double)sx[j] * (double)sm;
             h1 = __double2half(v);
             h2 = __double2half((v - (double)__half2float(h1)) * (double)kLoScale);
@@ -456,11 +456,11 @@ tc_gemm_final_ll_kernel(const double* __restrict__ part, int nctas, int Npr, int
 }
 
 __global__ void __launch_bounds__(256)
-tc_gemm_final_G_kernel(const double* __restrict__ Gp, int splits, int64_t NBp, int Npr, int N, int B, int n_lo, int ncols,
+tc_gemm_final_G_kernel(const double* __restrict__ Gp, int splits, int64_t NBp, int Npr, int N, int B, int F, int n_lo, int ncols,
                        const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
                        double* __restrict__ out_gw)
 {
-    const int64_t NB = (int64_t)N * B;
+    const int64_t NS = (int64_t)N * B, NB = NS + F;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (j, nl), nl fastest: coalesced partial reads
     if (idx >= NB * ncols) return;
     const int64_t j = idx / ncols;
@@ -468,8 +468,8 @@ tc_gemm_final_G_kernel(const double* __restrict__ Gp, int splits, int64_t NBp, i
     double s = 0.0;
     for (int z = 0; z < splits; ++z) s += Gp[((int64_t)z * NBp + j) * Npr + nl];
     const int n = n_lo + nl, pre = (int)(j / B);
-    const double a = A ? (double)A[(int64_t)pre * N + n] : 1.0;
-    const double ww = W ? W[(int64_t)pre * N + n] : 1.0;
+    const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+    const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
     out_gw[(int64_t)nl * NB + j] = (a * ww) * s / ((double)sx[j] * (double)kRScale);
 }
 
@@ -481,7 +481,7 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if (rc) return rc;
     if (!ws.gemm) ws.gemm = new GemmWorkspace();
     GemmWorkspace& g = *static_cast<GemmWorkspace*>(ws.gemm);
-    const int NB = a.N * a.B;
+    const int NB = a.N * a.B + a.F;
     const int nkc = (int)ceil_div(NB, 32);
     const int Kp = nkc * 32;
     const int Npr = (int)round_up(a.ncols, kGN);
@@ -498,7 +498,7 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if ((rc = ensure((void**)&g.part, &g.part_elems, (size_t)nctas * 4 * Npr * 2, sizeof(double)))) return rc;
 
     PYGLM_CUDA(cudaMemsetAsync(g.part, 0, (size_t)nctas * 4 * Npr * 2 * sizeof(double), stream));
-    tc_gemm_prep_M_kernel<<<Npr, 256, 0, stream>>>(a.w, a.A, a.W, a.bias, ws.sx, a.N, a.B, a.n_lo, a.ncols, Npr, Kp, g.Mp, g.colpar);
+    tc_gemm_prep_M_kernel<<<Npr, 256, 0, stream>>>(a.w, a.A, a.W, a.bias, ws.sx, a.N, a.B, a.F, a.n_lo, a.ncols, Npr, Kp, g.Mp, g.colpar);
     PYGLM_CUDA(cudaGetLastError());
 
     const CUtensorMap* xmaps = static_cast<const CUtensorMap*>(ws.tmaps);
@@ -538,7 +538,7 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     tc_gemm_bwd_kernel<<<gridb, kGThreads, smem_b, stream>>>(g.mapX64[0], g.mapX64[1], mR1, mR2, b);
     PYGLM_CUDA(cudaGetLastError());
     tc_gemm_final_G_kernel<<<(unsigned)ceil_div((int64_t)NB * a.ncols, 256), 256, 0, stream>>>(
-        g.Gp, (int)splits, NBp, Npr, a.N, a.B, a.n_lo, a.ncols, ws.sx, a.A, a.W, a.out_gw);
+        g.Gp, (int)splits, NBp, Npr, a.N, a.B, a.F, a.n_lo, a.ncols, ws.sx, a.A, a.W, a.out_gw);
     PYGLM_CUDA(cudaGetLastError());
     return PYGLM_B200_OK;
 }

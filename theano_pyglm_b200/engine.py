@@ -21,7 +21,8 @@ _NLINS = {"exp": NLIN_EXP, "explinear": NLIN_SOFTPLUS, "softplus": NLIN_SOFTPLUS
 
 EXPORTS = [
     "pyglm_b200_last_error", "pyglm_b200_abi_version",
-    "pyglm_b200_dataset_create", "pyglm_b200_dataset_destroy", "pyglm_b200_dataset_info",
+    "pyglm_b200_dataset_create", "pyglm_b200_dataset_create_stim", "pyglm_b200_dataset_destroy",
+    "pyglm_b200_dataset_num_stim", "pyglm_b200_filter_dense", "pyglm_b200_dataset_info",
     "pyglm_b200_dataset_get_fS", "pyglm_b200_dataset_device_X", "pyglm_b200_dataset_device_S",
     "pyglm_b200_dataset_refilter",
     "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_firing_rate",
@@ -51,6 +52,10 @@ def load_library():
     lib.pyglm_b200_last_error.argtypes = []
     lib.pyglm_b200_abi_version.restype = i32
     lib.pyglm_b200_dataset_create.argtypes = [p, i64, i32, i32, f64, p, i32, i32, i32, i32, C.POINTER(p)]
+    lib.pyglm_b200_dataset_create_stim.argtypes = [p, i64, i32, i32, f64, p, i32, i32, p, i32, i32, i32, C.POINTER(p)]
+    lib.pyglm_b200_dataset_num_stim.argtypes = [p]
+    lib.pyglm_b200_dataset_num_stim.restype = i32
+    lib.pyglm_b200_filter_dense.argtypes = [p, i64, i32, p, i32, i32, i32, p]
     lib.pyglm_b200_dataset_destroy.argtypes = [p]
     lib.pyglm_b200_dataset_info.argtypes = [p] + [p] * 7
     lib.pyglm_b200_dataset_get_fS.argtypes = [p, p]
@@ -109,10 +114,25 @@ def nlin_code(nlin):
     return int(nlin)
 
 
-class Dataset:
-    """One data sequence resident on one GPU: spikes + filtered spike train X (K1 output)."""
+def filter_dense(stim, ibasis, device=0):
+    """convolve_with_basis for a real-valued signal (utils/basis.py:201-236; the stimulus projection of
+    bkgd.py:145): stim (T, D), ibasis (R, B) -> (T, D, B) float64, computed on the GPU in FP64."""
+    stim = _f64(stim)
+    if stim.ndim == 1:
+        stim = stim.reshape(-1, 1)
+    ibasis = _f64(ibasis)
+    T, D = stim.shape
+    R, B = ibasis.shape
+    out = np.empty((T, D * B))
+    _check(load_library().pyglm_b200_filter_dense(_ptr(stim), T, D, _ptr(ibasis), R, B, int(device), _ptr(out)))
+    return out.reshape(T, D, B)
 
-    def __init__(self, S, dt, ibasis, halo=0, x_dtype="f32", device=0):
+
+class Dataset:
+    """One data sequence resident on one GPU: spikes + filtered spike train X (K1 output), optionally
+    followed by F filtered-stimulus features `fstim` (T, F) (data['fstim'], bkgd.py:154)."""
+
+    def __init__(self, S, dt, ibasis, halo=0, x_dtype="f32", device=0, fstim=None):
         lib = load_library()
         S = spikes_to_u8(S)
         if S.ndim != 2:
@@ -129,9 +149,17 @@ class Dataset:
         self.x_dtype = (X_F64 if x_dtype in ("f64", X_F64, np.float64) else
                         X_PLANES if x_dtype in ("planes", X_PLANES) else X_F32)
         self.h2d_bytes = S.nbytes + ibasis.nbytes
+        self.F = 0
+        if fstim is not None and np.size(fstim):
+            fstim = _f64(fstim)
+            if fstim.ndim != 2 or fstim.shape[0] != self.T:
+                raise ValueError("fstim must be (T, F) with T = %d bins" % self.T)
+            self.F = int(fstim.shape[1])
+            self.h2d_bytes += fstim.nbytes
         h = C.c_void_p()
-        _check(lib.pyglm_b200_dataset_create(_ptr(S), self.T, self.halo, self.N, self.dt, _ptr(ibasis),
-                                             self.R, self.B, self.x_dtype, self.device, C.byref(h)))
+        _check(lib.pyglm_b200_dataset_create_stim(_ptr(S), self.T, self.halo, self.N, self.dt, _ptr(ibasis),
+                                                  self.R, self.B, _ptr(fstim) if self.F else None, self.F,
+                                                  self.x_dtype, self.device, C.byref(h)))
         self._h = h
         ldx = C.c_int64()
         _check(lib.pyglm_b200_dataset_info(h, None, None, None, None, C.addressof(ldx), None, None))
@@ -163,28 +191,41 @@ class Dataset:
         return load_library().pyglm_b200_dataset_device_X(self._h)
 
     # -- K2
-    def _params(self, bias, w, A, W):
+    def _params(self, bias, w, A, W, w_stim=None):
         N, NB = self.N, self.N * self.B
         bias = _f64(bias, (N,))
         w = _f64(w, (N, NB))
+        if self.F:
+            if w_stim is None:
+                raise ValueError("this dataset carries %d stimulus features: pass w_stim (N, F)" % self.F)
+            w = np.ascontiguousarray(np.concatenate([w, _f64(w_stim, (N, self.F))], axis=1))
+        elif w_stim is not None and np.size(w_stim):
+            raise ValueError("w_stim given but the dataset has no stimulus features")
         A = None if A is None else np.ascontiguousarray(A, dtype=np.int8).reshape(N, N)
         W = None if W is None else _f64(W, (N, N))
         return bias, w, A, W
 
-    def ll_grad(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto", grad=True):
-        """(ll, g_bias, g_w) for neurons [n_lo, n_hi); host buffers in and out (the e2e call)."""
+    def ll_grad(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto", grad=True,
+                w_stim=None):
+        """(ll, g_bias, g_w) for neurons [n_lo, n_hi); host buffers in and out (the e2e call).
+        On a dataset with stimulus features, pass w_stim (N, F) and get (ll, g_bias, g_w, g_w_stim)."""
         n_hi = self.N if n_hi is None else n_hi
         nc = n_hi - n_lo
-        bias, w, A, W = self._params(bias, w, A, W)
+        bias, w, A, W = self._params(bias, w, A, W, w_stim)
+        NB = self.N * self.B
         ll = np.empty(nc)
         gb = np.empty(nc) if grad else None
-        gw = np.empty((nc, self.N * self.B)) if grad else None
+        gw = np.empty((nc, NB + self.F)) if grad else None
         _check(load_library().pyglm_b200_ll_grad(self._h, _ptr(bias), _ptr(w), _ptr(A), _ptr(W), nlin_code(nlin),
                                                  n_lo, n_hi, _PATHS.get(path, path), _ptr(ll), _ptr(gb), _ptr(gw)))
-        return (ll, gb, gw) if grad else ll
+        if not grad:
+            return ll
+        if self.F:
+            return ll, gb, np.ascontiguousarray(gw[:, :NB]), np.ascontiguousarray(gw[:, NB:])
+        return ll, gb, gw
 
-    def ll(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto"):
-        return self.ll_grad(bias, w, A, W, nlin, n_lo, n_hi, path, grad=False)
+    def ll(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto", w_stim=None):
+        return self.ll_grad(bias, w, A, W, nlin, n_lo, n_hi, path, grad=False, w_stim=w_stim)
 
     def ll_grad_dev(self, d_bias, d_w, d_A, d_W, nlin, n_lo, n_hi, path, d_ll, d_gb, d_gw, stream):
         """Device-pointer variant: arguments are integer device addresses (tensor.data_ptr())."""
@@ -197,7 +238,7 @@ class Dataset:
     def path_info(self, path="auto"):
         """What a call with `path` runs on this dataset (used by bench.py's roofline bookkeeping)."""
         use = load_library().pyglm_b200_resolve_path(self._h, _PATHS.get(path, path))
-        if use == PATH_TC and self.N * self.B > 160:
+        if use == PATH_TC and self.N * self.B + self.F > 160:
             return dict(name="tcgen05-gemm-f16split", dtype="f16x2-split/f32-acc/f64-sum", x_passes=2,
                         launches_per_eval=5, bound="tensor", kernel="tc_gemm_fwd_kernel+tc_gemm_bwd_kernel")
         if use == PATH_TC:
@@ -208,18 +249,18 @@ class Dataset:
                         kernel="simt_fwd_kernel+simt_bwd_kernel")
         raise EngineError("path %r unsupported for this dataset" % (path,))
 
-    def firing_rate(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None):
+    def firing_rate(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, w_stim=None):
         n_hi = self.N if n_hi is None else n_hi
-        bias, w, A, W = self._params(bias, w, A, W)
+        bias, w, A, W = self._params(bias, w, A, W, w_stim)
         out = np.empty((self.T, n_hi - n_lo))
         _check(load_library().pyglm_b200_firing_rate(self._h, _ptr(bias), _ptr(w), _ptr(A), _ptr(W), nlin_code(nlin),
                                                      n_lo, n_hi, _ptr(out)))
         return out
 
     # -- K4
-    def gibbs_begin(self, bias, w, A, W, nlin="explinear", n_lo=0, n_hi=None):
+    def gibbs_begin(self, bias, w, A, W, nlin="explinear", n_lo=0, n_hi=None, w_stim=None):
         n_hi = self.N if n_hi is None else n_hi
-        bias, w, A, W = self._params(bias, w, A, W)
+        bias, w, A, W = self._params(bias, w, A, W, w_stim)
         _check(load_library().pyglm_b200_gibbs_begin(self._h, _ptr(bias), _ptr(w), _ptr(A), _ptr(W), nlin_code(nlin),
                                                      n_lo, n_hi))
 

@@ -66,3 +66,9 @@ class Glm(Component):
         bias = np.array([self.bias_model.I_bias(x['glms'][n]['bias']) for n in range(N)], dtype=np.float64)
         w = np.stack([self.imp_model.weights(x['glms'][n]['imp']).reshape(-1) for n in range(N)])
         return bias, w, self.network.A(x['net']), self.network.W(x['net'])
+
+    def stim_weights(self, x):
+        """w_stim (N, F) of the state dict, or None when the model has no stimulus (bkgd.py:81)."""
+        if not self.bkgd_model.n_vars:
+            return None
+        return np.stack([self.bkgd_model.weights(x['glms'][n]['bkgd']) for n in range(self.model['N'])])

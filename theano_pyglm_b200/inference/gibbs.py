@@ -87,8 +87,14 @@ class HmcBiasUpdate(_HmcGlmBlockUpdate):
         return self._run(x, n, None, None, slice(0, 1))
 
 
-class HmcBkgdUpdate(ParallelMetropolisHastingsUpdate):
-    """gibbs.py:324-446; nothing to sample for the `none` background model."""
+class HmcBkgdUpdate(_HmcGlmBlockUpdate):
+    """gibbs.py:324-446: HMC on w_stim; nothing to sample for the `none` background model.  (The reference's
+    gradient drops the prior term, :400 -- see SURVEY appendix A; here the full log posterior is used.)"""
+    n_steps = 10
+
+    def update(self, x, n):
+        F = self.population.glm.bkgd_model.n_vars
+        return self._run(x, n, None, None, slice(1, 1 + F)) if F else x
 
 
 class HmcImpulseUpdate(_HmcGlmBlockUpdate):
@@ -96,8 +102,8 @@ class HmcImpulseUpdate(_HmcGlmBlockUpdate):
     n_steps = 10
 
     def update(self, x, n):
-        D = 1 + self.population.N * self.population.glm.imp_model.B
-        return self._run(x, n, None, None, slice(1, D))
+        o = 1 + self.population.glm.bkgd_model.n_vars         # vector order: bias, w_stim, w_ir
+        return self._run(x, n, None, None, slice(o, o + self.population.N * self.population.glm.imp_model.B))
 
 
 class HmcDirichletImpulseUpdate(_HmcGlmBlockUpdate):
@@ -114,7 +120,8 @@ class HmcDirichletImpulseUpdate(_HmcGlmBlockUpdate):
             key = 'g_%d' % n_pre
             if A[n_pre, n_post]:
                 k = names.index(key)
-                self._run(x, n_post, None, None, slice(1 + k * imp.B, 1 + (k + 1) * imp.B))
+                o = 1 + popn.glm.bkgd_model.n_vars
+                self._run(x, n_post, None, None, slice(o + k * imp.B, o + (k + 1) * imp.B))
             else:
                 x['glms'][n_post]['imp'][key] = np.random.gamma(imp.alpha, np.ones(imp.B))
         return x
@@ -148,7 +155,7 @@ class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
         popn = self.population
         bias, w, A, W = popn.glm.engine_params(x)
         ds = popn._handle()
-        ds.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code)
+        ds.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code, w_stim=popn.glm.stim_weights(x))
         self._resident = ds
         return ds
 

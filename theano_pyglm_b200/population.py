@@ -71,7 +71,7 @@ class Population:
         self.network.preprocess_data(data)
         self.glm.preprocess_data(data)
         data['_b200'] = engine.Dataset(data['S'], self.model['dt'], self.glm.imp_model.ibasis,
-                                       x_dtype=self.x_dtype, device=self.device)
+                                       x_dtype=self.x_dtype, device=self.device, fstim=data.get('fstim'))
         data['preprocessed'] = True
         return data
 
@@ -107,11 +107,16 @@ class Population:
         ll (n,), g_bias (n,), g_w (n, N*B) for neurons [n_lo, n_hi)."""
         bias, w, A, W = self.glm.engine_params(x)
         return self._handle(data).ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
-                                          path=self.path, grad=grad)
+                                          path=self.path, grad=grad, w_stim=self.glm.stim_weights(x))
 
     def compute_ll(self, vars):
         """sum_n ll_n on the current data sequence (population.py:71-86)."""
         return float(np.sum(self.ll_grad(vars, grad=False)))
+
+    def _ll_grad_blocks(self, data, bias, w, A, W, ws, **kw):
+        """ll, g_bias, g_w, g_w_stim (zero-width when the model has no stimulus) on one sequence."""
+        out = data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, path=self.path, w_stim=ws, **kw)
+        return out if len(out) == 4 else out + (np.zeros((len(out[0]), 0)),)
 
     def compute_log_prior(self, vars):
         lp = 0.0
@@ -132,29 +137,34 @@ class Population:
 
     def glm_log_p_grad(self, x, n):
         """log posterior of neuron n's GLM variables and its gradient as a flat vector in the
-        reference's sorted-key order (bias, imp): what coord_descent.nlp/grad_nlp evaluate
+        reference's sorted-key order (bias, bkgd, imp): what coord_descent.nlp/grad_nlp evaluate
         (coord_descent.py:40-80) -- prior plus the likelihood summed over data sequences."""
         xn = x['glms'][n]
         lp = self.glm.log_prior(xn)
         gp = self.glm.grad_log_prior(xn)
         bias, w, A, W = self.glm.engine_params(x)
-        g_bias, g_w = 0.0, 0.0
+        ws = self.glm.stim_weights(x)
+        g_bias, g_w, g_s = 0.0, 0.0, 0.0
         scale = self.glm.lkhd_scale.get_value()
         for data in self.data_sequences:
-            ll, gb, gw = data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, n_lo=n, n_hi=n + 1,
-                                               path=self.path)
+            ll, gb, gw, gs = self._ll_grad_blocks(data, bias, w, A, W, ws, n_lo=n, n_hi=n + 1)
             lp += scale * ll[0]
             g_bias = g_bias + scale * gb[0]
             g_w = g_w + scale * gw[0]
+            g_s = g_s + scale * gs[0]
         g_imp = self.glm.imp_model.chain_rule(xn['imp'], g_w)
         parts = [gp['bias']['bias'] + g_bias]
+        if ws is not None:
+            parts.append(gp['bkgd']['w_stim'] + g_s)
         for k in sorted(g_imp):
             parts.append(gp['imp'][k] + g_imp[k])
         return float(lp), np.concatenate([np.ravel(p) for p in parts])
 
     def glm_param_vector(self, xn):
-        """Differentiable GLM variables of one neuron as a flat vector, sorted-key order (bias < imp)."""
+        """Differentiable GLM variables of one neuron as a flat vector, sorted-key order (bias < bkgd < imp)."""
         parts = [np.ravel(xn['bias']['bias'])]
+        if self.glm.bkgd_model.n_vars:
+            parts.append(np.ravel(xn['bkgd']['w_stim']))
         for k in sorted(self.glm.imp_model.get_variables()):
             parts.append(np.ravel(xn['imp'][k]))
         return np.concatenate(parts).astype(np.float64)
@@ -162,6 +172,10 @@ class Population:
     def set_glm_param_vector(self, xn, vec):
         xn['bias']['bias'] = np.array(vec[:1], dtype=np.float64)
         off = 1
+        F = self.glm.bkgd_model.n_vars
+        if F:
+            xn['bkgd']['w_stim'] = np.array(vec[off:off + F], dtype=np.float64)
+            off += F
         for k, shp in sorted(self.glm.imp_model.get_variables().items()):
             sz = int(np.prod(shp))
             xn['imp'][k] = np.array(vec[off:off + sz], dtype=np.float64).reshape(shp)
@@ -171,17 +185,21 @@ class Population:
         """The per-neuron log posteriors of coord_descent.nlp/grad_nlp for ALL neurons from one engine call
         per data sequence: lp (N,), grad (N, D) in the order of `glm_param_vector`."""
         bias, w, A, W = self.glm.engine_params(x)
+        ws = self.glm.stim_weights(x)
         scale = self.glm.lkhd_scale.get_value()
-        ll, gb, gw = 0.0, 0.0, 0.0
+        ll, gb, gw, gs = 0.0, 0.0, 0.0, 0.0
         for data in self.data_sequences:
-            l, b, g = data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, path=self.path)
-            ll, gb, gw = ll + scale * l, gb + scale * b, gw + scale * g
+            l, b, g, s = self._ll_grad_blocks(data, bias, w, A, W, ws)
+            ll, gb, gw, gs = ll + scale * l, gb + scale * b, gw + scale * g, gs + scale * s
         lps, grads = [], []
         for n in range(self.N):
             xn = x['glms'][n]
             gp = self.glm.grad_log_prior(xn)
             g_imp = self.glm.imp_model.chain_rule(xn['imp'], gw[n])
-            parts = [gp['bias']['bias'] + gb[n]] + [np.ravel(gp['imp'][k] + g_imp[k]) for k in sorted(g_imp)]
+            parts = [gp['bias']['bias'] + gb[n]]
+            if ws is not None:
+                parts.append(gp['bkgd']['w_stim'] + gs[n])
+            parts += [np.ravel(gp['imp'][k] + g_imp[k]) for k in sorted(g_imp)]
             lps.append(self.glm.log_prior(xn) + ll[n])
             grads.append(np.concatenate(parts))
         return np.array(lps), np.stack(grads)
@@ -189,7 +207,8 @@ class Population:
     def eval_state(self, vars):
         """Firing rates and currents for the current state (population.py:88-123), engine-side lam."""
         bias, w, A, W = self.glm.engine_params(vars)
-        lam = self._handle().firing_rate(bias, w, A, W, nlin=self.glm.nlin_model.code)
+        lam = self._handle().firing_rate(bias, w, A, W, nlin=self.glm.nlin_model.code,
+                                         w_stim=self.glm.stim_weights(vars))
         state = {'net': {'graph': {'A': A if A is not None else np.ones((self.N, self.N))},
                          'weights': {'W': W if W is not None else np.ones((self.N, self.N))}},
                  'glms': []}
