@@ -13,53 +13,114 @@
 // base current, u and the spike are read once per bin and all Q candidates stay in registers.
 // Everything is FP64 with a fixed reduction order: the sampler's accept/reject decision
 // compares differences of these sums against logit(u), so results must be reproducible.
+#include <math_constants.h>
+
 #include "common.cuh"
 
 namespace pyglm {
 
+#ifndef PYGLM_GIBBS_MINBLOCKS
+#define PYGLM_GIBBS_MINBLOCKS 2      // 128 registers: two resident blocks per SM
+#endif
 constexpr int kGibbsThreads = 256;
 constexpr int kGibbsChunk = 8192;     // bins per block
 
 int gibbs_num_chunks(int64_t T) { return (int)ceil_div(T, kGibbsChunk); }
 
-// log(1+e^x) in FP64 for any x through the library functions (spike bins with x < 0, where log(lam) needs
-// lam to full RELATIVE accuracy)
-__device__ __forceinline__ double softplus_f64(double x)
-{
-    const double e = exp(-fabs(x));
-    const double l1p = e < 1e-16 ? e : log1p(e);
-    return x > 0.0 ? x + l1p : l1p;
-}
-
 // The per-bin rate of the softplus model is lam = max(x,0) + L(|x|), L(a) = log1p(e^-a).  The sampler evaluates
-// it (Q+1) T times per edge and the library exp + log1p pair costs ~95 instructions, so L is tabulated
-// instead: 149 intervals of width 1/4 centred on a = i/4, a degree-9 polynomial in z = 8(a - i/4) on each
-// (Chebyshev interpolant expanded in monomials, built once on the host in long double).  Absolute error
-// < 1e-16 on [0, 37]; beyond 37, L < 8.6e-17 and only matters (to 1e-19 per bin) when x < 0.
+// it (Q+1) T times per edge.  The library exp + log1p pair costs ~95 instructions per evaluation and its
+// branches keep the Q+1 candidates of a bin from overlapping, so L is computed by range instead
+// (absolute error < 1e-16 everywhere):
+//   a >= 5.5 : e = e^-a by Cody-Waite reduction and a degree-10 polynomial (coefficients in the constant bank),
+//              then L = e q, q = 1 - e/2 + e^2/3 - ... - e^5/6  (e < 4.1e-3).  ~25 FP64 operations, no branch and
+//              no memory access: the candidates' dependency chains interleave and keep the FP64 pipe busy.
+//   a < 5.5  : 23 intervals of width 1/4 centred on a = i/4, a degree-9 polynomial in z = 8(a - i/4) on each,
+//              coefficients in shared memory.  Applied as a fix-up after the branch-free pass, only in warps
+//              where some lane needs it.
+// Both polynomial sets are Chebyshev interpolants expanded in monomials, built once on the host in long double.
 constexpr int kSpDeg = 9;
-constexpr int kSpRows = 149;
-constexpr double kSpMax = 37.0;
+constexpr int kSpRows = 23;
+constexpr int kSpExpDeg = 10;
+constexpr double kSpSplit = 5.5;
+constexpr double kSpClamp = 708.0;                       // e^-708 is the smallest normal result
 constexpr double kSpMagic = 6755399441055744.0;          // 1.5 * 2^52: adding it rounds to the nearest integer
 __device__ double g_softplus_tab[kSpRows * (kSpDeg + 1)];
+__constant__ double c_sp_exp[kSpExpDeg + 1];
 
-__device__ __forceinline__ double softplus_tab(double x, const double* __restrict__ tab)
+// e = e^-a and q with L(a) = e q, for a in [5.5, 708] (finite garbage below 5.5; callers replace it)
+__device__ __forceinline__ void sp_exp_series(double a, double& e, double& q)
+{
+    const double t = fma(a, -1.4426950408889634, kSpMagic);
+    const int n = __double2loint(t);                      // rint(-a log2(e)) in [-1021, -8]
+    const double fn = t - kSpMagic;
+    double r = fma(fn, -6.93147180369123816490e-01, -a);
+    r = fma(fn, -1.90821492927058770002e-10, r);          // r = -a - n ln2, |r| <= ln2/2
+    double p = c_sp_exp[kSpExpDeg];
+#pragma unroll
+    for (int k = kSpExpDeg - 1; k >= 0; --k) p = fma(p, r, c_sp_exp[k]);
+    e = p * __hiloint2double((n + 1023) << 20, 0);
+    q = fma(e, -1.0 / 6.0, 0.2);
+    q = fma(q, e, -0.25);
+    q = fma(q, e, 1.0 / 3.0);
+    q = fma(q, e, -0.5);
+    q = fma(q, e, 1.0);
+}
+
+// L(a) for a < 5.5 from the shared-memory table
+__device__ __forceinline__ double sp_table(double a, const double* __restrict__ tab)
+{
+    const double tm = fma(a, 4.0, kSpMagic);
+    const int i = __double2loint(tm);                     // rint(4a) in 0..22
+    const double fi = tm - kSpMagic;
+    const double z = fma(a, 8.0, -2.0 * fi);              // in [-1, 1]
+    const double* __restrict__ r = tab + i * (kSpDeg + 1);
+    double p = r[kSpDeg];
+#pragma unroll
+    for (int k = kSpDeg - 1; k >= 0; --k) p = fma(p, z, r[k]);
+    return p;
+}
+
+// log(softplus(x)) for one value (spike bins).  For x <= -5.5, lam = e^x q exactly, so log(lam) = x + log(q)
+// with log(q) from the series of log1p(q - 1): full relative accuracy without an FP64 log.  Where e^x
+// underflows the reference formula gives log(0) = -inf (nlin.py:43, glm.py:52), and so does this.
+__device__ __forceinline__ double log_softplus(double x, const double* __restrict__ tab)
 {
     const double a = fabs(x);
-    double l1p;
-    if (a < kSpMax) {
-        const double tm = fma(a, 4.0, kSpMagic);
-        const int i = __double2loint(tm);                 // rint(4a) in 0..148
-        const double fi = tm - kSpMagic;
-        const double z = fma(a, 8.0, -2.0 * fi);          // in [-1, 1]
-        const double* __restrict__ r = tab + i * (kSpDeg + 1);
-        double p = r[kSpDeg];
-#pragma unroll
-        for (int k = kSpDeg - 1; k >= 0; --k) p = fma(p, z, r[k]);
-        l1p = p;
-    } else {
-        l1p = x < 0.0 ? (double)__expf((float)x) : 0.0;
+    if (a < kSpSplit) return log(fmax(x, 0.0) + sp_table(a, tab));
+    double e, q;
+    sp_exp_series(fmin(a, kSpClamp), e, q);
+    if (x > 0.0) return log(x + e * q);
+    if (x < -745.1332191019411) return -CUDART_INF;
+    const double d = q - 1.0;                             // |d| < 2.1e-3
+    double l = fma(d, 0.2, -0.25);
+    l = fma(l, d, 1.0 / 3.0);
+    l = fma(l, d, -0.5);
+    l = fma(l, d, 1.0);
+    return fma(l, d, x);
+}
+
+// Chebyshev interpolant of f on [c-h, c+h] of degree n-1, returned as monomial coefficients in (x - c)/h
+template <int n, typename Fn>
+static void cheb_monomial(Fn f, long double c, long double h, long double* out)
+{
+    long double Tm[n][n] = {};                            // Chebyshev polynomials as monomial coefficient rows
+    Tm[0][0] = 1;
+    if (n > 1) Tm[1][1] = 1;
+    for (int k = 2; k < n; ++k)
+        for (int j = 0; j <= k; ++j) Tm[k][j] = (j ? 2 * Tm[k - 1][j - 1] : 0) - Tm[k - 2][j];
+    const long double pi = acosl(-1.0L);
+    long double fv[n], cheb[n];
+    for (int k = 0; k < n; ++k) fv[k] = f(c + h * cosl(pi * (k + 0.5L) / n));
+    for (int j = 0; j < n; ++j) {
+        long double acc = 0;
+        for (int k = 0; k < n; ++k) acc += fv[k] * cosl(pi * j * (k + 0.5L) / n);
+        cheb[j] = acc * (j ? 2.0L : 1.0L) / n;
     }
-    return fmax(x, 0.0) + l1p;
+    for (int j = 0; j < n; ++j) {
+        long double m = 0;
+        for (int k = j; k < n; ++k) m += cheb[k] * Tm[k][j];
+        out[j] = m;
+    }
 }
 
 static int ensure_softplus_table()
@@ -70,34 +131,26 @@ static int ensure_softplus_table()
     if (dev >= 0 && dev < 64 && done[dev]) return PYGLM_B200_OK;
     constexpr int n = kSpDeg + 1;
     static double tab[kSpRows * n];
-    long double Tm[n][n] = {};                            // Chebyshev polynomials as monomial coefficient rows
-    Tm[0][0] = 1; Tm[1][1] = 1;
-    for (int k = 2; k < n; ++k)
-        for (int j = 0; j <= k; ++j) Tm[k][j] = (j ? 2 * Tm[k - 1][j - 1] : 0) - Tm[k - 2][j];
-    const long double pi = acosl(-1.0L);
+    long double m[16];
     for (int i = 0; i < kSpRows; ++i) {
-        long double f[n], cheb[n];
-        for (int k = 0; k < n; ++k) f[k] = log1pl(expl(-(0.25L * i + 0.125L * cosl(pi * (k + 0.5L) / n))));
-        for (int j = 0; j < n; ++j) {
-            long double acc = 0;
-            for (int k = 0; k < n; ++k) acc += f[k] * cosl(pi * j * (k + 0.5L) / n);
-            cheb[j] = acc * (j ? 2.0L : 1.0L) / n;
-        }
-        for (int j = 0; j < n; ++j) {
-            long double m = 0;
-            for (int k = j; k < n; ++k) m += cheb[k] * Tm[k][j];
-            tab[i * n + j] = (double)m;
-        }
+        cheb_monomial<n>([](long double a) { return log1pl(expl(-a)); }, 0.25L * i, 0.125L, m);
+        for (int j = 0; j < n; ++j) tab[i * n + j] = (double)m[j];
     }
+    double ce[kSpExpDeg + 1];
+    const long double h = 0.3470L;                        // |r| <= ln2/2 = 0.34657...
+    cheb_monomial<kSpExpDeg + 1>([](long double r) { return expl(r); }, 0.0L, h, m);
+    long double hp = 1;
+    for (int j = 0; j <= kSpExpDeg; ++j) { ce[j] = (double)(m[j] / hp); hp *= h; }
     PYGLM_CUDA(cudaMemcpyToSymbol(g_softplus_tab, tab, sizeof(tab)));
+    PYGLM_CUDA(cudaMemcpyToSymbol(c_sp_exp, ce, sizeof(ce)));
     if (dev >= 0 && dev < 64) done[dev] = true;
     return PYGLM_B200_OK;
 }
 
 // log(lam) of the Poisson term is needed only in the ~2% of bins that hold a spike.  Those bins are handed to
 // the whole warp: lane q evaluates candidate q, so one FP64 log serves all candidates.
-template <typename XT, int QMAX, int NLIN>
-__global__ void __launch_bounds__(kGibbsThreads)
+template <typename XT, int QMAX, int NLIN, int BMAX>
+__global__ void __launch_bounds__(kGibbsThreads, PYGLM_GIBBS_MINBLOCKS)
 gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t* __restrict__ pres,
                    int Q, const double* __restrict__ wcand)
 {
@@ -113,7 +166,7 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t NB = (int64_t)g.N * g.B + g.F;           // row pitch of w: all features
 
-    if (tid < g.B) sW[tid] = g.w[(int64_t)col * NB + (int64_t)pre * g.B + tid];
+    if (tid < kMaxBasis) sW[tid] = tid < g.B ? g.w[(int64_t)col * NB + (int64_t)pre * g.B + tid] : 0.0;
     if (NLIN == PYGLM_B200_NLIN_SOFTPLUS)
         for (int i = tid; i < kSpRows * (kSpDeg + 1); i += kGibbsThreads) sTab[i] = g_softplus_tab[i];
     __syncthreads();
@@ -135,48 +188,76 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     const uint8_t* __restrict__ st = g.St + (int64_t)col * g.T;
     const XT* __restrict__ xcol = X + (int64_t)pre * g.B * g.T;      // feature-major copy: Xt[j][t]
 
+    // the operands of the next 256 bins are fetched while the current ones are evaluated
+    XT xr[BMAX];
+    double ir;
+    unsigned sr;
+#define PYGLM_GIBBS_FETCH(TT)                                                                   \
+    do {                                                                                        \
+        const int64_t tt_ = (TT);                                                               \
+        const bool lv_ = tt_ < tend;                                                            \
+        _Pragma("unroll") for (int b = 0; b < BMAX; ++b)                                        \
+            xr[b] = (lv_ && b < g.B) ? xcol[(int64_t)b * g.T + tt_] : (XT)0;                    \
+        ir = lv_ ? inet[tt_] : 0.0;                                                             \
+        sr = lv_ ? (unsigned)st[tt_] : 0u;                                                      \
+    } while (0)
+    PYGLM_GIBBS_FETCH(tbeg + tid);
+
     for (int64_t t0 = tbeg; t0 < tend; t0 += kGibbsThreads) {        // warp-uniform trip count
-        const int64_t t = t0 + tid;
-        const bool live = t < tend;
-        double u = 0.0, base = 0.0, s = 0.0;
-        if (live) {
-            for (int b = 0; b < g.B; ++b) u += (double)xcol[(int64_t)b * g.T + t] * sW[b];
-            base = bias + (inet[t] - aw_old * u);
-            s = (double)st[t];
-        }
-        if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
-            if (live) {
+        const bool live = t0 + tid < tend;
+        double u = 0.0;
 #pragma unroll
-                for (int q = 0; q < QMAX; ++q)
-                    if (q < Q) acc[q] -= g.dt * softplus_tab(base + wq[q] * u, sTab);
+        for (int b = 0; b < BMAX; ++b) u = fma((double)xr[b], sW[b], u);
+        const double base = bias + (ir - aw_old * u);
+        const double s = (double)sr;
+        PYGLM_GIBBS_FETCH(t0 + kGibbsThreads + tid);
+        const double keep = live ? 1.0 : 0.0;                        // lanes past the end evaluate a dummy bin
+
+        if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
+            double lam[QMAX];
+            bool small = false;
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) {                         // branch-free pass: Q independent chains
+                const double x = fma(wq[q], u, base);
+                const double a = fabs(x);
+                double e, qq;
+                sp_exp_series(fmin(a, kSpClamp), e, qq);
+                lam[q] = fmax(x, 0.0) + e * qq;
+                small |= a < kSpSplit;
             }
+            if (__any_sync(0xffffffffu, small)) {                    // fix-up pass: |x| < 5.5 from the table
+#pragma unroll
+                for (int q = 0; q < QMAX; ++q) {
+                    const double x = fma(wq[q], u, base);
+                    const double a = fabs(x);
+                    if (a < kSpSplit) lam[q] = fmax(x, 0.0) + sp_table(a, sTab);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < QMAX; ++q) acc[q] = fma(keep, lam[q], acc[q]);
             // spike bins (~2%): one lane per candidate evaluates log(lam) for the whole warp
-            unsigned mask = __ballot_sync(0xffffffffu, live && s != 0.0);
+            unsigned mask = __ballot_sync(0xffffffffu, live && s != 0.0);   // (sr already holds the next bin)
             while (mask) {
                 const int src = __ffs(mask) - 1;
                 mask &= mask - 1;
                 const double bs = __shfl_sync(0xffffffffu, base, src);
                 const double us = __shfl_sync(0xffffffffu, u, src);
                 const double ss = __shfl_sync(0xffffffffu, s, src);
-                if (lane < Q) {
-                    const double x = bs + w_lane * us;
-                    acc_sp += ss * log(x >= 0.0 ? softplus_tab(x, sTab) : softplus_f64(x));
-                }
+                if (lane < Q) acc_sp += ss * log_softplus(fma(w_lane, us, bs), sTab);
             }
-        } else if (live) {
+        } else {
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) {
-                if (q < Q) {
-                    const double x = base + wq[q] * u;
-                    acc[q] += -g.dt * exp(x) + x * s;                // exp nonlinearity: log(lam) = x
-                }
+                const double x = fma(wq[q], u, base);
+                acc[q] = fma(keep, -g.dt * exp(x) + x * s, acc[q]);  // exp nonlinearity: log(lam) = x
             }
         }
     }
+#undef PYGLM_GIBBS_FETCH
     // block reduction, fixed order: lanes (xor tree), then warps 0..7; the spike sums live in lane q
 #pragma unroll
     for (int q = 0; q < QMAX; ++q) {
-        double v = acc[q];
+        double v = NLIN == PYGLM_B200_NLIN_SOFTPLUS ? -g.dt * acc[q] : acc[q];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) sRed[q][warp] = v;
@@ -285,17 +366,23 @@ int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const i
     const bool f32 = g.x_dtype == PYGLM_B200_X_F32;
     const bool sp = g.nlin == PYGLM_B200_NLIN_SOFTPLUS;
     if (sp) { int rc = ensure_softplus_table(); if (rc) return rc; }
+#define PYGLM_GIBBS_LAUNCH3(QM, BM)                                                                                   \
+    do {                                                                                                               \
+        if (f32 && sp)       gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_SOFTPLUS, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
+        else if (f32)        gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_EXP, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);      \
+        else if (sp)         gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_SOFTPLUS, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
+        else                 gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_EXP, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);     \
+    } while (0)
 #define PYGLM_GIBBS_LAUNCH(QM)                                                                                         \
     do {                                                                                                               \
-        if (f32 && sp)       gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_SOFTPLUS><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
-        else if (f32)        gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_EXP><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);      \
-        else if (sp)         gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_SOFTPLUS><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
-        else                 gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_EXP><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);     \
+        if (g.B <= 5) PYGLM_GIBBS_LAUNCH3(QM, 5);                                                                      \
+        else if (g.B <= 10) PYGLM_GIBBS_LAUNCH3(QM, 10);                                                               \
+        else PYGLM_GIBBS_LAUNCH3(QM, 16);                                                                              \
     } while (0)
-    if (Q <= 1) PYGLM_GIBBS_LAUNCH(1);
-    else if (Q <= 4) PYGLM_GIBBS_LAUNCH(4);
+    if (Q <= 4) PYGLM_GIBBS_LAUNCH(4);
     else if (Q <= 11) PYGLM_GIBBS_LAUNCH(11);
     else PYGLM_GIBBS_LAUNCH(16);
+#undef PYGLM_GIBBS_LAUNCH3
 #undef PYGLM_GIBBS_LAUNCH
     PYGLM_CUDA(cudaGetLastError());
     gibbs_reduce_kernel<<<(unsigned)ceil_div((int64_t)M * Q, 128), 128, 0, stream>>>(g.partial, M, g.nchunks, Q, d_out);

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpyglm_b200.so")
+LIB_PATH = os.environ.get("PYGLM_B200_LIB") or os.path.join(_HERE, "lib", "libpyglm_b200.so")   # env: A/B builds
 
 NLIN_EXP, NLIN_SOFTPLUS = 0, 1
 X_F32, X_F64, X_PLANES = 0, 1, 2
