@@ -31,8 +31,8 @@ int gibbs_num_chunks(int64_t T) { return (int)ceil_div(T, kGibbsChunk); }
 // it (Q+1) T times per edge.  The library exp + log1p pair costs ~95 instructions per evaluation and its
 // branches keep the Q+1 candidates of a bin from overlapping, so L is computed by range instead
 // (absolute error < 1e-16 everywhere):
-//   a >= 5.5 : e = e^-a by Cody-Waite reduction and a degree-10 polynomial (coefficients in the constant bank),
-//              then L = e q, q = 1 - e/2 + e^2/3 - ... - e^5/6  (e < 4.1e-3).  ~25 FP64 operations, no branch and
+//   a >= 5.5 : e = e^-a by Cody-Waite reduction and a degree-9 polynomial (coefficients in the constant bank),
+//              then L = e q, q = 1 - e/2 + e^2/3 - ... - e^5/6  (e < 4.1e-3).  ~21 FP64 operations, no branch and
 //              no memory access: the candidates' dependency chains interleave and keep the FP64 pipe busy.
 //   a < 5.5  : 23 intervals of width 1/4 centred on a = i/4, a degree-9 polynomial in z = 8(a - i/4) on each,
 //              coefficients in shared memory.  Applied as a fix-up after the branch-free pass, only in warps
@@ -40,31 +40,40 @@ int gibbs_num_chunks(int64_t T) { return (int)ceil_div(T, kGibbsChunk); }
 // Both polynomial sets are Chebyshev interpolants expanded in monomials, built once on the host in long double.
 constexpr int kSpDeg = 9;
 constexpr int kSpRows = 23;
-constexpr int kSpExpDeg = 10;
+constexpr int kSpExpDeg = 9;
 constexpr double kSpSplit = 5.5;
-constexpr double kSpClamp = 708.0;                       // e^-708 is the smallest normal result
 constexpr double kSpMagic = 6755399441055744.0;          // 1.5 * 2^52: adding it rounds to the nearest integer
 __device__ double g_softplus_tab[kSpRows * (kSpDeg + 1)];
 __constant__ double c_sp_exp[kSpExpDeg + 1];
 
-// e = e^-a and q with L(a) = e q, for a in [5.5, 708] (finite garbage below 5.5; callers replace it)
-__device__ __forceinline__ void sp_exp_series(double a, double& e, double& q)
+// e = e^-|x| and q with L(|x|) = e q, for |x| in [5.5, inf) (finite garbage below 5.5; callers replace it).
+// FP64 min/max/compare are multi-instruction on this part, so the range handling stays on the integer pipe:
+// the exponent n is clamped (e^-|x| flushes towards zero past |x| = 708) and 2^n is added into the exponent field.
+__device__ __forceinline__ void sp_exp_series(double x, double& e, double& q)
 {
-    const double t = fma(a, -1.4426950408889634, kSpMagic);
-    const int n = __double2loint(t);                      // rint(-a log2(e)) in [-1021, -8]
+    const double t = fma(fabs(x), -1.4426950408889634, kSpMagic);
+    const int n = max(__double2loint(t), -1022);          // rint(-|x| log2(e))
     const double fn = t - kSpMagic;
-    double r = fma(fn, -6.93147180369123816490e-01, -a);
-    r = fma(fn, -1.90821492927058770002e-10, r);          // r = -a - n ln2, |r| <= ln2/2
+    double r = fma(fn, -6.93147180369123816490e-01, -fabs(x));
+    r = fma(fn, -1.90821492927058770002e-10, r);          // r = -|x| - n ln2, |r| <= ln2/2
     double p = c_sp_exp[kSpExpDeg];
 #pragma unroll
     for (int k = kSpExpDeg - 1; k >= 0; --k) p = fma(p, r, c_sp_exp[k]);
-    e = p * __hiloint2double((n + 1023) << 20, 0);
+    e = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));       // p in [0.70, 1.42): p 2^n
     q = fma(e, -1.0 / 6.0, 0.2);
     q = fma(q, e, -0.25);
     q = fma(q, e, 1.0 / 3.0);
     q = fma(q, e, -0.5);
     q = fma(q, e, 1.0);
 }
+
+// max(x, 0) and |x| < 5.5 from the high word (integer pipe)
+__device__ __forceinline__ double sp_relu(double x)
+{
+    const int hi = __double2hiint(x);
+    return __hiloint2double(hi < 0 ? 0 : hi, hi < 0 ? 0 : __double2loint(x));
+}
+__device__ __forceinline__ bool sp_small(double x) { return (__double2hiint(x) & 0x7fffffff) < 0x40160000; }
 
 // L(a) for a < 5.5 from the shared-memory table
 __device__ __forceinline__ double sp_table(double a, const double* __restrict__ tab)
@@ -85,11 +94,10 @@ __device__ __forceinline__ double sp_table(double a, const double* __restrict__ 
 // underflows the reference formula gives log(0) = -inf (nlin.py:43, glm.py:52), and so does this.
 __device__ __forceinline__ double log_softplus(double x, const double* __restrict__ tab)
 {
-    const double a = fabs(x);
-    if (a < kSpSplit) return log(fmax(x, 0.0) + sp_table(a, tab));
+    if (sp_small(x)) return log(sp_relu(x) + sp_table(fabs(x), tab));
     double e, q;
-    sp_exp_series(fmin(a, kSpClamp), e, q);
-    if (x > 0.0) return log(x + e * q);
+    sp_exp_series(x, e, q);
+    if (x > 0.0) return log(fma(e, q, x));
     if (x < -745.1332191019411) return -CUDART_INF;
     const double d = q - 1.0;                             // |d| < 2.1e-3
     double l = fma(d, 0.2, -0.25);
@@ -211,30 +219,25 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
         const double base = bias + (ir - aw_old * u);
         const double s = (double)sr;
         PYGLM_GIBBS_FETCH(t0 + kGibbsThreads + tid);
-        const double keep = live ? 1.0 : 0.0;                        // lanes past the end evaluate a dummy bin
 
         if (NLIN == PYGLM_B200_NLIN_SOFTPLUS) {
-            double lam[QMAX];
             bool small = false;
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) {                         // branch-free pass: Q independent chains
                 const double x = fma(wq[q], u, base);
-                const double a = fabs(x);
                 double e, qq;
-                sp_exp_series(fmin(a, kSpClamp), e, qq);
-                lam[q] = fmax(x, 0.0) + e * qq;
-                small |= a < kSpSplit;
+                sp_exp_series(x, e, qq);
+                const bool sm = sp_small(x);
+                small |= sm;
+                acc[q] = fma((live && !sm) ? 1.0 : 0.0, fma(e, qq, sp_relu(x)), acc[q]);
             }
-            if (__any_sync(0xffffffffu, small)) {                    // fix-up pass: |x| < 5.5 from the table
+            if (__any_sync(0xffffffffu, small)) {                    // second pass: |x| < 5.5 from the table
 #pragma unroll
                 for (int q = 0; q < QMAX; ++q) {
                     const double x = fma(wq[q], u, base);
-                    const double a = fabs(x);
-                    if (a < kSpSplit) lam[q] = fmax(x, 0.0) + sp_table(a, sTab);
+                    if (live && sp_small(x)) acc[q] += sp_relu(x) + sp_table(fabs(x), sTab);
                 }
             }
-#pragma unroll
-            for (int q = 0; q < QMAX; ++q) acc[q] = fma(keep, lam[q], acc[q]);
             // spike bins (~2%): one lane per candidate evaluates log(lam) for the whole warp
             unsigned mask = __ballot_sync(0xffffffffu, live && s != 0.0);   // (sr already holds the next bin)
             while (mask) {
@@ -249,7 +252,7 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
 #pragma unroll
             for (int q = 0; q < QMAX; ++q) {
                 const double x = fma(wq[q], u, base);
-                acc[q] = fma(keep, -g.dt * exp(x) + x * s, acc[q]);  // exp nonlinearity: log(lam) = x
+                acc[q] = fma(live ? 1.0 : 0.0, -g.dt * exp(x) + x * s, acc[q]);  // exp nonlinearity: log(lam) = x
             }
         }
     }
