@@ -156,3 +156,53 @@ def test_gibbs_sample_runs_and_keeps_a_valid_state():
         assert any(not np.array_equal(smpls[0]['net']['weights']['W'], s['net']['weights']['W']) for s in smpls[1:])
         # engine state and host state stayed in sync through the sweep
         assert np.all(np.isfinite(last['net']['weights']['W']))
+
+
+def test_basis_stimulus_population_end_to_end():
+    """A standard GLM with a BasisStimulus background (bkgd.py:45-172): simulate with a stimulus, then the
+    reference's own assertion (lam from the likelihood graph == f_nlin of the simulated activation,
+    generate_synth_data.py:124-129), the oracle's ll, and the gradient wrt (bias, w_stim, w_ir)."""
+    N, T_stop = 3, 4.0
+    model = make_model('standard_glm', N=N, dt=0.001)
+    model['bkgd'] = {'type': 'basis', 'D_stim': 2, 'dt_max': 0.3, 'dt_stim': 0.1,
+                     'basis': dict(type='cosine', n_eye=0, n_cos=3, a=1 / 120., b=0.5, orth=False, norm=True)}
+    popn = Population(model)
+    np.random.seed(4)
+    x = popn.sample()
+    for n in range(N):
+        x['glms'][n]['imp']['w_ir'] *= 0.02
+        x['glms'][n]['bkgd']['w_stim'] = 2.0 * np.random.randn(6)      # a stimulus drive worth a few Hz
+    stim = np.random.randn(int(T_stop / 0.1), 2)
+    S, X = popn.simulate(x, (0, T_stop), 0.001, stim, 0.1)
+    data = {'S': S, 'X': X, 'N': N, 'dt': 0.001, 'T': T_stop, 'stim': stim, 'dt_stim': 0.1}
+    popn.add_data(data)
+    assert data['fstim'].shape == (4000, 6)
+    # stimulus filtering == the oracle's restatement of bkgd.py:122-154
+    ib_s = orc.interpolate_stim_basis(orc.create_basis(model['bkgd']['basis']), 0.001, 0.3, True)
+    _, fstim = orc.filter_stimulus(stim, 0.1, 4000, 0.001, ib_s)
+    assert np.max(np.abs(data['fstim'] - fstim)) < 1e-12 * max(1.0, np.max(np.abs(fstim)))
+    state = popn.eval_state(x)
+    for n in range(N):
+        assert np.allclose(state['glms'][n]['lam'], orc.nlin(X[:, n], orc.NLIN_SOFTPLUS), rtol=1e-6, atol=1e-8)
+    bias, w, A, W = popn.glm.engine_params(x)
+    ws = popn.glm.stim_weights(x)
+    fS = orc.convolve_with_basis(S, popn.glm.imp_model.ibasis)
+    ll, gb, gw, gs = orc.population_ll_grad(fS, S, 0.001, bias, w.reshape(N, N, -1), np.ones((N, N), np.int8),
+                                            np.ones((N, N)), orc.NLIN_SOFTPLUS, fstim=fstim, w_stim=ws)
+    assert abs(popn.compute_ll(x) - ll.sum()) < 1e-6 * abs(ll.sum())
+    lp1, g1 = popn.glm_log_p_grad(x, 1)
+    gp = popn.glm.grad_log_prior(x['glms'][1])
+    ref_g = np.concatenate([[gb[1] + gp['bias']['bias'][0]], gs[1] + gp['bkgd']['w_stim'],
+                            gw[1].ravel() + gp['imp']['w_ir']])
+    assert abs(lp1 - (ll[1] + popn.glm.log_prior(x['glms'][1]))) < 1e-6 * abs(lp1)
+    assert rel_err(g1, ref_g) < 1e-5
+    lps, gsb = popn.glms_log_p_grad(x)
+    assert np.allclose(gsb[1], g1, rtol=1e-9, atol=1e-9)
+    # MAP refit moves the stimulus weights towards the truth from zero
+    from theano_pyglm_b200.inference.coord_descent import coord_descent
+    x0 = copy.deepcopy(x)
+    for n in range(N):
+        x0['glms'][n]['bkgd']['w_stim'] = np.zeros(6)
+    lp0 = popn.compute_log_p(x0)
+    x_fit = coord_descent(popn, x0=x0, maxiter=1, batched=True)
+    assert popn.compute_log_p(x_fit) > lp0

@@ -115,3 +115,115 @@ def test_shard_planners_cover_everything_once():
     assert (lo, hi, halo) == (0, 250, 0)
     assert time_shard(1000, 4, 1, 200) == (250, 500, 200)
     assert time_shard(300, 4, 1, 200) == (75, 150, 75)      # halo clipped at the start of the recording
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic data, files, model conversion, stimulus component (host side, no GPU)
+# ----------------------------------------------------------------------------------------------
+class _GlobalStream:
+    """Feeds oracle.simulate from numpy's global stream, the stream Population.simulate consumes."""
+
+    @staticmethod
+    def random(n):
+        return np.random.rand(n)
+
+
+def test_population_simulate_matches_oracle_and_reference_draw_order():
+    N = 4
+    model = make_model('standard_glm', N=N, dt=0.001)
+    popn = Population(model)
+    np.random.seed(11)
+    x = popn.sample()
+    for n in range(N):                                  # moderate coupling: a few hundred spikes in 3 s
+        x['glms'][n]['imp']['w_ir'] *= 0.2
+    np.random.seed(5)
+    S, X = popn.simulate(x, (0, 3.0), 0.001, None, None)
+    assert S.shape == (3000, N) and X.shape == (3000, N) and S.sum() > 50 and S.max() <= 10
+    bias = np.array([x['glms'][n]['bias']['bias'][0] for n in range(N)])
+    imps = np.stack([popn.glm.imp_model.impulse(x['glms'][n]['imp']) for n in range(N)], axis=1)
+    np.random.seed(5)
+    S_o, X_o = orc.simulate(bias, imps, np.ones((N, N), np.int8), np.ones((N, N)), 3000, 0.001, orc.NLIN_SOFTPLUS,
+                            _GlobalStream)
+    assert np.array_equal(S, S_o) and np.allclose(X, X_o, rtol=0, atol=1e-12)
+    # the activation is the causal filter of the spikes: X = bias + fS . w  (generate_synth_data.py:124-129)
+    fS = orc.convolve_with_basis(S, popn.glm.imp_model.ibasis)
+    for n in range(N):
+        act = bias[n] + orc.impulse_current(fS, x['glms'][n]['imp']['w_ir'].reshape(N, -1)).sum(axis=1)
+        assert np.allclose(act, X[:, n], atol=1e-8)
+
+
+def test_data_files_roundtrip_and_segments(tmp_path):
+    from theano_pyglm_b200.utils import io as pio
+    rng = np.random.default_rng(0)
+    data = {'S': (rng.random((2000, 3)) < 0.05).astype(float), 'N': 3, 'dt': 0.001, 'T': 2.0,
+            'stim': rng.standard_normal((20, 2)), 'dt_stim': 0.1, '_b200': object(), 'preprocessed': True}
+    model = make_model('sparse_weighted_model', N=3)
+    pio.save_results(str(tmp_path), data=data, model=model, results=[{'ll': 1.0}])
+    back = pio.load_data(str(tmp_path / 'data.pkl'))
+    assert '_b200' not in back and 'preprocessed' not in back
+    assert np.array_equal(back['S'], data['S']) and back['N'] == 3 and back['dt_stim'] == 0.1
+    assert pio.load_pickle(str(tmp_path / 'model.pkl')) == model
+    assert pio.load_pickle(str(tmp_path / 'results.pkl')) == [{'ll': 1.0}]
+    seg = pio.segment_data(data, (0.5, 1.5))
+    # io.py:141-142 floors T // dt in floating point (0.5 // 0.001 == 499.0): same indices here
+    i0, i1 = int(0.5 // 0.001), int(1.5 // 0.001)
+    assert seg['T'] == 1.0 and seg['S'].shape == (i1 - i0, 3) and seg['stim'].shape == (10, 2)
+    assert np.array_equal(seg['S'], data['S'][i0:i1]) and '_b200' not in seg
+    with pytest.raises(Exception):
+        pio.load_data(str(tmp_path / 'data.txt'))
+
+
+def test_convert_model_projects_basis_impulses_onto_dirichlet_model():
+    from theano_pyglm_b200.models.model_factory import convert_model
+    N = 3
+    m_std = make_model('standard_glm', N=N, dt=0.001)
+    m_w = make_model('sparse_weighted_model', N=N, dt=0.001)
+    p_std, p_w = Population(m_std), Population(m_w)
+    np.random.seed(3)
+    x_std, x_w = p_std.sample(), p_w.sample()
+    # impulses that lie in the cone of the target basis, with known areas and signs
+    ib_w = p_w.glm.imp_model.ibasis
+    beta = np.random.dirichlet(np.ones(ib_w.shape[1]), size=(N, N))
+    W_true = np.random.randn(N, N) * 2.0
+    from scipy.linalg import lstsq
+    for n2 in range(N):
+        target = (W_true[:, n2, None] * beta[:, n2, :]) @ ib_w.T                     # (N_pre, R)
+        w_ir = lstsq(p_std.glm.imp_model.ibasis, target.T)[0].T                      # best fit in the standard basis
+        x_std['glms'][n2]['imp']['w_ir'] = w_ir.ravel()
+    conv = convert_model(p_std, m_std, x_std, p_w, m_w, x_w)
+    Wc = conv['net']['weights']['W'].reshape(N, N)
+    assert conv['net']['graph']['A'].dtype == np.int8 and conv['net']['graph']['A'].shape == (N, N)
+    for n2 in range(N):
+        assert conv['glms'][n2]['bias']['bias'] is x_std['glms'][n2]['bias']['bias']
+        imp_from = p_std.glm.imp_model.impulse(x_std['glms'][n2]['imp'])
+        imp_to = p_w.glm.imp_model.impulse(conv['glms'][n2]['imp']) * Wc[:, n2, None]
+        # the projection reproduces the impulse responses up to the fit residual of the two bases
+        assert np.linalg.norm(imp_to - imp_from) < 0.25 * np.linalg.norm(imp_from)
+        assert np.all(np.sign(Wc[:, n2]) == np.sign(W_true[:, n2]))
+
+
+def test_basis_stimulus_component_matches_oracle():
+    from theano_pyglm_b200.components.bkgd import BasisStimulus
+    model = make_model('standard_glm', N=2, dt=0.001)
+    model['bkgd'] = {'type': 'basis', 'D_stim': 2, 'dt_max': 0.3, 'dt_stim': 0.01,
+                     'basis': dict(type='cosine', n_eye=0, n_cos=3, a=1 / 120., b=0.5, orth=False, norm=True)}
+    comp = BasisStimulus(model)
+    ib = orc.interpolate_stim_basis(orc.create_basis(model['bkgd']['basis']), 0.001, 0.3, True)
+    assert np.allclose(comp.ibasis, ib, atol=1e-15) and comp.n_vars == 6
+    assert np.allclose(comp.ibasis.sum(axis=0), 1.0)                                # sum-normalised (bkgd.py:119)
+    w = np.linspace(-0.02, 0.03, 6)
+    assert np.isclose(comp.log_p({'w_stim': w}), orc.stim_log_prior(w))
+    eps = 1e-7
+    g = comp.grad_log_p({'w_stim': w})['w_stim']
+    for i in range(6):
+        d = np.zeros(6); d[i] = eps
+        fd = (comp.log_p({'w_stim': w + d}) - comp.log_p({'w_stim': w - d})) / (2 * eps)
+        assert np.isclose(g[i], fd, rtol=1e-5)
+    popn = Population(model)
+    x = popn.sample()
+    vec = popn.glm_param_vector(x['glms'][0])
+    assert vec.size == 1 + 6 + 2 * 5                                                 # bias < bkgd < imp
+    assert np.array_equal(vec[1:7], x['glms'][0]['bkgd']['w_stim'])
+    popn.set_glm_param_vector(x['glms'][0], vec * 2)
+    assert np.array_equal(x['glms'][0]['bkgd']['w_stim'], vec[1:7] * 2)
+    assert popn.glm.stim_weights(x).shape == (2, 6)

@@ -101,6 +101,63 @@ class Population:
             raise RuntimeError("no data sequence set")
         return data['_b200']
 
+    # -- synthetic data -------------------------------------------------------------------------
+    def simulate(self, vars, T_range, dt, stim=None, dt_stim=None, verbose=False):
+        """Draw spikes from the network of coupled GLMs by time rescaling (population.py:233-389): each
+        neuron integrates lam*dt and fires when the integral passes an Exp(1) threshold; a spike adds the
+        weighted impulse responses A*W*imp to the future activation of its targets; at most 10 spikes per
+        bin.  Returns (S, X): spike counts (nT, N) and the activation (nT, N), so that
+        f_nlin(X) is the firing rate the likelihood kernels must reproduce (generate_synth_data.py:124-129).
+        Host code: the recursion is sequential in time and is not part of the accelerated path."""
+        T_start, T_stop = T_range
+        N = self.N
+        nT = len(np.arange(int(T_start / dt), int(T_stop / dt)))
+        f = self.glm.nlin_model.f_nlin
+        X = np.zeros((nT, N))
+        for n in range(N):
+            X[:, n] = self.glm.bias_model.I_bias(vars['glms'][n]['bias'])
+        if self.glm.bkgd_model.n_vars:                                # stimulus current (population.py:259-270)
+            tmp = {'S': np.zeros((nT, N)), 'stim': stim, 'dt_stim': dt_stim, 'T': float(T_stop - T_start)}
+            self.glm.bkgd_model.preprocess_data(tmp)
+            for n in range(N):
+                X[:, n] += tmp['fstim'] @ self.glm.bkgd_model.weights(vars['glms'][n]['bkgd'])
+        if verbose:
+            print("Max background rate: %s" % str(f(np.amax(X))))
+        # imps[pre, post, lag] scaled by the network: what one spike of `pre` adds to `post`
+        imps = np.stack([self.glm.imp_model.impulse(vars['glms'][n]['imp']) for n in range(N)], axis=1)
+        A, W = self.network.A(vars['net']), self.network.W(vars['net'])
+        gain = (np.ones((N, N)) if A is None else A.astype(np.float64)) * (np.ones((N, N)) if W is None else W)
+        kick = imps * gain[:, :, None]
+        T_imp = kick.shape[2]
+        S = np.zeros((nT, N))
+        acc = np.zeros(N)
+        thr = -np.log(np.random.rand(N))
+        n_exceptions = 0
+        max_spks_per_bin = 10
+        for t in range(nT):
+            acc = acc + f(X[t, :]) * dt
+            i_spk = acc > thr
+            S[t, i_spk] += 1
+            n_spk = int(np.sum(i_spk))
+            t_imp = min(nT - t - 1, T_imp)
+            while n_spk > 0:
+                if np.any(S[t, :] >= max_spks_per_bin):
+                    n_exceptions += 1
+                    break
+                X[t + 1:t + t_imp + 1, :] += np.sum(kick[i_spk, :, :t_imp], axis=0).T
+                acc -= thr * i_spk
+                acc[acc < 0] = 0
+                thr[i_spk] = -np.log(np.random.rand(n_spk))
+                i_spk = acc > thr
+                S[t, i_spk] += 1
+                n_spk = int(np.sum(i_spk))
+        if verbose:
+            lam = f(X)
+            print("Sampled %s spikes." % str(np.sum(S, 0)))
+            print("Expected %s spikes." % str(np.trapz(lam, dt * np.arange(nT), axis=0)))
+            print("Number of exceptions arising from multiple spikes per bin: %d" % n_exceptions)
+        return S, X
+
     # -- probabilities ----------------------------------------------------------------------------
     def ll_grad(self, x, n_lo=0, n_hi=None, data=None, grad=True):
         """Per-neuron log-likelihoods (and gradients wrt the engine's dense blocks) on one sequence:
