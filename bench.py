@@ -7,7 +7,8 @@ One "step" = one ll+gradient evaluation for all N neurons of one data sequence
 (BASELINE.json metric).  Workload at one GPU: config C2
 (standard_glm, N=27, T=10^6 bins, B=5, R=200), synthetic Bernoulli(0.02) spikes.
 With --gpus G (torchrun, one rank per GPU) every rank owns its own T=10^6-bin sequence
-(time-sharded, weak scaling) and the per-step partial sums are all-reduced over NCCL,
+(time-sharded, weak scaling) and the per-step partial sums are added over ranks -- by the engine's
+one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu; --allreduce nccl uses NCCL instead) --
 exactly as the reference sums ll over data sequences (coord_descent.py:52-57).
 
 Prints ONE JSON line on rank 0 (contract in the task statement).
@@ -202,8 +203,25 @@ def run_ours(args, wl):
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    comm = None
+    collective = "none (single GPU)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        collective = "nccl all_reduce"
+        if args.allreduce == "p2p":
+            # one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu); every rank must agree on the choice
+            from theano_pyglm_b200.utils.parallel_util import make_peer_comm
+            ok = torch.ones(1, device=dev)
+            try:
+                comm = make_peer_comm(wl["N"] * (2 + wl["N"] * wl["B"]), local_rank)
+            except Exception as exc:                       # no peer access on this box: NCCL does the sum
+                sys.stderr.write("rank %d: peer all-reduce unavailable (%s); using NCCL\n" % (rank, exc))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1:
+                comm = None
+            else:
+                collective = "one-shot all-reduce over NVLink peer memory (allreduce_kernel)"
 
     N, T, B = wl["N"], wl["T"], wl["B"]
     NB = N * B
@@ -224,8 +242,10 @@ def run_ours(args, wl):
     def step_dev():
         ds.ll_grad_dev(d_bias.data_ptr(), d_w.data_ptr(), 0, 0, nlin, 0, N, path,
                        d_ll.data_ptr(), d_gb.data_ptr(), d_gw.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(d_out)          # sum of the time shards' partial ll / gradients
+        if comm is not None:                # sum of the time shards' partial ll / gradients
+            comm.allreduce_sum_dev(d_out.data_ptr(), d_out.data_ptr(), d_out.numel(), stream.cuda_stream)
+        elif world > 1:
+            dist.all_reduce(d_out)
 
     # host-buffer path (e2e): pinned parameter upload, eval, result download every step
     h_bias = torch.from_numpy(inp["bias"]).pin_memory()
@@ -241,7 +261,9 @@ def run_ours(args, wl):
         ds.ll_grad_dev(e_bias.data_ptr(), e_w.data_ptr(), 0, 0, nlin, 0, N, path,
                        e_out[:N].data_ptr(), e_out[N:2 * N].data_ptr(), e_out[2 * N:].data_ptr(),
                        stream.cuda_stream)
-        if world > 1:
+        if comm is not None:
+            comm.allreduce_sum_dev(e_out.data_ptr(), e_out.data_ptr(), e_out.numel(), stream.cuda_stream)
+        elif world > 1:
             dist.all_reduce(e_out)
         h_out.copy_(e_out, non_blocking=True)
         stream.synchronize()                # the caller reads ll / gradient on the host every step
@@ -322,11 +344,12 @@ def run_ours(args, wl):
                        "path": info.get("name", path), "l2": "inputs_exceed_l2 (X is %d MB per GPU)" % (x_bytes >> 20),
                        "sharding": "time-sharded: one T-bin sequence per GPU, allreduce(sum) of ll/grad partials"
                        if world > 1 else "single GPU",
+                       "collective": collective,
                        "ingest_s_incl_filter": ingest_s},
             "clocks": clocks,
             "e2e": {"value": world / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(info.get("launches_per_eval", 5)) * args.steps,
+            "gpu_launches": (int(info.get("launches_per_eval", 5)) + (1 if comm is not None else 0)) * args.steps,
             "roofline": roof,
         }
         # CPU baseline on a bounded sample (rank 0, N=1 only)
@@ -490,6 +513,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="auto", choices=["auto", "fp64", "tc"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--allreduce", default="p2p", choices=["p2p", "nccl"],
+                    help="collective of the time-sharded run: peer-memory one-shot kernel (default) or NCCL")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if wl.get("gibbs"):

@@ -207,6 +207,30 @@ PYGLM_B200_API int pyglm_b200_gibbs_commit(pyglm_b200_dataset* ds, int32_t M,
 PYGLM_B200_API int pyglm_b200_gibbs_get_state(const pyglm_b200_dataset* ds, int8_t* A, double* W);
 PYGLM_B200_API int pyglm_b200_gibbs_end(pyglm_b200_dataset* ds);
 
+/* ------------------------------------------------------------------------------------
+ * Sum over ranks of the time shards' partial results (one process per GPU).
+ * Replaces the client-side sums of the reference's parallel drivers: ll / log_p summed over
+ * engines (pyglm/utils/parallel_util.py:30,78) and over data sequences (population.py:41-43,
+ * coord_descent.py:52-57) -- here [ll | g_bias | g_w] summed over the GPUs that each hold a
+ * time shard of the recording.
+ *
+ * One-shot all-reduce over NVLink peer memory: every rank stores its vector into a slot of
+ * every peer's receive buffer, raises a flag, and adds the slots in rank order (bitwise
+ * identical results on all ranks, no host round trip).  Setup: comm_create on every rank,
+ * comm_export -> 128 opaque bytes (two cudaIpc handles), exchange them out of band (e.g.
+ * torch.distributed all_gather), comm_connect with the world*128 bytes in rank order.
+ * allreduce_sum_dev is asynchronous on `stream`; d_in may equal d_out; every rank must call
+ * it with the same n, in the same order.
+ * ---------------------------------------------------------------------------------- */
+typedef struct pyglm_b200_comm pyglm_b200_comm;
+PYGLM_B200_API int pyglm_b200_comm_create(int32_t rank, int32_t world, int32_t device, int64_t max_doubles,
+                           pyglm_b200_comm** out);
+PYGLM_B200_API int pyglm_b200_comm_export(const pyglm_b200_comm* comm, void* handles128);
+PYGLM_B200_API int pyglm_b200_comm_connect(pyglm_b200_comm* comm, const void* all_handles);
+PYGLM_B200_API int pyglm_b200_allreduce_sum_dev(pyglm_b200_comm* comm, const double* d_in, double* d_out,
+                                 int64_t n, void* stream);
+PYGLM_B200_API int pyglm_b200_comm_destroy(pyglm_b200_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,92 @@
+"""GPU test of the peer-memory all-reduce (csrc/allreduce.cu) and of time-sharded ll+gradient through it.
+
+The ranks are separate processes, as in production, but share cuda:0 (cudaIpc works between processes on one
+device), so the test runs on a single-GPU box; the handles travel over a gloo group."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pyglm_oracle as orc
+from tests.helpers import make_problem, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import theano_pyglm_b200 as pg
+        from theano_pyglm_b200.utils.parallel_util import make_peer_comm, time_shard
+        dev = torch.device("cuda", 0)
+        torch.cuda.set_device(dev)
+        stream = torch.cuda.current_stream()
+        comm = make_peer_comm(400000, 0)
+        # 1. plain vectors, several sizes and many back-to-back calls (epoch / double-buffer logic), in place
+        ok = True
+        for n in (1, 37, 3672, 300001):
+            for it in range(6):
+                x = torch.arange(n, dtype=torch.float64, device=dev) * (rank + 1) + it
+                comm.allreduce_sum_dev(x.data_ptr(), x.data_ptr(), n, stream.cuda_stream)
+                ref = torch.arange(n, dtype=torch.float64, device=dev) * sum(r + 1 for r in range(world)) + it * world
+                ok &= bool(torch.equal(x, ref))
+        # 2. time-sharded ll + gradient: K1 with an R-bin halo, tensor-core path, partials summed over ranks
+        p = make_problem(6000, 6, 5, network=True, seed=21)
+        R = p['ibasis'].shape[0]
+        lo, hi, halo = time_shard(p['T'], world, rank, R)
+        ds = pg.Dataset(p['S'][lo - halo:hi], p['dt'], p['ibasis'], halo=halo)
+        N, NB = p['N'], p['N'] * p['B']
+        d_bias = torch.from_numpy(p['bias']).to(dev)
+        d_w = torch.from_numpy(p['w'].reshape(N, NB)).to(dev)
+        d_A = torch.from_numpy(p['A']).to(dev)
+        d_W = torch.from_numpy(p['W']).to(dev)
+        out = torch.zeros(N * (2 + NB), dtype=torch.float64, device=dev)
+        ds.ll_grad_dev(d_bias.data_ptr(), d_w.data_ptr(), d_A.data_ptr(), d_W.data_ptr(), "explinear", 0, N, "auto",
+                       out[:N].data_ptr(), out[N:2 * N].data_ptr(), out[2 * N:].data_ptr(), stream.cuda_stream)
+        comm.allreduce_sum_dev(out.data_ptr(), out.data_ptr(), out.numel(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        q.put((rank, ok, out.cpu().numpy()))
+        dist.barrier()
+        comm.close()
+        ds.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_allreduce_and_time_sharded_ll_grad(world, engine_lib):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = {}
+    for _ in range(world):
+        rank, ok, out = q.get(timeout=240)
+        results[rank] = (ok, out)
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    p = make_problem(6000, 6, 5, network=True, seed=21)
+    N = p['N']
+    S = p['S'].astype(np.float64)
+    fS = orc.convolve_with_basis_direct(S, p['ibasis'])
+    ll0, gb0, gw0 = orc.population_ll_grad(fS, S, p['dt'], p['bias'], p['w'], p['A'], p['W'], orc.NLIN_SOFTPLUS)
+    for rank in range(world):
+        ok, out = results[rank]
+        assert ok, "rank %d: all-reduce of plain vectors is wrong" % rank
+        assert np.array_equal(out, results[0][1])                    # same summation order: bitwise identical
+        assert rel_err(out[:N], ll0) < 1e-6 and rel_err(out[N:2 * N], gb0) < 1e-5
+        assert rel_err(out[2 * N:], gw0.reshape(-1)) < 1e-5

@@ -185,7 +185,10 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
+            // acc0 = x1 m1 and acc1 = x1 m2 + x2 m1 sit in adjacent TMEM columns and M1 | M2 are adjacent in the
+            // stage, so x1 multiplies both in ONE N=256 MMA: x1 is read from shared memory once, not twice
             constexpr uint32_t idesc = umma_idesc(kGT, kGN, 0, 0);
+            constexpr uint32_t idesc2 = umma_idesc(kGT, 2 * kGN, 0, 0);
             uint32_t chunk = 0, it = 0;
             for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int ab = it & 1;
@@ -198,13 +201,12 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem + s * kFwdStageBytes);
                     const uint64_t dx1 = umma_desc(base, 16, 512), dx2 = umma_desc(base + kGT * 64, 16, 512);
-                    const uint64_t dm1 = umma_desc(base + 2 * kGT * 64, 16, 512), dm2 = umma_desc(base + 3 * kGT * 64, 16, 512);
+                    const uint64_t dm1 = umma_desc(base + 2 * kGT * 64, 16, 512);   // rows 128..255 of this tile are M2
 #pragma unroll
                     for (int ks = 0; ks < 2; ++ks) {
                         const uint32_t acc = (kc | ks) ? 1u : 0u;
-                        umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc, acc);     // X1 M1
-                        umma_f16(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc, acc);     // X2 M1
-                        umma_f16(t_b, dx1 + 2 * ks, dm2 + 2 * ks, idesc, 1u);      // X1 M2
+                        umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc2, acc);    // X1 [M1 | M2]
+                        umma_f16(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc, 1u);      // X2 M1
                     }
                     umma_commit(&bar_empty[s]);
                 }
@@ -365,6 +367,7 @@ tc_gemm_bwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(kGF, kGN, 1, 1);   // both operands MN-major
+            constexpr uint32_t idesc2 = umma_idesc(kGF, 2 * kGN, 1, 1);   // r1 | r2 stacked (adjacent chunks, adjacent TMEM)
             for (int i = 0; i < nt; ++i) {
                 const int gb = i & 1;
                 const uint32_t t_a = tmem_base + gb * 256, t_b = t_a + 128;
@@ -378,14 +381,12 @@ tc_gemm_bwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     const uint64_t dx1 = umma_desc(base, kBwdChunkBytes, 512);
                     const uint64_t dx2 = umma_desc(base + 4 * kBwdChunkBytes, kBwdChunkBytes, 512);
                     const uint64_t dr1 = umma_desc(base + 8 * kBwdChunkBytes, kBwdChunkBytes, 512);
-                    const uint64_t dr2 = umma_desc(base + 12 * kBwdChunkBytes, kBwdChunkBytes, 512);
 #pragma unroll
                     for (int ks = 0; ks < kBwdRows / 16; ++ks) {
                         const uint32_t acc = (hh | ks) ? 1u : 0u;
                         const uint64_t off = (uint64_t)(ks * 1024 >> 4);
-                        umma_f16(t_a, dx1 + off, dr1 + off, idesc, acc);          // X1^T r1
-                        umma_f16(t_b, dx2 + off, dr1 + off, idesc, acc);          // X2^T r1
-                        umma_f16(t_b, dx1 + off, dr2 + off, idesc, 1u);           // X1^T r2
+                        umma_f16(t_a, dx1 + off, dr1 + off, idesc2, acc);         // X1^T [r1 | r2]
+                        umma_f16(t_b, dx2 + off, dr1 + off, idesc, 1u);           // X2^T r1
                     }
                     umma_commit(&bar_empty[s]);
                 }

@@ -28,6 +28,8 @@ EXPORTS = [
     "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_firing_rate",
     "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_delta_ll_dev", "pyglm_b200_gibbs_commit",
     "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
+    "pyglm_b200_comm_create", "pyglm_b200_comm_export", "pyglm_b200_comm_connect", "pyglm_b200_allreduce_sum_dev",
+    "pyglm_b200_comm_destroy",
 ]
 
 _lib = None
@@ -74,6 +76,11 @@ def load_library():
     lib.pyglm_b200_gibbs_commit.argtypes = [p, i32, p, p, p, p]
     lib.pyglm_b200_gibbs_get_state.argtypes = [p, p, p]
     lib.pyglm_b200_gibbs_end.argtypes = [p]
+    lib.pyglm_b200_comm_create.argtypes = [i32, i32, i32, i64, C.POINTER(p)]
+    lib.pyglm_b200_comm_export.argtypes = [p, p]
+    lib.pyglm_b200_comm_connect.argtypes = [p, p]
+    lib.pyglm_b200_allreduce_sum_dev.argtypes = [p, p, p, i64, p]
+    lib.pyglm_b200_comm_destroy.argtypes = [p]
     for name in EXPORTS:      # every declared symbol must resolve
         getattr(lib, name)
     _lib = lib
@@ -296,3 +303,41 @@ class Dataset:
 
     def gibbs_end(self):
         _check(load_library().pyglm_b200_gibbs_end(self._h))
+
+
+class PeerComm:
+    """One-shot sum all-reduce over NVLink peer memory between the ranks of a torch.distributed job
+    (one process per GPU): the collective of time sharding.  `exchange` is a callable that takes this
+    rank's 128 handle bytes and returns the list of every rank's bytes in rank order (see
+    utils.parallel_util.make_peer_comm for the torch.distributed version)."""
+
+    def __init__(self, rank, world, device, max_doubles, exchange):
+        lib = load_library()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        h = C.c_void_p()
+        _check(lib.pyglm_b200_comm_create(self.rank, self.world, self.device, int(max_doubles), C.byref(h)))
+        self._h = h
+        if self.world > 1:
+            mine = (C.c_ubyte * 128)()
+            _check(lib.pyglm_b200_comm_export(h, mine))
+            parts = exchange(bytes(mine))
+            if len(parts) != self.world or any(len(b) != 128 for b in parts):
+                raise EngineError("peer handle exchange returned %d entries for world %d" % (len(parts), self.world))
+            blob = (C.c_ubyte * (128 * self.world)).from_buffer_copy(b"".join(parts))
+            _check(lib.pyglm_b200_comm_connect(h, blob))
+
+    def allreduce_sum_dev(self, d_in, d_out, n, stream):
+        """Device pointers (integers); asynchronous on `stream`; in place when d_in == d_out."""
+        _check(load_library().pyglm_b200_allreduce_sum_dev(self._h, C.c_void_p(d_in), C.c_void_p(d_out), int(n),
+                                                           C.c_void_p(stream)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            load_library().pyglm_b200_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

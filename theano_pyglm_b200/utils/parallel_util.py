@@ -73,6 +73,22 @@ def allgather_columns(local, N, device="cpu", group=None):
     return np.concatenate([p.cpu().numpy()[:w] for p, w in zip(parts, widths)], axis=0)
 
 
+def make_peer_comm(max_doubles, device, group=None):
+    """engine.PeerComm for the current torch.distributed job: the 128-byte cudaIpc handles are exchanged
+    with all_gather_object (any backend), after which the all-reduce runs over NVLink peer memory with no
+    further use of torch.distributed."""
+    from ..engine import PeerComm
+    if not (dist.is_available() and dist.is_initialized()):
+        return PeerComm(0, 1, device, max_doubles, lambda b: [b])
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def exchange(mine):
+        parts = [None] * world
+        dist.all_gather_object(parts, mine, group=group)
+        return parts
+    return PeerComm(rank, world, device, max_doubles, exchange)
+
+
 def splice_network_columns(A, W, n_lo, n_hi, A_cols, W_cols):
     """Write back the columns a rank resampled: A[:, n], W[:, n] for n in [n_lo, n_hi)."""
     A[:, n_lo:n_hi] = A_cols
