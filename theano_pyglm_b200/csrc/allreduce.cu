@@ -24,7 +24,7 @@
 
 namespace pyglm {
 
-constexpr int kArThreads = 512;
+constexpr int kArThreads = 256;
 constexpr int kArMaxWorld = 16;
 constexpr int kArMaxBlocks = 128;
 
@@ -168,7 +168,7 @@ int pyglm_b200_allreduce_sum_dev(pyglm_b200_comm* c, const double* d_in, double*
     if (!c->connected) { set_error("allreduce before comm_connect"); return PYGLM_B200_ESTATE; }
     c->epoch += 1;
     if (c->epoch == 0) c->epoch = 1;                       // flags start at 0
-    int blocks = (int)std::min<int64_t>(ceil_div(n, 4096), std::min(kArMaxBlocks, c->num_sms));
+    int blocks = (int)std::min<int64_t>(ceil_div(n, 2 * kArThreads), std::min(kArMaxBlocks, c->num_sms));   // >= 512 doubles per block
     if (blocks < 1) blocks = 1;
     allreduce_kernel<<<blocks, kArThreads, 0, st>>>(c->peers, c->rank, c->world, c->cap, c->epoch, d_in, d_out, n);
     PYGLM_CUDA(cudaGetLastError());
