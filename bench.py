@@ -34,6 +34,9 @@ WORKLOADS = {
     "c1": dict(N=4, T=60_000, B=5, desc="standard_glm N=4 T=60s (C1)"),
     "c2": dict(N=27, T=1_000_000, B=5, desc="standard_glm N=27 T=1e6 bins B=5 R=200 (C2)"),
     "c3": dict(N=256, T=1_000_000, B=5, desc="network GLM N=256 T=1e6 bins B=5 (C3, ll+grad part)"),
+    # one GPU's share of C4 (N=1024, T=4e6, B=10) under 8-way time sharding; planes-only ingest (no FP32 X resident)
+    "c4-shard": dict(N=1024, T=500_000, B=10, x_dtype="planes",
+                     desc="network-size GLM N=1024 B=10, T=5e5 bins = one of 8 time shards of C4 (ll+grad)"),
     # second headline metric: collapsed Gibbs over A/W, batched delta-ll (sparse_weighted_model)
     "c3-gibbs": dict(N=256, T=1_000_000, B=5, gibbs=True, desc="network GLM N=256 T=1e6 bins: collapsed Gibbs over A/W (C3)"),
     "gibbs-small": dict(N=32, T=200_000, B=5, gibbs=True, desc="network GLM N=32 T=2e5 bins: collapsed Gibbs over A/W (smoke size)"),
@@ -227,7 +230,7 @@ def run_ours(args, wl):
     NB = N * B
     inp = make_inputs(wl, seed=1234 + rank)      # every rank owns its own sequence (time shard)
     t_ing0 = time.perf_counter()
-    ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank)
+    ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank, x_dtype=wl.get("x_dtype", "f32"))
     ingest_s = time.perf_counter() - t_ing0
     path = args.path
     nlin = "explinear"

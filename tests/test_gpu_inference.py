@@ -158,6 +158,27 @@ def test_gibbs_sample_runs_and_keeps_a_valid_state():
         assert np.all(np.isfinite(last['net']['weights']['W']))
 
 
+def test_gibbs_sample_initialised_from_the_map_estimate():
+    """gibbs.py:2486-2507: fit a standard GLM by coordinate descent on the same data, project it onto the
+    weighted Dirichlet model (convert_model) and start the chain there."""
+    from theano_pyglm_b200.inference.gibbs import gibbs_sample, initial_state
+    model, popn, data, x = synth_network_glm(N=4, nT=6000, seed=9)
+    np.random.seed(3)
+    x0 = initial_state(popn, init_from_mle=True)
+    N = 4
+    assert x0['net']['graph']['A'].shape == (N, N) and x0['net']['graph']['A'].dtype == np.int8
+    for n in range(N):
+        for k in range(N):
+            g = x0['glms'][n]['imp']['g_%d' % k]
+            assert g.shape == (popn.glm.imp_model.B,) and np.all(g > 0)
+    np.random.seed(3)
+    lp_prior_draw = popn.compute_log_p(popn.sample())
+    assert np.isfinite(popn.compute_log_p(x0))
+    assert popn.compute_ll(x0) > popn.compute_ll(x) - abs(popn.compute_ll(x))      # a sane starting point, not a blow-up
+    smpls = gibbs_sample(popn, N_samples=1, init_from_mle=True)
+    assert len(smpls) == 2 and np.isfinite(popn.compute_log_p(smpls[-1])) and np.isfinite(lp_prior_draw)
+
+
 def test_basis_stimulus_population_end_to_end():
     """A standard GLM with a BasisStimulus background (bkgd.py:45-172): simulate with a stimulus, then the
     reference's own assertion (lam from the likelihood graph == f_nlin of the simulated activation,

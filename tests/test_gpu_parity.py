@@ -80,7 +80,9 @@ def test_ll_grad_fp64_path(eng, T, N, B, network, nlin):
 @pytest.mark.parametrize("T,N,B,network", [(3000, 4, 5, False), (6000, 27, 5, False), (1111, 10, 10, True),
                                            (2500, 16, 10, True), (130, 5, 3, True), (40000, 27, 5, True),
                                            # N*B > 160: the two-kernel GEMM path (column blocks of 128, split-K over time)
-                                           (3000, 40, 5, True), (5000, 64, 10, False), (2100, 130, 5, True)])
+                                           (3000, 40, 5, True), (5000, 64, 10, False), (2100, 130, 5, True),
+                                           # C4's population size: 10240 features, 8 column blocks
+                                           (1536, 1024, 10, True)])
 def test_ll_grad_tensor_core_path(eng, T, N, B, network, nlin):
     """tcgen05 path (FP16 split planes, FP32 epilogue, FP64 sums) at the north-star tolerances:
     1e-6 relative on ll, 1e-5 on gradients, against the float64 oracle."""

@@ -90,3 +90,58 @@ def test_peer_allreduce_and_time_sharded_ll_grad(world, engine_lib):
         assert np.array_equal(out, results[0][1])                    # same summation order: bitwise identical
         assert rel_err(out[:N], ll0) < 1e-6 and rel_err(out[N:2 * N], gb0) < 1e-5
         assert rel_err(out[2 * N:], gw0.reshape(-1)) < 1e-5
+
+
+def _gibbs_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from theano_pyglm_b200.inference.parallel_gibbs import parallel_gibbs_sample
+        from theano_pyglm_b200.models.model_factory import make_model, stabilize_sparsity
+        from theano_pyglm_b200.population import Population
+        N = 5
+        model = make_model('sparse_weighted_model', N=N, dt=0.001)
+        stabilize_sparsity(model)
+        popn = Population(model)
+        rng = np.random.default_rng(3)                               # same data on every rank
+        S = (rng.random((6000, N)) < 0.03).astype(float)
+        popn.add_data({'S': S, 'N': N, 'dt': 0.001, 'T': 6.0, 'stim': None, 'dt_stim': 0.1})
+        np.random.seed(1)
+        x0 = popn.sample()                                           # identical start on every rank
+        smpls = parallel_gibbs_sample(popn, N_samples=2, x0=x0, seed=100)
+        lp = popn.compute_log_p(smpls[-1])
+        q.put((rank, smpls[0], smpls[-1], lp))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neuron_sharded_gibbs_splices_to_one_state(engine_lib):
+    """parallel_gibbs_sample (parallel_gibbs.py:40-197): two ranks each resample their own columns on the
+    engine; after the all-gather splice both hold the same state, and every column was touched."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gibbs_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        rank, first, last, lp = q.get(timeout=300)
+        res[rank] = (first, last, lp)
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    (f0, l0, lp0), (f1, l1, lp1) = res[0], res[1]
+    N = 5
+    assert np.isfinite(lp0) and lp0 == lp1
+    assert l0['net']['graph']['A'].dtype == np.int8
+    assert np.array_equal(l0['net']['graph']['A'], l1['net']['graph']['A'])
+    assert np.array_equal(l0['net']['weights']['W'], l1['net']['weights']['W'])
+    W0 = f0['net']['weights']['W'].reshape(N, N)
+    Wl = l0['net']['weights']['W'].reshape(N, N)
+    for n in range(N):
+        assert l0['glms'][n]['bias']['bias'] == l1['glms'][n]['bias']['bias']
+        assert l0['glms'][n]['n'] == n
+        assert not np.array_equal(W0[:, n], Wl[:, n])                # columns of both shards were resampled
+        assert np.all(np.diag(l0['net']['graph']['A']) == 1)         # self edges stay (p_A = 1 - 1e-8 on the diagonal)

@@ -150,12 +150,14 @@ class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
             self.mu_w_ref, self.sigma_w_ref = self.mu_w, self.sigma_w
 
     # -- engine residency ------------------------------------------------------------------------
-    def begin(self, x):
-        """Upload the state and build I_net for every column (seval(glm.I_net), gibbs.py:812-864)."""
+    def begin(self, x, n_lo=0, n_hi=None):
+        """Upload the state and build I_net for the columns [n_lo, n_hi) (seval(glm.I_net), gibbs.py:812-864);
+        a neuron-sharded rank makes only its own columns resident."""
         popn = self.population
         bias, w, A, W = popn.glm.engine_params(x)
         ds = popn._handle()
-        ds.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code, w_stim=popn.glm.stim_weights(x))
+        ds.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
+                       w_stim=popn.glm.stim_weights(x))
         self._resident = ds
         return ds
 
@@ -235,18 +237,20 @@ class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
         return x
 
     # -- B200 schedule: all columns in lock-step ---------------------------------------------------
-    def sweep_batched(self, x):
-        ds = self._resident or self.begin(x)
+    def sweep_batched(self, x, n_lo=0, n_hi=None):
+        """Columns [n_lo, n_hi) (all by default) advance through their shuffled presynaptic orders together."""
         N = x['net']['graph']['A'].shape[0]
+        n_hi = N if n_hi is None else n_hi
+        ds = self._resident or self.begin(x, n_lo, n_hi)
         p_A = self.network.graph.pA.get_value()
-        orders = np.stack([np.random.permutation(N) for _ in range(N)])        # one shuffled order per column
-        cols = np.arange(N, dtype=np.int32)
+        cols = np.arange(n_lo, n_hi, dtype=np.int32)
+        orders = np.stack([np.random.permutation(N) for _ in cols])            # one shuffled order per column
         for s in range(N):
             pres = orders[:, s].astype(np.int32)
-            cand = np.stack([self._candidates(pres[n], n) for n in range(N)])
-            ll = ds.gibbs_delta_ll(cols, pres, cand)                            # N edges x 11 candidates, one launch
-            for n in range(N):
-                self._resample_edge(ds, x, int(pres[n]), n, ll[n], p_A)
+            cand = np.stack([self._candidates(pres[i], n) for i, n in enumerate(cols)])
+            ll = ds.gibbs_delta_ll(cols, pres, cand)                            # one edge per column x 11 candidates, one launch
+            for i, n in enumerate(cols):
+                self._resample_edge(ds, x, int(pres[i]), int(n), ll[i], p_A)
         return x
 
 
@@ -263,15 +267,31 @@ def initialize_updates(population):
     return serial_updates, parallel_updates
 
 
+def initial_state(population, init_from_mle=False, verbose=False):
+    """Prior draw, optionally moved to the MAP estimate of a standard GLM fitted to the same data and projected
+    onto this model by convert_model (gibbs.py:2486-2507)."""
+    x0 = population.sample()
+    if init_from_mle:
+        from ..models.model_factory import convert_model, make_model
+        from ..population import Population
+        from .coord_descent import coord_descent
+        if verbose:
+            print("Initializing with coordinate descent")
+        mle_model = make_model('standard_glm', N=population.model['N'], dt=population.model['dt'])
+        mle_popn = Population(mle_model, device=population.device)
+        for data in population.data_sequences:
+            mle_popn.add_data({k: v for k, v in data.items() if k not in ('_b200', 'preprocessed', 'fstim')})
+        mle_x0 = coord_descent(mle_popn, x0=mle_popn.sample(), maxiter=1)
+        x0 = convert_model(mle_popn, mle_model, mle_x0, population, population.model, x0)
+    return x0
+
+
 def gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=False, callback=None, batched=True,
                  verbose=False):
-    """Sample the posterior over parameters (gibbs.py:2475-2571).  `init_from_mle` needs convert_model
-    (models/model_factory.py:187-268, a 'next' row) and is not available yet."""
-    if init_from_mle:
-        raise NotImplementedError("init_from_mle needs convert_model, which is outside the built scope")
+    """Sample the posterior over parameters (gibbs.py:2475-2571)."""
     N = population.model['N']
     if x0 is None:
-        x0 = population.sample()
+        x0 = initial_state(population, init_from_mle, verbose)
     serial_updates, parallel_updates = initialize_updates(population)
     net_update = parallel_updates[-1]
     x = x0
