@@ -89,20 +89,27 @@ def test_ll_grad_tensor_core_path(eng, T, N, B, network, nlin):
     p = make_problem(T, N, B, network=network)
     if nlin == orc.NLIN_EXP:
         p['bias'] = p['bias'] - 17.0
-    _, ll, gb, gw = oracle_all(p, nlin)
+    fS_o, ll, gb, gw = oracle_all(p, nlin)
     ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
     assert ds.path_info("auto")["name"].startswith("tcgen05")
     ll_g, gb_g, gw_g = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="tc")
-    assert np.max(np.abs(ll_g - ll) / np.abs(ll)) < LL_RTOL, (ll_g, ll)
+    ll_den = np.abs(ll)
+    if N * B > 2048:
+        # 10^4-feature dot products accumulated in FP32: the bound is relative to the size of the sum's terms
+        # (for the exp model at a 20 Hz rate, -dt*lam and S*log(lam) cancel to a small ll in some neurons)
+        x = orc.population_activation(fS_o, p['bias'], p['w'], p['A'], p['W'])
+        lam, _d, loglam = orc.nlin_and_derivative(x, nlin)
+        ll_den = np.sum(np.abs(p['dt'] * lam) + np.abs(loglam * p['S']), axis=0)
+    assert np.max(np.abs(ll_g - ll) / ll_den) < LL_RTOL, (ll_g, ll)
     assert rel_err(gb_g, gb) < GRAD_RTOL
     assert rel_err(gw_g, gw) < GRAD_RTOL
     # second call reuses the planes; sub-range of neurons; ll-only
     lo, hi = 1, N - 1
     ll_s, gb_s, gw_s = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, n_lo=lo, n_hi=hi, path="tc")
-    assert np.max(np.abs(ll_s - ll[lo:hi]) / np.abs(ll[lo:hi])) < LL_RTOL
+    assert np.max(np.abs(ll_s - ll[lo:hi]) / ll_den[lo:hi]) < LL_RTOL
     assert rel_err(gw_s, gw[lo:hi]) < GRAD_RTOL
     ll_only = ds.ll(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="tc")
-    assert np.max(np.abs(ll_only - ll) / np.abs(ll)) < LL_RTOL
+    assert np.max(np.abs(ll_only - ll) / ll_den) < LL_RTOL
     # and it agrees with the exact FP64 path on the device
     ll_x, gb_x, gw_x = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="fp64")
     assert rel_err(gw_g, gw_x) < GRAD_RTOL and rel_err(gb_g, gb_x) < GRAD_RTOL
