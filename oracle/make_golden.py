@@ -82,10 +82,33 @@ def golden_gibbs_column():
                         A_dec=np.array([r['A'] for r in rec], dtype=np.int8), A_final=A, W_final=W)
 
 
+def golden_stimulus_glm():
+    """standard_glm with a BasisStimulus background (bkgd.py:45-172): a 2-D stimulus sampled at 10 ms,
+    interpolated to the bins, projected on a 3-function basis, weights w_stim (N, 6)."""
+    rng = np.random.default_rng(5)
+    N, B, nT, dt, dt_stim = 5, 5, 2500, 0.001, 0.01
+    p = make_problem(nT, N, B, seed=77, network=True)
+    stim = np.cumsum(rng.standard_normal((int(np.ceil(nT * dt / dt_stim)) + 1, 2)), axis=0) * 0.1
+    prms = dict(type='cosine', n_eye=0, n_cos=3, a=1.0 / 120, b=0.5, orth=False, norm=True)
+    ib_s = orc.interpolate_stim_basis(orc.create_basis(prms), dt, 0.3, True)
+    istim, fstim = orc.filter_stimulus(stim, dt_stim, nT, dt, ib_s)
+    w_stim = 0.05 * rng.standard_normal((N, fstim.shape[1]))
+    fS = orc.convolve_with_basis(p['S'].astype(np.float64), p['ibasis'])
+    ll, gb, gw, gs = orc.population_ll_grad(fS, p['S'], dt, p['bias'], p['w'], p['A'], p['W'], orc.NLIN_SOFTPLUS,
+                                            fstim=fstim, w_stim=w_stim)
+    np.savez_compressed(os.path.join(OUT, "stimulus_glm_n5.npz"),
+                        S=p['S'], ibasis=p['ibasis'], dt=dt, bias=p['bias'], w=p['w'], A=p['A'], W=p['W'],
+                        stim=stim, dt_stim=dt_stim, stim_ibasis=ib_s, istim_rows=istim[::100], fstim_rows=fstim[::100],
+                        w_stim=w_stim, ll=ll, g_bias=gb, g_w=gw, g_w_stim=gs, nlin=orc.NLIN_SOFTPLUS,
+                        lp_stim=np.array([orc.stim_log_prior(w_stim[n]) for n in range(N)]))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    golden_standard_glm()
-    golden_network_glm()
-    golden_gibbs_column()
+    if "--only-new" not in sys.argv:      # the first four fixtures are frozen; regenerate them only on purpose
+        golden_standard_glm()
+        golden_network_glm()
+        golden_gibbs_column()
+    golden_stimulus_glm()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

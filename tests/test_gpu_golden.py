@@ -1,0 +1,84 @@
+"""GPU parity against the committed golden fixtures (tests/golden/*.npz, minted by oracle/make_golden.py):
+the engine is fed the fixture's inputs through the C ABI and must reproduce the stored filter rows,
+log-likelihoods, gradients and Gibbs decisions.  No oracle code runs here except the decision rule."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyglm_oracle as orc
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name)))
+
+
+@pytest.fixture(scope="module")
+def eng(engine_lib):
+    import theano_pyglm_b200 as pg
+    return pg
+
+
+@pytest.mark.parametrize("name", ["standard_glm_n4.npz", "network_glm_n9_softplus.npz", "network_glm_n9_exp.npz"])
+def test_engine_reproduces_golden_ll_and_gradient(eng, name):
+    g = load(name)
+    N = g['S'].shape[1]
+    gw = g['g_w'].reshape(N, -1)
+    for x_dtype, path, lt, gt in (("f64", "fp64", 1e-11, 1e-9), ("f32", "fp64", 1e-6, 1e-5), ("f32", "tc", 1e-6, 1e-5)):
+        ds = eng.Dataset(g['S'], float(g['dt']), g['ibasis'], x_dtype=x_dtype)
+        fS = ds.fS()
+        tol = 1e-12 if x_dtype == "f64" else 2e-7 * np.max(np.abs(g['fS_rows']))
+        assert np.max(np.abs(fS[::100] - g['fS_rows'])) <= tol
+        ll, gb, gwe = ds.ll_grad(g['bias'], g['w'], g['A'], g['W'], nlin=int(g['nlin']), path=path)
+        assert np.max(np.abs(ll - g['ll']) / np.abs(g['ll'])) < lt, (name, x_dtype, path)
+        assert rel_err(gb, g['g_bias']) < gt and rel_err(gwe, gw) < gt, (name, x_dtype, path)
+        ds.close()
+
+
+def test_engine_reproduces_golden_stimulus_fixture(eng):
+    g = load("stimulus_glm_n5.npz")
+    T, N = g['S'].shape
+    # stimulus projection on the GPU from the interpolated stimulus (bkgd.py:134-154)
+    t = float(g['dt']) * np.arange(T)
+    t_stim = float(g['dt_stim']) * np.arange(g['stim'].shape[0])
+    istim = np.stack([np.interp(t, t_stim, g['stim'][:, d]) for d in range(g['stim'].shape[1])], axis=1)
+    fstim = eng.engine.filter_dense(istim, g['stim_ibasis']).reshape(T, -1)
+    assert np.max(np.abs(fstim[::100] - g['fstim_rows'])) < 1e-12 * np.max(np.abs(g['fstim_rows']))
+    gw = g['g_w'].reshape(N, -1)
+    for x_dtype, path, lt, gt in (("f64", "fp64", 1e-11, 1e-9), ("f32", "tc", 1e-6, 1e-5)):
+        ds = eng.Dataset(g['S'], float(g['dt']), g['ibasis'], x_dtype=x_dtype, fstim=fstim)
+        ll, gb, gwe, gs = ds.ll_grad(g['bias'], g['w'], g['A'], g['W'], nlin=int(g['nlin']), path=path, w_stim=g['w_stim'])
+        assert np.max(np.abs(ll - g['ll']) / np.abs(g['ll'])) < lt
+        assert rel_err(gb, g['g_bias']) < gt and rel_err(gwe, gw) < gt and rel_err(gs, g['g_w_stim']) < gt
+        ds.close()
+
+
+def test_engine_reproduces_golden_gibbs_column(eng):
+    """The stored column sweep (shuffled order, uniforms, weight draws): same candidate log-likelihoods, same
+    log odds, identical accept / reject decisions, identical final A and W."""
+    g = load("gibbs_column_n5.npz")
+    N = g['S'].shape[1]
+    n_post = int(g['n_post'])
+    ds = eng.Dataset(g['S'], float(g['dt']), g['ibasis'], x_dtype="f64")
+    A, W = g['A0'].copy(), g['W0'].copy()
+    ds.gibbs_begin(g['bias'], g['w'], A, W, nlin="explinear")
+    for i, n_pre in enumerate(g['order']):
+        mu, sig = (-0.2, 0.5) if n_pre == n_post else (0.0, 1.0)
+        cand = np.concatenate([orc.gh_candidates(mu, sig), [0.0]])
+        out = ds.gibbs_delta_ll([n_post], [n_pre], cand[None, :])[0]
+        assert np.allclose(out[:10], g['log_L'][i], rtol=1e-10, atol=1e-9)
+        assert abs(out[10] - g['ll_noA'][i]) <= 1e-10 * abs(g['ll_noA'][i]) + 1e-9
+        lp_noA, lp_A = orc.collapsed_edge_log_odds(out[:10], out[10], g['p_A'][n_pre, n_post])
+        assert abs(lp_A - g['log_pr_A'][i]) <= 1e-9 * abs(g['log_pr_A'][i]) + 1e-9
+        a_new = orc.log_sum_exp_sample([lp_noA, lp_A], g['uniforms'][i])
+        assert a_new == g['A_dec'][i]
+        w_new = mu + sig * g['wnorm'][n_pre]
+        ds.gibbs_commit([n_post], [n_pre], [a_new], [w_new])
+    A_g, W_g = ds.gibbs_state()
+    assert np.array_equal(A_g, g['A_final']) and np.allclose(W_g, g['W_final'], rtol=0, atol=0)
+    ds.gibbs_end()
+    ds.close()

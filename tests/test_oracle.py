@@ -32,6 +32,39 @@ def test_oracle_reproduces_golden_ll_and_gradient(name):
         assert np.allclose(w1, g['g_w'][n], rtol=1e-9, atol=1e-10)
 
 
+def test_oracle_reproduces_golden_stimulus_fixture():
+    g = load("stimulus_glm_n5.npz")
+    S = g['S'].astype(np.float64)
+    nT = S.shape[0]
+    ib_s = orc.interpolate_stim_basis(orc.create_basis(dict(type='cosine', n_eye=0, n_cos=3, a=1.0 / 120, b=0.5,
+                                                            orth=False, norm=True)), float(g['dt']), 0.3, True)
+    assert np.allclose(ib_s, g['stim_ibasis'], rtol=0, atol=1e-15)
+    istim, fstim = orc.filter_stimulus(g['stim'], float(g['dt_stim']), nT, float(g['dt']), ib_s)
+    assert np.allclose(istim[::100], g['istim_rows'], rtol=0, atol=1e-13)
+    assert np.allclose(fstim[::100], g['fstim_rows'], rtol=0, atol=1e-12)
+    # the FFT filter of the real-valued stimulus == its defining causal sum
+    direct = np.zeros_like(fstim)
+    R, Bs = ib_s.shape
+    for d in range(2):
+        for b in range(Bs):
+            direct[:, d * Bs + b] = np.convolve(istim[:, d], np.concatenate([[0.0], ib_s[:, b]]))[:nT]
+    assert np.max(np.abs(direct - fstim)) < 1e-12 * np.max(np.abs(fstim))
+    fS = orc.convolve_with_basis(S, g['ibasis'])
+    ll, gb, gw, gs = orc.population_ll_grad(fS, S, float(g['dt']), g['bias'], g['w'], g['A'], g['W'], int(g['nlin']),
+                                            fstim=fstim, w_stim=g['w_stim'])
+    assert rel_err(ll, g['ll']) < 1e-12 and rel_err(gb, g['g_bias']) < 1e-10
+    assert rel_err(gw, g['g_w']) < 1e-10 and rel_err(gs, g['g_w_stim']) < 1e-10
+    # d ll / d w_stim by central differences
+    eps = 1e-6
+    for (n, f) in ((0, 0), (3, 5)):
+        wp, wm = g['w_stim'].copy(), g['w_stim'].copy()
+        wp[n, f] += eps
+        wm[n, f] -= eps
+        lp = orc.population_ll_grad(fS, S, float(g['dt']), g['bias'], g['w'], g['A'], g['W'], int(g['nlin']), fstim=fstim, w_stim=wp)[0][n]
+        lm = orc.population_ll_grad(fS, S, float(g['dt']), g['bias'], g['w'], g['A'], g['W'], int(g['nlin']), fstim=fstim, w_stim=wm)[0][n]
+        assert abs((lp - lm) / (2 * eps) - gs[n, f]) < 1e-5 * max(1.0, abs(gs[n, f]))
+
+
 def test_golden_standard_glm_matches_simulator_activation():
     """The reference's own check (test/generate_synth_data.py:124-129): firing rate from the likelihood
     graph equals f_nlin of the activation the simulator accumulated in lag space."""
