@@ -175,21 +175,33 @@ __device__ __forceinline__ void poisson_terms(float x, float s, float dt, float&
             lam = x;
             sig = 1.0f;
         } else {
-            const float e = __expf(-fabsf(x));                 // in (0,1]
-            float l1p = e * (1.0f - e * (0.5f - e * (0.33333334f - 0.25f * e)));   // log1p series, |err| < e^5/5
-            if (__any_sync(0xffffffffu, e >= 0.03125f)) {      // log(u) * e/(u-1) undoes the rounding of u = 1+e
+            const float e = __expf(-fabsf(x));                 // in [0,1]; flushes to 0 below x ~ -87
+            // q = log1p(e)/e, so that for x < 0 lam = e q, log(lam) = x + log(q) and f'/lam = 1/((1+e) q) stay
+            // finite and accurate however negative x is (log(lam) -> x, f'/lam -> 1), as in FP64
+            float q = 1.0f - e * (0.5f - e * (0.33333334f - 0.25f * e));       // series, |err| < e^4/5
+            if (__any_sync(0xffffffffu, e >= 0.03125f)) {      // log(u)/(u-1) undoes the rounding of u = 1+e
                 const float u = 1.0f + e;
-                const float big = __logf(u) * __fdividef(e, u - 1.0f);
-                l1p = e >= 0.03125f ? big : l1p;
+                const float big = __fdividef(__logf(u), u - 1.0f);
+                q = e >= 0.03125f ? big : q;
             }
+            const float l1p = e * q;
             lam = x > 0.f ? x + l1p : l1p;
             float inv1pe;
             asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv1pe) : "f"(1.0f + e));   // 1 ulp; f' enters r linearly
             sig = x > 0.f ? inv1pe : e * inv1pe;
+            term = -dt * lam;
+            r = -dt * sig;
+            if (any_spike) {                                   // ~2% of bins have s != 0
+                const float loglam = x > 0.f ? __logf(lam) : x + __logf(q);
+                const float ratio = x > 0.f ? __fdividef(sig, lam) : __fdividef(inv1pe, q);
+                term = fmaf(s, s != 0.f ? loglam : 0.f, term);
+                r = fmaf(s, ratio, r);
+            }
+            return;
         }
         term = -dt * lam;
         r = -dt * sig;
-        if (any_spike) {                                       // ~2% of bins have s != 0
+        if (any_spike) {
             term = fmaf(s, s != 0.f ? __logf(lam) : 0.f, term);
             r = fmaf(__fdividef(s, lam), sig, r);
         }
