@@ -390,3 +390,49 @@ def test_gibbs_delta_ll_with_stimulus_and_extreme_activations(eng):
     assert seen_lo and seen_hi                                   # the test really visited both tails
     ds.gibbs_end()
     ds.close()
+
+
+# ----------------------------------------------------------------------------------------------
+# Randomised sweep over ragged shapes
+# ----------------------------------------------------------------------------------------------
+def _ragged_cases():
+    rng = np.random.default_rng(2024)
+    cases = []
+    for i in range(28):
+        T = int(rng.choice([1, 2, 31, 127, 128, 129, 255, 257, 700, 1500]))
+        N = int(rng.choice([1, 2, 3, 7, 27, 31, 32, 33, 45]))
+        B = int(rng.choice([1, 2, 5, 8, 10, 16]))
+        R = int(rng.choice([1, 3, 50, 200]))
+        cases.append((i, T, N, B, R, bool(rng.integers(2)), int(rng.integers(2)), float(rng.choice([0.0, 0.02, 0.3]))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _ragged_cases(), ids=lambda c: "c%d-T%d-N%d-B%d-R%d" % c[:5])
+def test_ragged_shapes_all_paths(eng, case):
+    """Shapes that do not fill a tile, a warp, a chunk or a basis window (T < R, N = 1, B = 16, silent and
+    very active recordings): filter bit-exact in float64, ll / gradients on every path that applies."""
+    i, T, N, B, R, network, nlin, rate = case
+    p = make_problem(T, N, B, seed=500 + i, rate=rate, network=network, R=R)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 17.0
+    S = p['S'].astype(np.float64)
+    fS = orc.convolve_with_basis_direct(S, p['ibasis'])
+    ll, gb, gw = orc.population_ll_grad(fS, p['S'], p['dt'], p['bias'], p['w'], p['A'], p['W'], nlin)
+    gw = gw.reshape(N, -1)
+    ll_den = np.maximum(np.abs(ll), 1e-3)                         # a silent one-bin recording has ll ~ -dt*lam ~ 0.02
+    d64 = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f64")
+    assert np.array_equal(d64.fS(), fS)                            # same summation order as the oracle's causal sum
+    l, b, w = d64.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="fp64")
+    assert np.max(np.abs(l - ll) / ll_den) < 1e-11 and rel_err(b, gb) < 1e-9
+    assert np.max(np.abs(w - gw)) <= 1e-9 * max(np.max(np.abs(gw)), 1e-12)
+    d64.close()
+    d32 = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+    # The FP32 epilogue rounds every bin's term at ~2^-23 relative; over the long recordings of the configs these
+    # roundings average out (1e-7 at T = 1e6), over a hundred bins they do not, so the bound widens as 1/sqrt(T).
+    tc_tol = LL_RTOL * max(1.0, (2000.0 / T) ** 0.5)
+    for path in ("fp64", "tc"):
+        l, b, w = d32.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path=path)
+        assert np.max(np.abs(l - ll) / ll_den) < (tc_tol if path == "tc" else LL_RTOL), (path, l, ll)
+        assert np.max(np.abs(b - gb)) <= GRAD_RTOL * max(np.max(np.abs(gb)), 1e-6), path
+        assert np.max(np.abs(w - gw)) <= GRAD_RTOL * max(np.max(np.abs(gw)), 1e-6), path
+    d32.close()
