@@ -436,3 +436,45 @@ def test_ragged_shapes_all_paths(eng, case):
         assert np.max(np.abs(b - gb)) <= GRAD_RTOL * max(np.max(np.abs(gb)), 1e-6), path
         assert np.max(np.abs(w - gw)) <= GRAD_RTOL * max(np.max(np.abs(gw)), 1e-6), path
     d32.close()
+
+
+def _gibbs_cases():
+    rng = np.random.default_rng(77)
+    out = []
+    for i in range(14):
+        out.append((i, int(rng.choice([1, 37, 255, 256, 257, 1000, 8192, 8193, 9000])), int(rng.choice([1, 2, 5, 9])),
+                    int(rng.choice([1, 5, 10, 16])), int(rng.choice([1, 3, 4, 11, 16])), int(rng.integers(2)),
+                    str(rng.choice(["f64", "f32"]))))
+    return out
+
+
+@pytest.mark.parametrize("case", _gibbs_cases(), ids=lambda c: "g%d-T%d-N%d-B%d-Q%d-nl%d-%s" % c)
+def test_gibbs_delta_ll_ragged(eng, case):
+    """K4 on shapes that do not fill a block (8192 bins), a 256-bin pass or a warp, for every candidate-count
+    and basis-size template, both nonlinearities: each candidate ll against gibbs.py:910-937 restated."""
+    i, T, N, B, Q, nlin, x_dtype = case
+    p = make_problem(T, N, B, seed=900 + i, network=True, dirichlet=bool(i % 2), rate=0.05)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 17.0
+        p['W'] = p['W'] * (0.02 if i % 2 else 1.0)                  # unit-area impulses under exp: keep rates finite
+    rng = np.random.default_rng(i)
+    fS = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype)
+    ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)
+    n_post, n_pre = int(rng.integers(N)), int(rng.integers(N))
+    cand = rng.standard_normal(Q) * (0.02 if (nlin == orc.NLIN_EXP and i % 2) else 1.0)
+    out = ds.gibbs_delta_ll([n_post], [n_pre], cand[None, :])[0]
+    I_imp = orc.impulse_current(fS, p['w'][n_post])
+    Weff = orc.effective_weights(p['A'], p['W'], n_post).copy()
+    Weff[n_pre] = 0.0
+    I_other = I_imp @ Weff
+    for q in range(Q):
+        ref = orc.gibbs_glm_ll(p['bias'][n_post], 0.0, I_other, I_imp[:, n_pre], cand[q], p['S'][:, n_post], p['dt'], nlin)
+        if not np.isfinite(ref):
+            assert not np.isfinite(out[q]) or abs(out[q]) > 1e300
+            continue
+        scale = abs(ref) + 1e-3
+        tol = (1e-10 if x_dtype == "f64" else 3e-6) * scale + (1e-9 if x_dtype == "f64" else 2e-5)
+        assert abs(out[q] - ref) <= tol, (q, out[q], ref)
+    ds.gibbs_end()
+    ds.close()
