@@ -471,6 +471,13 @@ def run_gibbs(args, wl):
     peak, peak_src = load_peaks()
     alg_bytes = N * T * (8 + B * 8 + 1)          # per edge and bin: I_net f64 + X slice f64 + spike byte
     achieved = alg_bytes / (ms_dev * 1e-3) / 1e9
+    gibbs_traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            gibbs_traffic = json.load(f).get("gibbs_delta_kernel", {}).get(args.workload)
+    # FP64 work per bin: Q softplus evaluations of 21 fused operations + the u / base current (B + 2)
+    fp64_flops = 2.0 * N * T * (Q * 21 + B + 2)
     line = {
         "metric": "Gibbs edge-sweeps/sec", "value": 1.0 / (N * ms_dev * 1e-3), "unit": "sweeps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
@@ -484,8 +491,12 @@ def run_gibbs(args, wl):
                 "includes": "host decision rule (logsumexp, Bernoulli draw) and gibbs_commit"},
         "gpu_launches": 2 * args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "gibbs_delta_kernel", "peak_source": peak_src, "kernel_ms": ms_dev,
-                     "algorithmic_bytes": alg_bytes},
+                     "traffic": gibbs_traffic, "kernel": "gibbs_delta_kernel", "peak_source": peak_src, "kernel_ms": ms_dev,
+                     "algorithmic_bytes": alg_bytes,
+                     "note": "FP64-ALU bound, not HBM (SURVEY.md 8d): the second figure is the FP64 rate",
+                     "fp64": {"achieved": fp64_flops / (ms_dev * 1e-3) / 1e12, "peak": 40.0, "unit": "TFLOP/s",
+                              "frac": fp64_flops / (ms_dev * 1e-3) / 1e12 / 40.0,
+                              "peak_source": "nominal B200 FP64 (not in MEASURED_PEAKS.json)"}},
     }
     if not args.no_cpu:
         from oracle import pyglm_oracle as orc

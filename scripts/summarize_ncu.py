@@ -2,6 +2,7 @@
 
     python scripts/summarize_ncu.py launches gpurun_out/launches.csv profiles/r1_launches_c2.md
     python scripts/summarize_ncu.py full gpurun_out/prof.ncu-rep profiles/r1_fused_kernel_c2.md
+    python scripts/summarize_ncu.py multi gpurun_out/launches_c3_gemm.csv profiles/r1_launches_c3_gemm.md
 """
 import collections
 import csv
@@ -25,6 +26,14 @@ KEYS = [
     "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "lts__t_bytes.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 
 
@@ -56,5 +65,27 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def multi(src, dst):
+    """Launch list captured with several --metrics: one row per kernel, one column per metric (means)."""
+    lines = [l for l in open(src) if l.startswith('"')]
+    agg = collections.OrderedDict()
+    units = {}
+    for row in csv.DictReader(lines):
+        k = row["Kernel Name"].split("(")[0]
+        v = row["Metric Value"].replace(",", "")
+        if v == "":
+            continue
+        agg.setdefault(k, collections.OrderedDict()).setdefault(row["Metric Name"], []).append(float(v))
+        units[row["Metric Name"]] = row["Metric Unit"]
+    metrics = list(units)
+    with open(dst, "w") as f:
+        f.write("| kernel | launches | " + " | ".join("%s [%s]" % (m, units[m]) for m in metrics) + " |\n")
+        f.write("|---|---|" + "---|" * len(metrics) + "\n")
+        for k, d in agg.items():
+            n = max(len(v) for v in d.values())
+            f.write("| `%s` | %d | " % (k, n) + " | ".join("%.4g" % (sum(d[m]) / len(d[m])) if m in d else "" for m in metrics) + " |\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "multi": multi}[sys.argv[1]](sys.argv[2], sys.argv[3])
