@@ -140,11 +140,24 @@ struct GemmFwdArgs {
     float dt;
 };
 
-template <int NLIN>
+// PAIR: launched in clusters of two CTAs that work on the two column blocks 2j, 2j+1 of the same time tile.  The
+// X chunk is the same for both, so each CTA fetches half of its rows and multicasts them into both CTAs' stages:
+// the X planes cross L2 once per pair instead of once per CTA (the kernel is L2-throughput bound).  A stage may be
+// refilled only when BOTH consumers are done with it, so the MMA commits arrive on both CTAs' empty barriers.
+// With PAIR the X maps have 64-row boxes.
+template <int NLIN, bool PAIR>
 __global__ void __launch_bounds__(kGThreads, 1)
 tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
                    const __grid_constant__ CUtensorMap mapM1, const __grid_constant__ CUtensorMap mapM2, GemmFwdArgs a)
 {
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    // work items of this CTA: w = first, first + stride, ...; item -> (time tile, column block)
+    const int64_t w_first = PAIR ? blockIdx.x / 2 : blockIdx.x;
+    const int64_t w_stride = PAIR ? gridDim.x / 2 : gridDim.x;
+    const int cbw = PAIR ? a.ncb / 2 : a.ncb;                    // column-block work items per time tile
+    const int64_t nwork = a.ntt * cbw;
+    auto tile_tt = [&](int64_t w) { return w / cbw; };
+    auto tile_cb = [&](int64_t w) { return PAIR ? 2 * (int)(w % cbw) + (int)crank : (int)(w % cbw); };
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdStages * kFwdStageBytes);
@@ -156,7 +169,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kFwdStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < kFwdStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], PAIR ? 2 : 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kGEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -166,24 +179,30 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();            // the peer's barriers are initialised before anything is multicast into them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int64_t ntiles = a.ntt * a.ncb;
 
     if (warp == kGTmaWarp) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             uint32_t chunk = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int row0 = (int)((tile / a.ncb) * kGT);
-                const int col0 = (int)((tile % a.ncb) * kGN);
+            for (int64_t w = w_first; w < nwork; w += w_stride) {
+                const int row0 = (int)(tile_tt(w) * kGT);
+                const int col0 = tile_cb(w) * kGN;
                 for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
                     const int s = chunk % kFwdStages;
                     mbar_wait(&bar_empty[s], ((chunk / kFwdStages) & 1) ^ 1);
                     mbar_arrive_expect_tx(&bar_full[s], kFwdStageBytes);
                     unsigned char* st = smem + s * kFwdStageBytes;
-                    tma_load_2d(st, &mapX1, &bar_full[s], kc * 32, row0);
-                    tma_load_2d(st + kGT * 64, &mapX2, &bar_full[s], kc * 32, row0);
+                    if (PAIR) {                  // this CTA's half of the rows, into both CTAs
+                        const int half = (int)crank * (kGT / 2);
+                        tma_load_2d_multicast(st + half * 64, &mapX1, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
+                        tma_load_2d_multicast(st + kGT * 64 + half * 64, &mapX2, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
+                    } else {
+                        tma_load_2d(st, &mapX1, &bar_full[s], kc * 32, row0);
+                        tma_load_2d(st + kGT * 64, &mapX2, &bar_full[s], kc * 32, row0);
+                    }
                     tma_load_2d(st + 2 * kGT * 64, &mapM1, &bar_full[s], kc * 32, col0);
                     tma_load_2d(st + 3 * kGT * 64, &mapM2, &bar_full[s], kc * 32, col0);
                 }
@@ -202,7 +221,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
             // warps drain every finished segment into FP32 registers (round-to-nearest adds) while the next
             // one accumulates.  Short running sums are small, and so are their rounding losses.
             uint32_t chunk = 0, sgc = 0;
-            for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int64_t w = w_first; w < nwork; w += w_stride) {
                 for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
                     const int ab = sgc & 1;
                     const int in_seg = kc % a.seg;
@@ -223,7 +242,8 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                         umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc2, acc);    // X1 [M1 | M2]
                         umma_f16(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc, 1u);      // X2 M1
                     }
-                    umma_commit(&bar_empty[s]);
+                    if (PAIR) umma_commit_multicast(&bar_empty[s], (uint16_t)3);
+                    else umma_commit(&bar_empty[s]);
                     if (in_seg == a.seg - 1 || kc == a.nkc - 1) {
                         umma_commit(&bar_acc_full[ab]);
                         ++sgc;
@@ -240,9 +260,9 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
         double* my_part = a.part + ((int64_t)blockIdx.x * 4 + q) * a.Npr * 2;
         const int nseg = (a.nkc + a.seg - 1) / a.seg;
         uint32_t sgc = 0;
-        for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const int64_t t = (tile / a.ncb) * kGT + row;
-            const int col0 = (int)((tile % a.ncb) * kGN) + cg * kGColsPerWarp;      // first of this warp's 32 columns
+        for (int64_t w = w_first; w < nwork; w += w_stride) {
+            const int64_t t = tile_tt(w) * kGT + row;
+            const int col0 = tile_cb(w) * kGN + cg * kGColsPerWarp;                 // first of this warp's 32 columns
             const float lv = t < a.T ? 1.0f : 0.0f;
             // column parameters: lane l holds column col0 + l
             const float ism_l = a.colpar[col0 + lane], bias_l = a.colpar[a.Npr + col0 + lane];
@@ -334,6 +354,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();            // neither CTA leaves while the other may still signal its barriers
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -530,7 +551,13 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if ((rc = ensure((void**)&g.Mp, &g.Mp_elems, (size_t)2 * Npr * Kp, sizeof(__half)))) return rc;
     if ((rc = ensure((void**)&g.colpar, &g.colpar_elems, (size_t)2 * Npr, sizeof(float)))) return rc;
     if ((rc = ensure((void**)&g.R, &g.R_elems, (size_t)2 * a.T * Npr, sizeof(__half)))) return rc;
-    const int nctas = (int)std::min<int64_t>(ntt * ncb, ws.num_sms);
+    // Optional: column blocks in pairs (clusters of two CTAs, X tile multicast).  Measured at C3: L2 bytes 28.3 -> 25.4 GB
+    // but crossbar-to-SM bytes 20.9 -> 26.1 GB and the same 2.44 ms: what limits the kernel is the ~30 B/clk each SM can
+    // ingest, which multicast does not reduce.  Off unless PYGLM_GEMM_PAIR=1.
+    bool pair = false;
+    if (const char* env = getenv("PYGLM_GEMM_PAIR")) pair = atoi(env) != 0 && (ncb % 2 == 0) && ws.num_sms >= 2;
+    int nctas = (int)std::min<int64_t>(pair ? ntt * ncb : ntt * ncb, ws.num_sms);
+    if (pair) nctas &= ~1;
     if ((rc = ensure((void**)&g.part, &g.part_elems, (size_t)nctas * 4 * Npr * 2, sizeof(double)))) return rc;
 
     PYGLM_CUDA(cudaMemsetAsync(g.part, 0, (size_t)nctas * 4 * Npr * 2 * sizeof(double), stream));
@@ -552,19 +579,33 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if (const char* env = getenv("PYGLM_GEMM_SEG")) f.seg = std::max(1, atoi(env));      // precision experiments
     f.ntt = ntt; f.ncb = ncb; f.colpar = g.colpar; f.R = g.R; f.plane = (int64_t)a.T * Npr; f.part = g.part; f.dt = (float)a.dt;
     const int smem_f = kFwdStages * kFwdStageBytes + 256 + 1024;
-    auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP> : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS>;
-    PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
-    kf<<<nctas, kGThreads, smem_f, stream>>>(xmaps[0], xmaps[1], mM1, mM2, f);
-    PYGLM_CUDA(cudaGetLastError());
-    tc_gemm_final_ll_kernel<<<(unsigned)a.ncols, 256, 0, stream>>>(g.part, nctas, Npr, a.ncols, a.out_ll, a.out_gb);
-    PYGLM_CUDA(cudaGetLastError());
-    if (!grad) return PYGLM_B200_OK;
-
     if (!g.mapX64_ready) {
         if ((rc = tc_make_map_2d(&g.mapX64[0], ws.X1, ws.ldp, a.T, ws.ldp, 32, kBwdRows))) return rc;
         if ((rc = tc_make_map_2d(&g.mapX64[1], ws.X2, ws.ldp, a.T, ws.ldp, 32, kBwdRows))) return rc;
         g.mapX64_ready = true;
     }
+    if (pair) {
+        auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, true>
+                                                : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, true>;
+        PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)nctas); cfg.blockDim = dim3(kGThreads); cfg.dynamicSmemBytes = smem_f; cfg.stream = stream;
+        cudaLaunchAttribute attr{};
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        PYGLM_CUDA(cudaLaunchKernelEx(&cfg, kf, g.mapX64[0], g.mapX64[1], mM1, mM2, f));
+    } else {
+        auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, false>
+                                                : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, false>;
+        PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+        kf<<<nctas, kGThreads, smem_f, stream>>>(xmaps[0], xmaps[1], mM1, mM2, f);
+    }
+    PYGLM_CUDA(cudaGetLastError());
+    tc_gemm_final_ll_kernel<<<(unsigned)a.ncols, 256, 0, stream>>>(g.part, nctas, Npr, a.ncols, a.out_ll, a.out_gb);
+    PYGLM_CUDA(cudaGetLastError());
+    if (!grad) return PYGLM_B200_OK;
+
     if ((rc = tc_make_map_2d(&mR1, g.R, Npr, a.T, Npr, 32, kBwdRows))) return rc;
     if ((rc = tc_make_map_2d(&mR2, g.R + (size_t)a.T * Npr, Npr, a.T, Npr, 32, kBwdRows))) return rc;
     int64_t splits = std::max<int64_t>(1, (int64_t)ws.num_sms / ((int64_t)nfb * ncb));

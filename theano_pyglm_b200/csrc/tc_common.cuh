@@ -64,6 +64,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, 
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` and each of those
+// CTAs' barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1,
+                                                      uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -112,6 +131,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar)
                  ::"r"(smem_u32(bar)) : "memory");
 }
 // 32 lanes x 32 columns of FP32 accumulators -> 32 registers per thread (thread = TMEM lane)
+// commit that arrives on the barrier at the same offset of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
 {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
