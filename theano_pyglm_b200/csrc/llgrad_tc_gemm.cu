@@ -132,7 +132,7 @@ struct GemmFwdArgs {
     int64_t T; int n_lo, ncols, Npr;
     int nkc;                           // 32-feature chunks
     int seg;                           // chunks per TMEM accumulation segment (see the MMA issuer)
-    int debug;                         // experiments only (PYGLM_GEMM_DEBUG)
+    int debug;                         // experiments (PYGLM_GEMM_DEBUG): 1 no MMAs, 2 always the same tile (L2-hot loads), 4 no epilogue math
     int64_t ntt; int ncb;              // time tiles, column blocks
     const float* colpar;               // [2][Npr]
     __half* R; int64_t plane;          // residual planes: R1 at R, R2 at R + plane; row pitch Npr
@@ -140,46 +140,64 @@ struct GemmFwdArgs {
     float dt;
 };
 
-// PAIR: launched in clusters of two CTAs that work on the two column blocks 2j, 2j+1 of the same time tile.  The
-// X chunk is the same for both, so each CTA fetches half of its rows and multicasts them into both CTAs' stages:
-// the X planes cross L2 once per pair instead of once per CTA (the kernel is L2-throughput bound).  A stage may be
-// refilled only when BOTH consumers are done with it, so the MMA commits arrive on both CTAs' empty barriers.
-// With PAIR the X maps have 64-row boxes.
-template <int NLIN, bool PAIR>
+// MODE 0: one CTA per 128 x 128 tile.
+// MODE 1 (experiment, PYGLM_GEMM_PAIR=1): clusters of two CTAs on the column blocks 2j, 2j+1 of one time tile; the X
+//         chunk is the same for both, so each CTA fetches half of its rows and multicasts them into both stages
+//         (X maps with 64-row boxes; a stage is refilled when BOTH consumers are done: commits go to both CTAs).
+// MODE 2: CTA pair (cta_group::2).  The pair owns 256 bins x 128 neurons: each CTA holds its own 128 bins of X and
+//         only 64 of the 128 weight columns, the leader issues 256 x 128 x 16 MMAs that read both halves, and each
+//         CTA's TMEM receives the accumulators of its own bins.  A CTA ingests 24 KB per K chunk instead of 32 KB
+//         for the same outputs: the forward kernel is bound by what an SM can ingest.  All TMA transactions signal
+//         the leader's full barrier; the leader's commits release the stages and publish the accumulators in both
+//         CTAs; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.  (M maps: 64-row boxes.)
+constexpr int kFwdStages2 = 8;
+constexpr int kFwdStageBytes2 = 2 * kGT * 64 + 2 * (kGN / 2) * 64;       // X1, X2 [128 rows], M1, M2 halves [64 rows]
+static_assert(kFwdStages2 * kFwdStageBytes2 == kFwdStages * kFwdStageBytes, "both layouts use the same shared memory");
+
+template <int NLIN, int MODE>
 __global__ void __launch_bounds__(kGThreads, 1)
 tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
                    const __grid_constant__ CUtensorMap mapM1, const __grid_constant__ CUtensorMap mapM2, GemmFwdArgs a)
 {
-    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    constexpr bool PAIR = MODE == 1;
+    constexpr bool DUO = MODE == 2;
+    constexpr int kStages = DUO ? kFwdStages2 : kFwdStages;
+    constexpr int kStageBytes = DUO ? kFwdStageBytes2 : kFwdStageBytes;
+    const uint32_t crank = MODE ? cluster_ctarank() : 0u;
     // work items of this CTA: w = first, first + stride, ...; item -> (time tile, column block)
-    const int64_t w_first = PAIR ? blockIdx.x / 2 : blockIdx.x;
-    const int64_t w_stride = PAIR ? gridDim.x / 2 : gridDim.x;
-    const int cbw = PAIR ? a.ncb / 2 : a.ncb;                    // column-block work items per time tile
-    const int64_t nwork = a.ntt * cbw;
-    auto tile_tt = [&](int64_t w) { return w / cbw; };
+    const int64_t w_first = MODE ? blockIdx.x / 2 : blockIdx.x;
+    const int64_t w_stride = MODE ? gridDim.x / 2 : gridDim.x;
+    const int cbw = PAIR ? a.ncb / 2 : a.ncb;                    // column-block work items per time tile (pair)
+    const int64_t nwork = (DUO ? (a.ntt + 1) / 2 : a.ntt) * cbw;
+    auto tile_tt = [&](int64_t w) { return DUO ? 2 * (w / cbw) + crank : w / cbw; };
     auto tile_cb = [&](int64_t w) { return PAIR ? 2 * (int)(w % cbw) + (int)crank : (int)(w % cbw); };
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kFwdStages * kFwdStageBytes);
-    uint64_t* bar_full = bars;                       // [6]
-    uint64_t* bar_empty = bars + kFwdStages;         // [6]
-    uint64_t* bar_acc_full = bars + 2 * kFwdStages;  // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* bar_full = bars;                       // [kStages]
+    uint64_t* bar_empty = bars + kStages;            // [kStages]
+    uint64_t* bar_acc_full = bars + 2 * kStages;     // [2]
     uint64_t* bar_acc_empty = bar_acc_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kFwdStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], PAIR ? 2 : 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], kGEpiWarps); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], PAIR ? 2 : 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_acc_full[i], 1); mbar_init(&bar_acc_empty[i], DUO ? 2 * kGEpiWarps : kGEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (DUO) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();            // the peer's barriers are initialised before anything is multicast into them
+    if (MODE) cluster_sync_all();            // the peer's barriers and TMEM exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -188,33 +206,44 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
         if (lane == 0) {
             uint32_t chunk = 0;
             for (int64_t w = w_first; w < nwork; w += w_stride) {
-                const int row0 = (int)(tile_tt(w) * kGT);
+                const int row0 = (a.debug & 2) ? 0 : (int)(tile_tt(w) * kGT);
                 const int col0 = tile_cb(w) * kGN;
                 for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
-                    const int s = chunk % kFwdStages;
-                    mbar_wait(&bar_empty[s], ((chunk / kFwdStages) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[s], kFwdStageBytes);
-                    unsigned char* st = smem + s * kFwdStageBytes;
-                    if (PAIR) {                  // this CTA's half of the rows, into both CTAs
-                        const int half = (int)crank * (kGT / 2);
-                        tma_load_2d_multicast(st + half * 64, &mapX1, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
-                        tma_load_2d_multicast(st + kGT * 64 + half * 64, &mapX2, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
+                    const int s = chunk % kStages;
+                    mbar_wait(&bar_empty[s], ((chunk / kStages) & 1) ^ 1);
+                    unsigned char* st = smem + s * kStageBytes;
+                    if constexpr (DUO) {         // every transaction of the pair lands on the leader's barrier
+                        if (crank == 0) mbar_arrive_expect_tx(&bar_full[s], 2 * kStageBytes);
+                        const uint32_t lead_full = mapa_u32(&bar_full[s], 0);
+                        const int colh = col0 + (int)crank * (kGN / 2);
+                        tma_load_2d_pair(st, &mapX1, lead_full, kc * 32, row0);
+                        tma_load_2d_pair(st + kGT * 64, &mapX2, lead_full, kc * 32, row0);
+                        tma_load_2d_pair(st + 2 * kGT * 64, &mapM1, lead_full, kc * 32, colh);
+                        tma_load_2d_pair(st + 2 * kGT * 64 + (kGN / 2) * 64, &mapM2, lead_full, kc * 32, colh);
                     } else {
-                        tma_load_2d(st, &mapX1, &bar_full[s], kc * 32, row0);
-                        tma_load_2d(st + kGT * 64, &mapX2, &bar_full[s], kc * 32, row0);
+                        mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+                        if (PAIR) {              // this CTA's half of the rows, into both CTAs
+                            const int half = (int)crank * (kGT / 2);
+                            tma_load_2d_multicast(st + half * 64, &mapX1, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
+                            tma_load_2d_multicast(st + kGT * 64 + half * 64, &mapX2, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
+                        } else {
+                            tma_load_2d(st, &mapX1, &bar_full[s], kc * 32, row0);
+                            tma_load_2d(st + kGT * 64, &mapX2, &bar_full[s], kc * 32, row0);
+                        }
+                        tma_load_2d(st + 2 * kGT * 64, &mapM1, &bar_full[s], kc * 32, col0);
+                        tma_load_2d(st + 3 * kGT * 64, &mapM2, &bar_full[s], kc * 32, col0);
                     }
-                    tma_load_2d(st + 2 * kGT * 64, &mapM1, &bar_full[s], kc * 32, col0);
-                    tma_load_2d(st + 3 * kGT * 64, &mapM2, &bar_full[s], kc * 32, col0);
                 }
             }
         }
     } else if (warp == kGMmaWarp) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        if (lane == 0 && (!DUO || crank == 0)) {
             // acc0 = x1 m1 and acc1 = x1 m2 + x2 m1 sit in adjacent TMEM columns and M1 | M2 are adjacent in the
             // stage, so x1 multiplies both in ONE N=256 MMA: x1 is read from shared memory once, not twice
             constexpr uint32_t idesc = umma_idesc(kGT, kGN, 0, 0);
             constexpr uint32_t idesc2 = umma_idesc(kGT, 2 * kGN, 0, 0);
+            constexpr uint32_t idesc_duo = umma_idesc(2 * kGT, kGN, 0, 0);          // 256 bins (two CTAs) x 128 neurons
             // FP32 accumulation in TMEM loses ~1 ulp of the running sum per MMA step, and the loss does not
             // average out: over K = 10^4 features the activation error reached 2e-6 relative.  So the K loop
             // is cut into segments of `seg` chunks that alternate between the two TMEM buffers; the epilogue
@@ -230,23 +259,40 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                         mbar_wait(&bar_acc_empty[ab], ((sgc >> 1) & 1) ^ 1);
                         tc_fence_after();
                     }
-                    const int s = chunk % kFwdStages;
-                    mbar_wait(&bar_full[s], (chunk / kFwdStages) & 1);
+                    const int s = chunk % kStages;
+                    mbar_wait(&bar_full[s], (chunk / kStages) & 1);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + s * kFwdStageBytes);
+                    const uint32_t base = smem_u32(smem + s * kStageBytes);
                     const uint64_t dx1 = umma_desc(base, 16, 512), dx2 = umma_desc(base + kGT * 64, 16, 512);
-                    const uint64_t dm1 = umma_desc(base + 2 * kGT * 64, 16, 512);   // rows 128..255 of this tile are M2
+                    const uint64_t dm1 = umma_desc(base + 2 * kGT * 64, 16, 512);   // MODE 0/1: rows 128..255 of this tile are M2
+                    if constexpr (DUO) {
+                        const uint64_t dm2 = umma_desc(base + 2 * kGT * 64 + (kGN / 2) * 64, 16, 512);
 #pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        const uint32_t acc = (in_seg | ks) ? 1u : ((a.debug & 2) && kc ? 1u : 0u);   // debug 2: never restart
-                        umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc2, acc);    // X1 [M1 | M2]
-                        umma_f16(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc, 1u);      // X2 M1
-                    }
-                    if (PAIR) umma_commit_multicast(&bar_empty[s], (uint16_t)3);
-                    else umma_commit(&bar_empty[s]);
-                    if (in_seg == a.seg - 1 || kc == a.nkc - 1) {
-                        umma_commit(&bar_acc_full[ab]);
-                        ++sgc;
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint32_t acc = (in_seg | ks) ? 1u : 0u;
+                            umma_f16_pair(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc_duo, acc);   // X1 M1
+                            umma_f16_pair(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc_duo, acc);   // X2 M1
+                            umma_f16_pair(t_b, dx1 + 2 * ks, dm2 + 2 * ks, idesc_duo, 1u);    // X1 M2
+                        }
+                        umma_commit_pair(&bar_empty[s], (uint16_t)3);
+                        if (in_seg == a.seg - 1 || kc == a.nkc - 1) {
+                            umma_commit_pair(&bar_acc_full[ab], (uint16_t)3);
+                            ++sgc;
+                        }
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            if (a.debug & 1) break;
+                            const uint32_t acc = (in_seg | ks) ? 1u : 0u;
+                            umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc2, acc);    // X1 [M1 | M2]
+                            umma_f16(t_b, dx2 + 2 * ks, dm1 + 2 * ks, idesc, 1u);      // X2 M1
+                        }
+                        if (PAIR) umma_commit_multicast(&bar_empty[s], (uint16_t)3);
+                        else umma_commit(&bar_empty[s]);
+                        if (in_seg == a.seg - 1 || kc == a.nkc - 1) {
+                            umma_commit(&bar_acc_full[ab]);
+                            ++sgc;
+                        }
                     }
                 }
             }
@@ -289,12 +335,6 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                 const int ab = sgc & 1;
                 mbar_wait(&bar_acc_full[ab], (sgc >> 1) & 1);
                 tc_fence_after();
-                if ((a.debug & 1) && sg != nseg - 1) {                   // experiment: intermediate drains without TMEM reads
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
-                    continue;
-                }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     float da[16], db[16];
@@ -306,7 +346,10 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_acc_empty[ab]);
+                if (lane == 0) {
+                    if (DUO) mbar_arrive_cluster(mapa_u32(&bar_acc_empty[ab], 0));     // the leader's barrier
+                    else mbar_arrive(&bar_acc_empty[ab]);
+                }
             }
             __half* r1row = a.R + (t < a.T ? t : 0) * a.Npr + col0;
             __half* r2row = r1row + a.plane;
@@ -319,7 +362,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     const int cc = sub * 8 + c;
                     const float ism = __shfl_sync(0xffffffffu, ism_l, cc), bc = __shfl_sync(0xffffffffu, bias_l, cc);
                     float term = 0.f, r = 0.f;
-                    if (col0 + cc < a.ncols) {                                       // warp-uniform
+                    if (col0 + cc < a.ncols && !(a.debug & 4)) {                     // warp-uniform
                         const float x = fmaf(act[cc], ism, bc);
                         poisson_terms<NLIN>(x, (float)((sp[cc >> 2] >> ((cc & 3) * 8)) & 0xffu), a.dt, term, r);
                         term *= lv;
@@ -354,9 +397,10 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();            // neither CTA leaves while the other may still signal its barriers
+    if (MODE) cluster_sync_all();            // neither CTA leaves while the other may still signal its barriers / TMEM
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (DUO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -551,13 +595,17 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if ((rc = ensure((void**)&g.Mp, &g.Mp_elems, (size_t)2 * Npr * Kp, sizeof(__half)))) return rc;
     if ((rc = ensure((void**)&g.colpar, &g.colpar_elems, (size_t)2 * Npr, sizeof(float)))) return rc;
     if ((rc = ensure((void**)&g.R, &g.R_elems, (size_t)2 * a.T * Npr, sizeof(__half)))) return rc;
-    // Optional: column blocks in pairs (clusters of two CTAs, X tile multicast).  Measured at C3: L2 bytes 28.3 -> 25.4 GB
-    // but crossbar-to-SM bytes 20.9 -> 26.1 GB and the same 2.44 ms: what limits the kernel is the ~30 B/clk each SM can
-    // ingest, which multicast does not reduce.  Off unless PYGLM_GEMM_PAIR=1.
-    bool pair = false;
-    if (const char* env = getenv("PYGLM_GEMM_PAIR")) pair = atoi(env) != 0 && (ncb % 2 == 0) && ws.num_sms >= 2;
-    int nctas = (int)std::min<int64_t>(pair ? ntt * ncb : ntt * ncb, ws.num_sms);
-    if (pair) nctas &= ~1;
+    // mode 0 (default): single CTAs.  Modes 1 (X multicast over a cluster of two) and 2 (cta_group::2 pairs) are
+    // parity-tested experiments selected with PYGLM_GEMM_MODE; measured at C3 (forward only): 2.47 / 2.6 / 2.75 ms.
+    // With the MMAs removed the TMA pipeline alone takes 1.7 ms (20 GB at the ~12 TB/s L2-to-SM cap) in mode 0 and
+    // 2.8 ms in mode 2: the pair's cross-SM barrier traffic costs more than its 25 % fewer bytes save.
+    int mode = 0;
+    if (const char* env = getenv("PYGLM_GEMM_MODE")) mode = atoi(env);
+    if (mode == 1 && (ncb % 2 != 0)) mode = 0;
+    if (mode != 0 && ws.num_sms < 2) mode = 0;
+    const int64_t nwork = mode == 2 ? ceil_div(ntt, 2) * ncb * 2 : ntt * ncb;            // in CTAs
+    int nctas = (int)std::min<int64_t>(nwork, ws.num_sms);
+    if (mode) nctas &= ~1;
     if ((rc = ensure((void**)&g.part, &g.part_elems, (size_t)nctas * 4 * Npr * 2, sizeof(double)))) return rc;
 
     PYGLM_CUDA(cudaMemsetAsync(g.part, 0, (size_t)nctas * 4 * Npr * 2 * sizeof(double), stream));
@@ -584,9 +632,13 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
         if ((rc = tc_make_map_2d(&g.mapX64[1], ws.X2, ws.ldp, a.T, ws.ldp, 32, kBwdRows))) return rc;
         g.mapX64_ready = true;
     }
-    if (pair) {
-        auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, true>
-                                                : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, true>;
+    if (mode) {
+        CUtensorMap mM1h, mM2h;                                   // 64-column boxes of the weight planes (mode 2)
+        if ((rc = tc_make_map_2d(&mM1h, g.Mp, Kp, Npr, Kp, 32, kGN / 2))) return rc;
+        if ((rc = tc_make_map_2d(&mM2h, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, 32, kGN / 2))) return rc;
+        void (*kf)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, GemmFwdArgs);
+        if (mode == 2) kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, 2> : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, 2>;
+        else kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, 1> : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, 1>;
         PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)nctas); cfg.blockDim = dim3(kGThreads); cfg.dynamicSmemBytes = smem_f; cfg.stream = stream;
@@ -594,10 +646,11 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
         cfg.attrs = &attr; cfg.numAttrs = 1;
-        PYGLM_CUDA(cudaLaunchKernelEx(&cfg, kf, g.mapX64[0], g.mapX64[1], mM1, mM2, f));
+        if (mode == 2) PYGLM_CUDA(cudaLaunchKernelEx(&cfg, kf, xmaps[0], xmaps[1], mM1h, mM2h, f));
+        else PYGLM_CUDA(cudaLaunchKernelEx(&cfg, kf, g.mapX64[0], g.mapX64[1], mM1, mM2, f));
     } else {
-        auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, false>
-                                                : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, false>;
+        auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, 0>
+                                                : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, 0>;
         PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
         kf<<<nctas, kGThreads, smem_f, stream>>>(xmaps[0], xmaps[1], mM1, mM2, f);
     }
