@@ -37,7 +37,7 @@ constexpr int kGTmaWarp = kGEpiWarps;
 constexpr int kGMmaWarp = kGEpiWarps + 1;
 constexpr int kGThreads = 32 * (kGEpiWarps + 2);
 constexpr int kGColsPerWarp = kGN / 4;       // 32 columns per epilogue warp (4 column groups x 4 lane quarters)
-constexpr int kFwdStages = 6;
+constexpr int kFwdStages = 7;                // 7 x 32 KB + barriers = 225 KB of the 227 KB a CTA may use
 constexpr int kFwdSegChunks = 8;             // forward: 256 features per TMEM accumulation segment ...
 constexpr int kFwdSingleSegmentChunks = 48;  // ... when there are more than 1536 features
 constexpr int kFwdStageBytes = 4 * kGT * 64; // X1, X2, M1, M2 chunks of [128 rows][32 halves]
@@ -150,9 +150,9 @@ struct GemmFwdArgs {
 //         for the same outputs: the forward kernel is bound by what an SM can ingest.  All TMA transactions signal
 //         the leader's full barrier; the leader's commits release the stages and publish the accumulators in both
 //         CTAs; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.  (M maps: 64-row boxes.)
-constexpr int kFwdStages2 = 8;
+constexpr int kFwdStages2 = 9;
 constexpr int kFwdStageBytes2 = 2 * kGT * 64 + 2 * (kGN / 2) * 64;       // X1, X2 [128 rows], M1, M2 halves [64 rows]
-static_assert(kFwdStages2 * kFwdStageBytes2 == kFwdStages * kFwdStageBytes, "both layouts use the same shared memory");
+static_assert(kFwdStages2 * kFwdStageBytes2 <= kFwdStages * kFwdStageBytes, "the pair layout fits in the same shared memory");
 
 template <int NLIN, int MODE>
 __global__ void __launch_bounds__(kGThreads, 1)
@@ -204,17 +204,17 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     if (warp == kGTmaWarp) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            uint32_t chunk = 0;
+            uint32_t s = 0, ph = 1;              // stage and the parity its empty barrier is waited on
+            const uint32_t lead_full0 = DUO ? mapa_u32(&bar_full[0], 0) : 0u;
             for (int64_t w = w_first; w < nwork; w += w_stride) {
                 const int row0 = (a.debug & 2) ? 0 : (int)(tile_tt(w) * kGT);
                 const int col0 = tile_cb(w) * kGN;
-                for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
-                    const int s = chunk % kStages;
-                    mbar_wait(&bar_empty[s], ((chunk / kStages) & 1) ^ 1);
+                for (int kc = 0; kc < a.nkc; ++kc) {
+                    mbar_wait(&bar_empty[s], ph);
                     unsigned char* st = smem + s * kStageBytes;
                     if constexpr (DUO) {         // every transaction of the pair lands on the leader's barrier
                         if (crank == 0) mbar_arrive_expect_tx(&bar_full[s], 2 * kStageBytes);
-                        const uint32_t lead_full = mapa_u32(&bar_full[s], 0);
+                        const uint32_t lead_full = lead_full0 + s * 8;
                         const int colh = col0 + (int)crank * (kGN / 2);
                         tma_load_2d_pair(st, &mapX1, lead_full, kc * 32, row0);
                         tma_load_2d_pair(st + kGT * 64, &mapX2, lead_full, kc * 32, row0);
@@ -233,6 +233,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                         tma_load_2d(st + 2 * kGT * 64, &mapM1, &bar_full[s], kc * 32, col0);
                         tma_load_2d(st + 3 * kGT * 64, &mapM2, &bar_full[s], kc * 32, col0);
                     }
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -249,24 +250,27 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
             // is cut into segments of `seg` chunks that alternate between the two TMEM buffers; the epilogue
             // warps drain every finished segment into FP32 registers (round-to-nearest adds) while the next
             // one accumulates.  Short running sums are small, and so are their rounding losses.
-            uint32_t chunk = 0, sgc = 0;
+            // this one thread feeds the tensor pipe, a K chunk every ~400 cycles: the loop carries its stage / phase /
+            // segment counters and descriptor bases instead of recomputing them with divisions
+            uint32_t sgc = 0, s = 0, ph = 0;
+            const uint64_t d_stage0 = umma_desc(smem_u32(smem), 16, 512);
             for (int64_t w = w_first; w < nwork; w += w_stride) {
-                for (int kc = 0; kc < a.nkc; ++kc, ++chunk) {
+                int in_seg = 0;
+                for (int kc = 0; kc < a.nkc; ++kc) {
                     const int ab = sgc & 1;
-                    const int in_seg = kc % a.seg;
                     const uint32_t t_a = tmem_base + ab * 256, t_b = t_a + 128;
                     if (in_seg == 0) {
                         mbar_wait(&bar_acc_empty[ab], ((sgc >> 1) & 1) ^ 1);
                         tc_fence_after();
                     }
-                    const int s = chunk % kStages;
-                    mbar_wait(&bar_full[s], (chunk / kStages) & 1);
+                    mbar_wait(&bar_full[s], ph);
                     tc_fence_after();
-                    const uint32_t base = smem_u32(smem + s * kStageBytes);
-                    const uint64_t dx1 = umma_desc(base, 16, 512), dx2 = umma_desc(base + kGT * 64, 16, 512);
-                    const uint64_t dm1 = umma_desc(base + 2 * kGT * 64, 16, 512);   // MODE 0/1: rows 128..255 of this tile are M2
+                    const uint64_t dx1 = d_stage0 + (uint64_t)(s * (kStageBytes >> 4));
+                    const uint64_t dx2 = dx1 + ((kGT * 64) >> 4);
+                    const uint64_t dm1 = dx1 + ((2 * kGT * 64) >> 4);               // MODE 0/1: rows 128..255 of this tile are M2
+                    const bool seg_end = in_seg == a.seg - 1 || kc == a.nkc - 1;
                     if constexpr (DUO) {
-                        const uint64_t dm2 = umma_desc(base + 2 * kGT * 64 + (kGN / 2) * 64, 16, 512);
+                        const uint64_t dm2 = dm1 + (((kGN / 2) * 64) >> 4);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
                             const uint32_t acc = (in_seg | ks) ? 1u : 0u;
@@ -275,10 +279,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                             umma_f16_pair(t_b, dx1 + 2 * ks, dm2 + 2 * ks, idesc_duo, 1u);    // X1 M2
                         }
                         umma_commit_pair(&bar_empty[s], (uint16_t)3);
-                        if (in_seg == a.seg - 1 || kc == a.nkc - 1) {
-                            umma_commit_pair(&bar_acc_full[ab], (uint16_t)3);
-                            ++sgc;
-                        }
+                        if (seg_end) umma_commit_pair(&bar_acc_full[ab], (uint16_t)3);
                     } else {
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
@@ -289,11 +290,10 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                         }
                         if (PAIR) umma_commit_multicast(&bar_empty[s], (uint16_t)3);
                         else umma_commit(&bar_empty[s]);
-                        if (in_seg == a.seg - 1 || kc == a.nkc - 1) {
-                            umma_commit(&bar_acc_full[ab]);
-                            ++sgc;
-                        }
+                        if (seg_end) umma_commit(&bar_acc_full[ab]);
                     }
+                    if (seg_end) { ++sgc; in_seg = 0; } else ++in_seg;
+                    if (++s == kStages) { s = 0; ph ^= 1; }
                 }
             }
         }
