@@ -352,8 +352,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 const uint64_t dr0 = umma_desc(sR1, kRBytes, 512);                // LBO steps r1 -> r2
                 for (int mt = 0; mt < ((a.debug & 2) ? 0 : a.nmt); ++mt) {
                     const uint32_t t_g = tmem_base + kGradBase + gb * kGradBuf + mt * kFwdCols;
-                    const uint64_t dx1_0 = umma_desc(sX1 + mt * 4 * kChunkBytes, kChunkBytes, 512);   // 4 chunks per tile
-                    const uint64_t dx2_0 = umma_desc(sX2 + mt * 4 * kChunkBytes, kChunkBytes, 512);
+                    // Tile 0 spans chunks 0..3 (LBO = one chunk).  Tile 1 has a single chunk (features 128..159): with
+                    // LBO = 0 all four 32-row groups of its M = 128 alias that chunk, so every TMEM lane quarter holds
+                    // a copy of the same 32 gradient rows and the epilogue warps can take turns folding them.
+                    const uint32_t lbo = mt ? 0u : (uint32_t)kChunkBytes;
+                    const uint64_t dx1_0 = umma_desc(sX1 + mt * 4 * kChunkBytes, lbo, 512);
+                    const uint64_t dx2_0 = umma_desc(sX2 + mt * 4 * kChunkBytes, lbo, 512);
 #pragma unroll
                     for (int ks = 0; ks < kTileT / 16; ++ks) {                    // 16 bins per step
                         const uint32_t acc = ks ? 1u : 0u;
@@ -381,12 +385,12 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
         const float2* cpar = reinterpret_cast<const float2*>(sPar);     // (1/sm, bias) per column
         double* gp = a.part + (int64_t)blockIdx.x * ((int64_t)a.nmt * 128 * kNcol + 2 * kNcol);
-        const int NBreal = a.nfeat;
         double gacc[kColsPerWarp], gacc1[kColsPerWarp];  // gradient tiles 0 / 1 (features 0..127 / 128..): FP64 in registers
 #pragma unroll
         for (int c = 0; c < kColsPerWarp; ++c) { gacc[c] = 0.0; gacc1[c] = 0.0; }
-        // fold tile j's TMEM gradient block into FP64; tile 1 (features >= 128, at most 32 real rows on this
-        // path) is read only by the warps that own real rows
+        // fold tile j's TMEM gradient block into FP64.  Gradient tile 1 (features >= 128: one 32-feature chunk,
+        // replicated into all four lane quarters by the issuer) is folded by quarter j % 4 only, so the extra work
+        // rotates over the warps instead of doubling the load of quarter 0; tc_final_kernel adds the four copies.
         auto fold_gradient = [&](int j) {
             float g0[kColsPerWarp], g1[kColsPerWarp], g2[kColsPerWarp];
             const int gb = j & 1;
@@ -397,7 +401,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             if (trf) a.trace[1536 + j * 4 + 1] = clock64();
             tc_fence_after();
             if (!(a.debug & 8)) {
-                const bool tile1 = a.nmt > 1 && 128 + q * 32 < NBreal;         // warp-uniform: rows with real features
+                const bool tile1 = a.nmt > 1 && (j & 3) == q;                  // warp-uniform
                 tmem_ld<kColsPerWarp>(t_g + 0, g0);
                 tmem_ld<kColsPerWarp>(t_g + 32, g1);
                 tmem_ld<kColsPerWarp>(t_g + 64, g2);
@@ -606,10 +610,13 @@ tc_final_kernel(const double* __restrict__ part, int nctas, int nmt, int N, int 
     const int nl = threadIdx.x & 31, slice = threadIdx.x >> 5;
     const bool tail = blockIdx.x == NB;                      // the ll / g_bias block
     const int64_t off = tail ? (int64_t)nmt * 128 * kNcol : (int64_t)blockIdx.x * kNcol;
+    const bool rep = !tail && blockIdx.x >= 128;             // gradient tile 1: four lane-quarter copies, 32 rows apart
     double s0 = 0.0, s1 = 0.0;
     for (int c = slice; c < nctas; c += kFinalSlices) {
-        s0 += part[c * per_cta + off + nl];
-        if (tail) s1 += part[c * per_cta + off + kNcol + nl];
+        const double* pc = part + c * per_cta + off + nl;
+        s0 += pc[0];
+        if (rep) s0 += pc[32 * kNcol] + pc[64 * kNcol] + pc[96 * kNcol];
+        if (tail) s1 += pc[kNcol];
     }
     sh[slice][nl] = s0;
     sh[slice][kNcol + nl] = s1;
