@@ -313,7 +313,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
             // column parameters: lane l holds column col0 + l
             const float ism_l = a.colpar[col0 + lane], bias_l = a.colpar[a.Npr + col0 + lane];
             uint32_t sp[8];
-            if (t < a.T) {
+            if (t < a.T && col0 < a.ncols) {     // padded column groups: nothing to read (Sp has N rounded up to 32, +32)
                 const uint4* src = reinterpret_cast<const uint4*>(a.Sp + t * a.Nps + a.n_lo + col0);
                 if (((a.n_lo + col0) & 15) == 0) {
                     const uint4 v0 = src[0], v1 = src[1];
