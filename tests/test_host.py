@@ -227,3 +227,20 @@ def test_basis_stimulus_component_matches_oracle():
     popn.set_glm_param_vector(x['glms'][0], vec * 2)
     assert np.array_equal(x['glms'][0]['bkgd']['w_stim'], vec[1:7] * 2)
     assert popn.glm.stim_weights(x).shape == (2, 6)
+
+
+def test_make_synth_dataset_packages_the_reference_data_dict():
+    """generate_synth_data.py:56-135 without the files: model, prior draw (re-drawn until stable), simulation and
+    the data dict the rest of the reference consumes."""
+    from theano_pyglm_b200.utils.synth import make_synth_dataset
+    model, popn, x_true, data = make_synth_dataset('standard_glm', N=3, T_stop=2.0, seed=4)
+    assert set(['S', 'X', 'N', 'dt', 'T', 'stim', 'dt_stim', 'vars']) <= set(data)
+    assert data['S'].shape == (2000, 3) and data['X'].shape == (2000, 3) and data['N'] == 3 and data['T'] == 2.0
+    assert data['vars'] is x_true and data['stim'].shape == (20, 1)
+    assert np.all(data['S'] == np.floor(data['S'])) and data['S'].min() >= 0 and data['S'].max() <= 10
+    assert check_stability(model, x_true, 3)
+    # the recorded activation reproduces the firing rate from bias + filtered spikes (generate_synth_data.py:124-129)
+    fS = orc.convolve_with_basis(data['S'], popn.glm.imp_model.ibasis)
+    for n in range(3):
+        act = x_true['glms'][n]['bias']['bias'][0] + orc.impulse_current(fS, x_true['glms'][n]['imp']['w_ir'].reshape(3, -1)).sum(axis=1)
+        assert np.allclose(act, data['X'][:, n], atol=1e-8)
