@@ -498,3 +498,27 @@ def test_gibbs_delta_ll_ragged(eng, case):
         assert abs(out[q] - ref) <= tol, (q, out[q], ref)
     ds.gibbs_end()
     ds.close()
+
+
+def test_host_entry_graph_replay_sees_fresh_parameters(eng):
+    """pyglm_b200_ll_grad replays a captured CUDA graph from its third call with the same signature on: every call
+    must still read the caller's current parameter values, survive interleaved calls that move engine buffers,
+    and match the oracle."""
+    p = make_problem(4000, 27, 5, network=True, seed=8)
+    fS = orc.convolve_with_basis_direct(p['S'].astype(np.float64), p['ibasis'])
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+    rng = np.random.default_rng(0)
+    for it in range(7):
+        bias = p['bias'] + 0.05 * rng.standard_normal(27)
+        w = p['w'] * (1.0 + 0.1 * it)
+        W = p['W'] + 0.01 * it
+        ll, gb, gw = orc.population_ll_grad(fS, p['S'], p['dt'], bias, w, p['A'], W, orc.NLIN_SOFTPLUS)
+        ll_g, gb_g, gw_g = ds.ll_grad(bias, w, p['A'], W, nlin="explinear", path="tc")
+        assert np.max(np.abs(ll_g - ll) / np.abs(ll)) < LL_RTOL, it
+        assert rel_err(gb_g, gb) < GRAD_RTOL and rel_err(gw_g, gw.reshape(27, -1)) < GRAD_RTOL, it
+        if it == 3:                                 # other entry points grow workspaces between replays
+            ds.firing_rate(bias, w, p['A'], W)
+            ds.ll_grad(bias, w, p['A'], W, nlin="explinear", path="fp64", n_lo=3, n_hi=20)
+        if it == 5:
+            assert np.allclose(ds.ll(bias, w, p['A'], W, nlin="explinear", path="tc"), ll_g, rtol=1e-12)
+    ds.close()

@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <atomic>
 #include <new>
 #include <vector>
 
@@ -11,6 +12,10 @@
 namespace pyglm {
 
 static thread_local char g_err[1024] = "";
+
+static std::atomic<unsigned long long> g_alloc_epoch{0};
+void note_allocation() { g_alloc_epoch.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long allocation_epoch() { return g_alloc_epoch.load(std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...)
 {
@@ -29,6 +34,7 @@ struct DevBuf {
         if (count <= n) return PYGLM_B200_OK;
         if (p) cudaFree(p);
         p = nullptr; n = 0;
+        note_allocation();
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
         if (e != cudaSuccess) {
             set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
@@ -65,6 +71,19 @@ struct pyglm_b200_dataset {
     DevBuf<double> p_bias, p_w, p_W, M, Weff, Rres, llp, gbp, Gp, o_ll, o_gb, o_gw, lam;
     DevBuf<int8_t> p_A;
     TcWorkspace tc;
+
+    // host-buffer entry point (pyglm_b200_ll_grad): pinned staging + a CUDA graph of the whole call, replayed while the
+    // call signature stays the same (an optimiser calls it hundreds of times with new parameter values only)
+    struct HostCall {
+        double *bias = nullptr, *w = nullptr, *W = nullptr, *ll = nullptr, *gb = nullptr, *gw = nullptr;
+        int8_t* A = nullptr;
+        size_t cap_w = 0, cap_gw = 0;                 // doubles allocated for w / gw
+        int key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};     // nlin, n_lo, n_hi, path, hasA, hasW, want_gb, want_gw
+        int seen = 0;                                 // calls with this key so far
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long epoch = 0;                 // allocation_epoch() when `exec` was captured
+        bool disabled = false;                        // capture failed once: plain stream calls from then on
+    } hc;
 
     // Gibbs state
     bool gibbs_active = false;
@@ -200,6 +219,9 @@ int pyglm_b200_dataset_destroy(pyglm_b200_dataset* ds)
     ds->partial.release(); ds->g_wcand.release(); ds->g_out.release(); ds->g_wnew.release();
     ds->g_anew.release(); ds->g_cols.release(); ds->g_pres.release();
     ds->tc.release();
+    if (ds->hc.exec) cudaGraphExecDestroy(ds->hc.exec);
+    cudaFreeHost(ds->hc.bias); cudaFreeHost(ds->hc.w); cudaFreeHost(ds->hc.W); cudaFreeHost(ds->hc.A);
+    cudaFreeHost(ds->hc.ll); cudaFreeHost(ds->hc.gb); cudaFreeHost(ds->hc.gw);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
     return PYGLM_B200_OK;
@@ -367,6 +389,27 @@ static int stage_params(pyglm_b200_dataset* ds, const double* bias, const double
     return PYGLM_B200_OK;
 }
 
+// everything one host-buffer call enqueues: parameter upload from the pinned staging, the evaluation, result download
+static int enqueue_host_call(pyglm_b200_dataset* ds, bool hasA, bool hasW, int nlin, int n_lo, int n_hi, int path,
+                             bool want_gb, bool want_gw, cudaStream_t st)
+{
+    auto& h = ds->hc;
+    const size_t N = ds->N, NF = (size_t)ds->NF();
+    const int ncols = n_hi - n_lo;
+    const bool grad = want_gb || want_gw;
+    PYGLM_CUDA(cudaMemcpyAsync(ds->p_bias.p, h.bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->p_w.p, h.w, N * NF * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (hasA) PYGLM_CUDA(cudaMemcpyAsync(ds->p_A.p, h.A, N * N, cudaMemcpyHostToDevice, st));
+    if (hasW) PYGLM_CUDA(cudaMemcpyAsync(ds->p_W.p, h.W, N * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, hasA ? ds->p_A.p : nullptr, hasW ? ds->p_W.p : nullptr,
+                         nlin, n_lo, n_hi, path, ds->o_ll.p, grad ? ds->o_gb.p : nullptr, grad ? ds->o_gw.p : nullptr,
+                         nullptr, nullptr, st));
+    PYGLM_CUDA(cudaMemcpyAsync(h.ll, ds->o_ll.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_gb) PYGLM_CUDA(cudaMemcpyAsync(h.gb, ds->o_gb.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (want_gw) PYGLM_CUDA(cudaMemcpyAsync(h.gw, ds->o_gw.p, (size_t)ncols * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return PYGLM_B200_OK;
+}
+
 int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
                        const double* bias, const double* w, const int8_t* A, const double* W,
                        int32_t nlin, int32_t n_lo, int32_t n_hi, int32_t path,
@@ -374,22 +417,76 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
 {
     DS_GUARD(ds);
     PYGLM_REQUIRE(out_ll != nullptr, "ll_grad: out_ll is null");
+    PYGLM_REQUIRE(bias && w, "null bias / w");
     PYGLM_REQUIRE(0 <= n_lo && n_lo <= n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
     const int ncols = n_hi - n_lo;
     if (ncols == 0) return PYGLM_B200_OK;
-    const size_t NB = (size_t)ds->NF();
+    const size_t N = ds->N, NF = (size_t)ds->NF();
     cudaStream_t st = ds->stream;
-    TRY(stage_params(ds, bias, w, A, W, ds->p_bias, ds->p_w, ds->p_A, ds->p_W, st));
-    const bool grad = out_g_bias != nullptr || out_g_w != nullptr;
-    TRY(ds->o_ll.ensure(ncols));
-    if (grad) { TRY(ds->o_gb.ensure(ncols)); TRY(ds->o_gw.ensure((size_t)ncols * NB)); }
-    TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, A ? ds->p_A.p : nullptr, W ? ds->p_W.p : nullptr,
-                         nlin, n_lo, n_hi, path, ds->o_ll.p, grad ? ds->o_gb.p : nullptr, grad ? ds->o_gw.p : nullptr,
-                         nullptr, nullptr, st));
-    PYGLM_CUDA(cudaMemcpyAsync(out_ll, ds->o_ll.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (out_g_bias) PYGLM_CUDA(cudaMemcpyAsync(out_g_bias, ds->o_gb.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (out_g_w) PYGLM_CUDA(cudaMemcpyAsync(out_g_w, ds->o_gw.p, (size_t)ncols * NB * sizeof(double), cudaMemcpyDeviceToHost, st));
+    auto& h = ds->hc;
+    const bool want_gb = out_g_bias != nullptr, want_gw = out_g_w != nullptr, grad = want_gb || want_gw;
+
+    // device and pinned staging (grow only)
+    TRY(ds->p_bias.ensure(N)); TRY(ds->p_w.ensure(N * NF));
+    if (A) TRY(ds->p_A.ensure(N * N));
+    if (W) TRY(ds->p_W.ensure(N * N));
+    TRY(ds->o_ll.ensure(ds->N));
+    if (grad) { TRY(ds->o_gb.ensure(ds->N)); TRY(ds->o_gw.ensure(N * NF)); }
+    if (!h.bias) {
+        PYGLM_CUDA(cudaMallocHost(&h.bias, N * sizeof(double)));
+        PYGLM_CUDA(cudaMallocHost(&h.ll, N * sizeof(double)));
+        PYGLM_CUDA(cudaMallocHost(&h.gb, N * sizeof(double)));
+        PYGLM_CUDA(cudaMallocHost(&h.W, N * N * sizeof(double)));
+        PYGLM_CUDA(cudaMallocHost(&h.A, N * N));
+        PYGLM_CUDA(cudaMallocHost(&h.w, N * NF * sizeof(double)));
+        PYGLM_CUDA(cudaMallocHost(&h.gw, N * NF * sizeof(double)));
+    }
+    memcpy(h.bias, bias, N * sizeof(double));
+    memcpy(h.w, w, N * NF * sizeof(double));
+    if (A) memcpy(h.A, A, N * N);
+    if (W) memcpy(h.W, W, N * N * sizeof(double));
+
+    const int key[8] = {nlin, n_lo, n_hi, path, A != nullptr, W != nullptr, want_gb, want_gw};
+    if (memcmp(key, h.key, sizeof(key)) != 0) {
+        if (h.exec) { cudaGraphExecDestroy(h.exec); h.exec = nullptr; }
+        memcpy(h.key, key, sizeof(key));
+        h.seen = 0;
+    }
+    h.seen += 1;
+    if (h.exec && h.epoch != allocation_epoch()) {       // some engine buffer moved since the capture: pointers may be stale
+        cudaGraphExecDestroy(h.exec);
+        h.exec = nullptr;
+        h.seen = 1;                                      // run once plainly (lets every buffer settle), then capture again
+    }
+    if (h.exec) {
+        PYGLM_CUDA(cudaGraphLaunch(h.exec, st));
+    } else if (h.seen >= 2 && !h.disabled && ds->T > 0) {
+        // second call with this signature: every buffer it needs exists by now, so the enqueue is pure stream work
+        cudaGraph_t graph = nullptr;
+        int rc = PYGLM_B200_OK;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e == cudaSuccess) {
+            rc = enqueue_host_call(ds, A != nullptr, W != nullptr, nlin, n_lo, n_hi, path, want_gb, want_gw, st);
+            e = cudaStreamEndCapture(st, &graph);
+        }
+        if (e == cudaSuccess && rc == PYGLM_B200_OK && graph) e = cudaGraphInstantiate(&h.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess || rc != PYGLM_B200_OK || !h.exec) {
+            cudaGetLastError();
+            h.exec = nullptr;
+            h.disabled = true;
+            TRY(enqueue_host_call(ds, A != nullptr, W != nullptr, nlin, n_lo, n_hi, path, want_gb, want_gw, st));
+        } else {
+            h.epoch = allocation_epoch();
+            PYGLM_CUDA(cudaGraphLaunch(h.exec, st));
+        }
+    } else {
+        TRY(enqueue_host_call(ds, A != nullptr, W != nullptr, nlin, n_lo, n_hi, path, want_gb, want_gw, st));
+    }
     PYGLM_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_ll, h.ll, ncols * sizeof(double));
+    if (want_gb) memcpy(out_g_bias, h.gb, ncols * sizeof(double));
+    if (want_gw) memcpy(out_g_w, h.gw, (size_t)ncols * NF * sizeof(double));
     return PYGLM_B200_OK;
 }
 

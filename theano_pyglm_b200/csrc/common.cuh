@@ -11,6 +11,11 @@ namespace pyglm {
 
 void set_error(const char* fmt, ...);
 
+// Counts device (re)allocations of engine buffers.  A captured CUDA graph holds raw device pointers, so the host entry
+// point re-captures whenever this has moved since its graph was built.
+void note_allocation();
+unsigned long long allocation_epoch();
+
 #define PYGLM_CUDA(call)                                                               \
     do {                                                                               \
         cudaError_t e_ = (call);                                                       \

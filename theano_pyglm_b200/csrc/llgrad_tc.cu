@@ -680,6 +680,7 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaGetDevice(&dev));
     PYGLM_CUDA(cudaDeviceGetAttribute(&ws.num_sms, cudaDevAttrMultiProcessorCount, dev));
     const size_t plane = (size_t)T * ws.ldp;
+    note_allocation();
     PYGLM_CUDA(cudaMalloc(&ws.X1, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.X2, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.sx, NB * sizeof(float)));
@@ -772,6 +773,7 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     if (ws.part_elems < per_cta * nctas) {
         cudaFree(ws.part);
         ws.part = nullptr; ws.part_elems = 0;
+        note_allocation();
         PYGLM_CUDA(cudaMalloc(&ws.part, per_cta * nctas * sizeof(double)));
         ws.part_elems = per_cta * nctas;
     }

@@ -61,6 +61,7 @@ static int ensure(void** p, size_t* have, size_t want, size_t esz)
     if (*have >= want) return PYGLM_B200_OK;
     cudaFree(*p);
     *p = nullptr; *have = 0;
+    note_allocation();
     PYGLM_CUDA(cudaMalloc(p, want * esz));
     *have = want;
     return PYGLM_B200_OK;
