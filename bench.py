@@ -300,6 +300,17 @@ def run_ours(args, wl):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
+    # the same evaluation through the host-buffer C-ABI call a Python user makes (numpy in, numpy out; the library
+    # stages through its own pinned buffers and replays a CUDA graph): wall clock, single GPU only
+    host_entry = None
+    if world == 1:
+        for _ in range(3):
+            ds.ll_grad(inp["bias"], inp["w"], nlin=nlin, path=path)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ds.ll_grad(inp["bias"], inp["w"], nlin=nlin, path=path)
+        host_entry = args.steps / (time.perf_counter() - t0)
+
     # dominant-kernel timing for the roofline: the ll+grad launch sequence alone (no collective)
     def step_kernel():
         ds.ll_grad_dev(d_bias.data_ptr(), d_w.data_ptr(), 0, 0, nlin, 0, N, path,
@@ -351,7 +362,11 @@ def run_ours(args, wl):
                        "ingest_s_incl_filter": ingest_s},
             "clocks": clocks,
             "e2e": {"value": world / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "call": "pyglm_b200_ll_grad_dev between a pinned-host upload of the parameters and a pinned-host "
+                            "download of ll / gradients, one stream synchronise per step",
+                    "host_entry_value": host_entry,
+                    "host_entry_call": "pyglm_b200_ll_grad (numpy arrays in and out through ctypes), wall clock"},
             "gpu_launches": (int(info.get("launches_per_eval", 5)) + (1 if comm is not None else 0)) * args.steps,
             "roofline": roof,
         }
