@@ -22,7 +22,7 @@ from scipy.special import logsumexp
 
 from ..components.impulse import DirichletImpulses
 from .ars import adaptive_rejection_sample
-from .hmc import hmc
+from .hmc import hmc, hmc_batched
 from .log_sum_exp import log_sum_exp_sample
 
 
@@ -125,6 +125,103 @@ class HmcDirichletImpulseUpdate(_HmcGlmBlockUpdate):
             else:
                 x['glms'][n_post]['imp'][key] = np.random.gamma(imp.alpha, np.ones(imp.B))
         return x
+
+
+# ------------------------------------------------------------------------------------------------
+# The same HMC updates for all neurons in lock-step (one engine call per leapfrog step)
+# ------------------------------------------------------------------------------------------------
+class BatchedHmcGlmUpdate(MetropolisHastingsUpdate):
+    """HMC on one block of every neuron's GLM parameters at once.  The chains are the reference's per-neuron chains
+    (gibbs.py:164-321 bias, :324-446 background, :449-566 impulse weights, :569-772 Dirichlet impulses): same
+    leapfrog, same accept rule, per-neuron adaptive step sizes; they only share their engine calls, which is what
+    the conditional independence of the GLMs (gibbs.py:53-61) allows."""
+
+    def __init__(self, block, n_steps):
+        self.block, self.n_steps = block, n_steps
+        self.step_sz = None
+        self.avg_accept_rate = None
+
+    def _slices(self, x):
+        """(lo, hi, active) for this block: columns [lo, hi) of the parameter vectors, active (N, hi-lo)."""
+        popn = self.population
+        N, F = popn.N, popn.glm.bkgd_model.n_vars
+        imp = popn.glm.imp_model
+        if self.block == 'bias':
+            return 0, 1, np.ones((N, 1))
+        if self.block == 'bkgd':
+            return 1, 1 + F, np.ones((N, F))
+        lo = 1 + F
+        if self.block == 'imp':
+            return lo, lo + N * imp.B, np.ones((N, N * imp.B))
+        k = self.block[1]                                  # ('g', k): Dirichlet block of presynaptic neuron k
+        names = sorted(imp.get_variables())
+        j = names.index('g_%d' % k)
+        A = x['net']['graph']['A']
+        return lo + j * imp.B, lo + (j + 1) * imp.B, np.repeat(A[k, :].astype(np.float64)[:, None], imp.B, axis=1)
+
+    def update(self, x, n_lo=0, n_hi=None):
+        popn = self.population
+        N = popn.N
+        n_hi = N if n_hi is None else n_hi
+        lo, hi, active = self._slices(x)
+        if hi == lo:
+            return x
+        own = np.zeros((N, 1))
+        own[n_lo:n_hi] = 1.0                               # a neuron-sharded rank moves only its own neurons
+        active = active * own
+        if self.step_sz is None:
+            self.step_sz = np.full(N, 0.1)
+            self.avg_accept_rate = np.full(N, 0.9)
+        full0 = np.stack([popn.glm_param_vector(x['glms'][n]) for n in range(N)])
+
+        def U_and_grad(Q):
+            for n in range(n_lo, n_hi):
+                v = full0[n].copy()
+                v[lo:hi] = Q[n]
+                popn.set_glm_param_vector(x['glms'][n], v)
+            lp, g = popn.glms_log_p_grad(x)
+            return -lp, -g[:, lo:hi]
+
+        q, self.step_sz, self.avg_accept_rate = hmc_batched(U_and_grad, self.step_sz, self.n_steps, full0[:, lo:hi],
+                                                            active=active, avg_accept_rate=self.avg_accept_rate)
+        for n in range(n_lo, n_hi):
+            v = full0[n].copy()
+            v[lo:hi] = q[n]
+            popn.set_glm_param_vector(x['glms'][n], v)
+        return x
+
+
+class BatchedDirichletImpulseUpdate(MetropolisHastingsUpdate):
+    """gibbs.py:569-772 for all postsynaptic neurons at once: for each presynaptic k, two leapfrog steps on g_k in
+    the neurons that have the edge k -> n, a Gamma(alpha, 1) prior draw in those that do not (:764-767)."""
+
+    def preprocess(self, population):
+        self.population = population
+        self.blocks = [BatchedHmcGlmUpdate(('g', k), 2) for k in range(population.N)]
+        for b in self.blocks:
+            b.preprocess(population)
+
+    def update(self, x, n_lo=0, n_hi=None):
+        popn = self.population
+        imp = popn.glm.imp_model
+        n_hi = popn.N if n_hi is None else n_hi
+        A = x['net']['graph']['A']
+        for k, blk in enumerate(self.blocks):
+            blk.update(x, n_lo, n_hi)
+            for n in range(n_lo, n_hi):
+                if not A[k, n]:
+                    x['glms'][n]['imp']['g_%d' % k] = np.random.gamma(imp.alpha, np.ones(imp.B))
+        return x
+
+
+def initialize_batched_updates(population):
+    """The GLM-parameter updates of `initialize_updates` in their lock-step form."""
+    ups = [BatchedHmcGlmUpdate('bias', 10), BatchedHmcGlmUpdate('bkgd', 10)]
+    ups.append(BatchedDirichletImpulseUpdate() if isinstance(population.glm.imp_model, DirichletImpulses)
+               else BatchedHmcGlmUpdate('imp', 10))
+    for u in ups:
+        u.preprocess(population)
+    return ups
 
 
 # ------------------------------------------------------------------------------------------------
@@ -293,6 +390,7 @@ def gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=False, callb
     if x0 is None:
         x0 = initial_state(population, init_from_mle, verbose)
     serial_updates, parallel_updates = initialize_updates(population)
+    batched_updates = initialize_batched_updates(population) if batched else None
     net_update = parallel_updates[-1]
     x = x0
     x_smpls = [copy.deepcopy(x0)]
@@ -301,9 +399,13 @@ def gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=False, callb
             callback(x)
         if verbose:
             print("Gibbs iteration %d. Log prob: %.3f" % (smpl, population.compute_log_p(x)))
-        for upd in parallel_updates[:-1]:
-            for n in range(N):
-                upd.update(x, n)
+        if batched:                                           # all neurons in lock-step: one engine call per leapfrog step
+            for upd in batched_updates:
+                upd.update(x)
+        else:                                                 # the reference's schedule: neuron by neuron
+            for upd in parallel_updates[:-1]:
+                for n in range(N):
+                    upd.update(x, n)
         net_update.begin(x)                                   # GLM parameters changed: rebuild the resident currents
         if batched:
             net_update.sweep_batched(x)

@@ -14,7 +14,7 @@ import numpy as np
 import torch.distributed as dist
 
 from ..utils.parallel_util import allgather_columns, neuron_shard
-from .gibbs import initial_state, initialize_updates
+from .gibbs import initial_state, initialize_batched_updates, initialize_updates
 
 
 def _world(group=None):
@@ -57,6 +57,7 @@ def parallel_gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=Fal
     if seed is not None:
         np.random.seed(seed + 7919 * rank)                      # independent streams per shard
     serial_updates, parallel_updates = initialize_updates(population)
+    batched_updates = initialize_batched_updates(population)
     net_update = parallel_updates[-1]
     x = x0
     x_smpls = [copy.deepcopy(x0)]
@@ -65,9 +66,9 @@ def parallel_gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=Fal
             callback(x)
         if verbose and rank == 0:
             print("Gibbs iteration %d. Log prob: %.3f" % (smpl, population.compute_log_p(x)))
-        for upd in parallel_updates[:-1]:
-            for n in range(n_lo, n_hi):
-                upd.update(x, n)
+        if n_hi > n_lo:
+            for upd in batched_updates:                           # this rank's neurons, in lock-step
+                upd.update(x, n_lo, n_hi)
         if n_hi > n_lo:
             net_update.begin(x, n_lo, n_hi)
             net_update.sweep_batched(x, n_lo, n_hi)
