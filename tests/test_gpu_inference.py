@@ -227,3 +227,45 @@ def test_basis_stimulus_population_end_to_end():
     lp0 = popn.compute_log_p(x0)
     x_fit = coord_descent(popn, x0=x0, maxiter=1, batched=True)
     assert popn.compute_log_p(x_fit) > lp0
+
+
+def test_lock_step_hmc_targets_the_same_posterior_as_the_per_neuron_chains():
+    """BatchedHmcGlmUpdate('bias') (all neurons share each engine call) and HmcBiasUpdate (the reference's
+    neuron-by-neuron schedule, gibbs.py:164-321) are chains on the same conditional posterior of each bias:
+    their sample means agree within Monte-Carlo error, and both sit at the optimum of the log posterior."""
+    from theano_pyglm_b200.inference.gibbs import BatchedHmcGlmUpdate, HmcBiasUpdate
+    model, popn, data, x_true = synth_standard_glm(N=3, nT=8000, seed=6)
+    popn.add_data(data)
+    N = 3
+
+    def run(update_all, x, n_iter=300, burn=100):
+        out = []
+        for it in range(n_iter):
+            update_all(x)
+            if it >= burn:
+                out.append([x['glms'][n]['bias']['bias'][0] for n in range(N)])
+        return np.array(out)
+
+    np.random.seed(0)
+    xb = copy.deepcopy(x_true)
+    ub = BatchedHmcGlmUpdate('bias', 10)
+    ub.preprocess(popn)
+    Sb = run(lambda x: ub.update(x), xb)
+    np.random.seed(1)
+    xs = copy.deepcopy(x_true)
+    us = HmcBiasUpdate()
+    us.preprocess(popn)
+    Ss = run(lambda x: [us.update(x, n) for n in range(N)], xs, n_iter=160, burn=60)
+    sd = np.maximum(Sb.std(axis=0), 1e-3)
+    assert np.all(sd < 2.0)                                             # the data pin the bias down
+    assert np.all(np.abs(Sb.mean(axis=0) - Ss.mean(axis=0)) < 1.0 * sd + 0.05)
+    # the posterior mode of each bias (1-D Newton on the engine's gradient) lies inside the sampled cloud
+    xm = copy.deepcopy(x_true)
+    for n in range(N):
+        for _ in range(30):
+            lp, g = popn.glm_log_p_grad(xm, n)
+            b0 = xm['glms'][n]['bias']['bias'][0]
+            xm['glms'][n]['bias']['bias'] = np.array([b0 + 1e-3])
+            g2 = (popn.glm_log_p_grad(xm, n)[1][0] - g[0]) / 1e-3
+            xm['glms'][n]['bias']['bias'] = np.array([b0 - g[0] / g2])
+        assert abs(xm['glms'][n]['bias']['bias'][0] - Sb.mean(axis=0)[n]) < 3.0 * sd[n] + 0.05
