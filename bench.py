@@ -151,15 +151,16 @@ def cpu_prepare(inp, wl, T_sample, shape="gemm"):
     return per_neuron
 
 
-def cpu_eval_time(inp, wl, T_sample, repeats, shape="gemm"):
-    """Best-of-`repeats` seconds for one CPU eval on the first T_sample bins."""
+def cpu_eval_time(inp, wl, T_sample, budget_s, shape="gemm"):
+    """Mean seconds for one CPU eval on the first T_sample bins: one warm-up call, then repeats until `budget_s`
+    seconds of timed work (at least 2).  Returns (seconds per eval, repeats)."""
     fn = cpu_prepare(inp, wl, T_sample, shape)
-    best = float("inf")
-    for _ in range(repeats):
-        t0 = time.perf_counter()
+    fn()
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or time.perf_counter() - t0 < budget_s:
         fn()
-        best = min(best, time.perf_counter() - t0)
-    return best
+        n += 1
+    return (time.perf_counter() - t0) / n, n
 
 
 def run_reference(args, wl):
@@ -167,7 +168,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     inp = make_inputs(wl, seed=1234)
-    T_sample = min(wl["T"], 100_000)
+    T_sample = min(wl["T"], 500_000 if wl["N"] <= 64 else 50_000)
     scale = wl["T"] / T_sample
     cores = os.cpu_count() or 1
     fn = cpu_prepare(inp, wl, T_sample, "gemm")
@@ -372,15 +373,18 @@ def run_ours(args, wl):
         }
         # CPU baseline on a bounded sample (rank 0, N=1 only)
         if world == 1 and not args.no_cpu:
-            T_s = min(T, 100_000)
-            t_gemm = cpu_eval_time(inp, wl, T_s, 2, "gemm") * (T / T_s)
-            T_r = min(T, 20_000)
-            t_ref = cpu_eval_time(inp, wl, T_r, 1, "reference") * (T / T_r)
+            T_s = min(T, 500_000 if N <= 64 else 50_000)
+            t_gemm, n_gemm = cpu_eval_time(inp, wl, T_s, 10.0, "gemm")
+            t_gemm *= T / T_s
+            T_r = min(T, 100_000 if N <= 64 else 10_000)
+            t_ref, n_ref = cpu_eval_time(inp, wl, T_r, 5.0, "reference")
+            t_ref *= T / T_r
             line["cpu_baseline"] = {
                 "value": 1.0 / t_gemm, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                "sample": "float64 oracle, whole-population BLAS GEMM form on the first %d of %d bins, scaled; "
-                          "reference-shaped per-neuron loop (impulse.py:58 style, %d bins, scaled): %.4g evals/s"
-                          % (T_s, T, T_r, 1.0 / t_ref),
+                "sample": "float64 oracle, whole-population BLAS GEMM form: mean of %d evals on the first %d of %d bins "
+                          "(~10 s of CPU work), scaled to the full recording; reference-shaped per-neuron loop "
+                          "(impulse.py:58 style, %d evals on %d bins, scaled): %.4g evals/s"
+                          % (n_gemm, T_s, T, n_ref, T_r, 1.0 / t_ref),
                 "reference_shaped_value": 1.0 / t_ref}
         print(json.dumps(line), flush=True)
     ds.close()
