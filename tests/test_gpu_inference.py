@@ -269,3 +269,37 @@ def test_lock_step_hmc_targets_the_same_posterior_as_the_per_neuron_chains():
             g2 = (popn.glm_log_p_grad(xm, n)[1][0] - g[0]) / 1e-3
             xm['glms'][n]['bias']['bias'] = np.array([b0 - g[0] / g2])
         assert abs(xm['glms'][n]['bias']['bias'][0] - Sb.mean(axis=0)[n]) < 3.0 * sd[n] + 0.05
+
+
+@pytest.mark.parametrize("kind", ["standard", "network", "stimulus"])
+def test_dense_log_posterior_matches_the_per_neuron_dict_path(kind):
+    """glms_log_p_grad_dense (priors, Dirichlet normalisation and chain rule vectorised over neurons) against
+    glms_log_p_grad (component by component through the state dict) and glm_log_p_grad (one neuron)."""
+    if kind == "standard":
+        model, popn, data, x = synth_standard_glm(N=4, nT=5000, seed=3)
+        popn.add_data(data)
+    elif kind == "network":
+        model, popn, data, x = synth_network_glm(N=12, nT=4000, seed=4)      # 12 > 10: 'g_10' sorts before 'g_2'
+    else:
+        N = 3
+        model = make_model('standard_glm', N=N, dt=0.001)
+        model['bkgd'] = {'type': 'basis', 'D_stim': 1, 'dt_max': 0.3, 'dt_stim': 0.1,
+                         'basis': dict(type='cosine', n_eye=0, n_cos=3, a=1 / 120., b=0.5, orth=False, norm=True)}
+        popn = Population(model)
+        np.random.seed(2)
+        x = popn.sample()
+        for n in range(N):
+            x['glms'][n]['imp']['w_ir'] *= 0.02
+        S = (np.random.rand(3000, N) < 0.03).astype(float)
+        popn.add_data({'S': S, 'N': N, 'dt': 0.001, 'T': 3.0, 'stim': np.random.randn(30, 1), 'dt_stim': 0.1})
+    P = popn.dense_glm_params(x)
+    lp_d, g_d = popn.glms_log_p_grad_dense(P, x)
+    lp_s, g_s = popn.glms_log_p_grad(x)
+    assert np.allclose(lp_d, lp_s, rtol=1e-12, atol=1e-9)
+    assert np.allclose(g_d, g_s, rtol=1e-10, atol=1e-9)
+    lp1, g1 = popn.glm_log_p_grad(x, 1)
+    assert abs(lp1 - lp_d[1]) < 1e-9 * abs(lp1) and np.allclose(g1, g_d[1], rtol=1e-9, atol=1e-8)
+    # round trip of the dense parameters
+    x2 = copy.deepcopy(x)
+    popn.set_dense_glm_params(x2, P * 1.5)
+    assert np.allclose(popn.dense_glm_params(x2), P * 1.5)

@@ -110,3 +110,27 @@ def test_hmc_batched_samples_independent_gaussians_and_respects_the_mask():
     assert np.max(np.abs(S.std(axis=0) / np.broadcast_to(sig, (M, D)) - 1.0)[free]) < 0.2      # 2500 correlated draws
     assert np.all(S[:, 1, 2] == 0.0) and np.all(S[:, 4, :] == 0.0)
     assert step[4] == 0.3 and rate[4] == 0.9 and np.all(step[:4] != 0.3)
+
+
+def test_batched_edge_decisions_equal_the_per_edge_rule():
+    """The vectorised decision of the lock-step sweep == _log_odds + log_sum_exp_sample edge by edge (gibbs.py:1002-1039,
+    log_sum_exp.py:4-37), including NaN candidates, p_A = 0 / tiny / near 1 and uniforms on both sides of the threshold."""
+    from theano_pyglm_b200.inference.gibbs import CollapsedGibbsNetworkColumnUpdate
+    from theano_pyglm_b200.inference.log_sum_exp import log_sum_exp_sample
+    upd = CollapsedGibbsNetworkColumnUpdate()
+    rng = np.random.default_rng(5)
+    M = 400
+    ll = -1000.0 + 30.0 * rng.standard_normal((M, 11))
+    ll[rng.random((M, 11)) < 0.02] = np.nan
+    ll[:, 10] = np.where(np.isnan(ll[:, 10]), -1000.0, ll[:, 10])        # a NaN w=0 likelihood would make p(no edge) 0
+    pA = rng.choice([0.003, 0.3, 0.5, 0.97], size=M)
+    u = rng.random(M)
+    a_vec = upd._decide_batch(ll, pA, u)
+
+    for m in range(M):
+        lp_no, lp_A = upd._log_odds(ll[m, :10], ll[m, 10], pA[m])
+        lnp = np.array([lp_no, lp_A])
+        p = np.exp(lnp - np.logaddexp(lp_no, lp_A))
+        a_ref = 0 if u[m] <= p[0] else 1                                # first index with u <= cumsum (log_sum_exp.py:26-32)
+        assert a_vec[m] == a_ref, (m, p, u[m])
+    assert 0 < a_vec.sum() < M

@@ -69,6 +69,19 @@ class LinearBasisImpulses(_BasisImpulses):
     def impulse(self, xn_imp):
         return self.weights(xn_imp) @ self.ibasis.T                  # impulse.py:65
 
+    # -- all postsynaptic neurons at once: V (M, N*B) holds each neuron's variables in parameter-vector order --------
+    def batch_weights(self, V):
+        return np.asarray(V)
+
+    def batch_log_p(self, V):
+        return self.prior.log_p_batch(np.reshape(V, (-1, self.N, self.B)))
+
+    def batch_grad_log_p(self, V):
+        return np.reshape(self.prior.grad_log_p_batch(np.reshape(V, (-1, self.N, self.B))), np.shape(V))
+
+    def batch_chain_rule(self, V, g_w):
+        return np.asarray(g_w)
+
     def set_hyperparameters(self, model):
         self.prior.set_hyperparameters(model['prior'])
 
@@ -114,6 +127,41 @@ class DirichletImpulses(_BasisImpulses):
 
     def impulse(self, xn_imp):
         return self.weights(xn_imp) @ self.ibasis.T
+
+    # -- all postsynaptic neurons at once.  V (M, N*B): the blocks g_k in parameter-vector order, i.e. sorted by NAME
+    #    ('g_0', 'g_1', 'g_10', ...: theano_func_wrapper.py:53-67), so block j belongs to presynaptic neuron order[j].
+    @property
+    def order(self):
+        if not hasattr(self, '_order'):
+            self._order = np.array([int(name[2:]) for name in sorted(self.get_variables())])
+            self._inverse = np.argsort(self._order)
+        return self._order
+
+    def _blocks(self, V):
+        return np.reshape(np.asarray(V, dtype=np.float64), (-1, self.N, self.B))
+
+    def batch_weights(self, V):
+        """beta of every (post, pre) pair, pre-major like the engine's w rows: (M, N*B)."""
+        g = np.abs(self._blocks(V))
+        beta = g / g.sum(axis=2, keepdims=True)
+        self.order
+        return beta[:, self._inverse, :].reshape(len(beta), -1)
+
+    def batch_log_p(self, V):
+        g = np.abs(self._blocks(V))
+        return np.sum((self.alpha - 1.0) * np.log(g) - g, axis=(1, 2))
+
+    def batch_grad_log_p(self, V):
+        g = self._blocks(V)
+        return (np.sign(g) * ((self.alpha - 1.0) / np.abs(g) - 1.0)).reshape(np.shape(V))
+
+    def batch_chain_rule(self, V, g_w):
+        """d ll / d g (vector order) from the engine's d ll / d beta rows (pre-major)."""
+        g = self._blocks(V)
+        s = np.abs(g).sum(axis=2, keepdims=True)
+        beta = np.abs(g) / s
+        gb = np.reshape(g_w, (-1, self.N, self.B))[:, self.order, :]
+        return (np.sign(g) * (gb - np.sum(gb * beta, axis=2, keepdims=True)) / s).reshape(np.shape(V))
 
     def sample(self, acc):
         return {'g_%d' % n: np.random.gamma(self.alpha, np.ones(self.B)) for n in range(self.N)}   # impulse.py:350

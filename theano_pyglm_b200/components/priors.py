@@ -29,6 +29,13 @@ class Gaussian(Component):
     def grad_log_p(self, value):
         return -(np.asarray(value) - self.mu.get_value()) / self.sigma.get_value() ** 2
 
+    def log_p_batch(self, value):
+        """log_p of every leading-axis slice of value (M, groups, B) -> (M,)."""
+        v = np.asarray(value)
+        return -0.5 / self.sigma.get_value() ** 2 * np.sum((v - self.mu.get_value()) ** 2, axis=tuple(range(1, v.ndim)))
+
+    grad_log_p_batch = grad_log_p                       # elementwise
+
     def set_hyperparameters(self, model):
         self.mu.set_value(model['mu'])
         self.sigma.set_value(model['sigma'])
@@ -56,6 +63,16 @@ class GroupLasso(Component):
         fit_glm's NaN guard (coord_descent.py:176-180) relies on seeing it."""
         z = self._z(value)
         nrm = np.sqrt(np.sum(z ** 2, axis=1, keepdims=True))
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return -self.lam.get_value() * z / nrm / self.sigma.get_value()
+
+    def log_p_batch(self, value):
+        """value (M, groups, B) -> (M,): the group norms run over the last axis."""
+        return -1.0 * self.lam.get_value() * np.sum(np.sqrt(np.sum(self._z(value) ** 2, axis=-1)), axis=-1)
+
+    def grad_log_p_batch(self, value):
+        z = self._z(value)
+        nrm = np.sqrt(np.sum(z ** 2, axis=-1, keepdims=True))
         with np.errstate(invalid='ignore', divide='ignore'):
             return -self.lam.get_value() * z / nrm / self.sigma.get_value()
 

@@ -159,35 +159,37 @@ class BatchedHmcGlmUpdate(MetropolisHastingsUpdate):
         A = x['net']['graph']['A']
         return lo + j * imp.B, lo + (j + 1) * imp.B, np.repeat(A[k, :].astype(np.float64)[:, None], imp.B, axis=1)
 
-    def update(self, x, n_lo=0, n_hi=None):
+    def update_dense(self, P, x, n_lo=0, n_hi=None):
+        """One HMC transition of this block for neurons [n_lo, n_hi), in place on the parameter matrix P (N, D)."""
         popn = self.population
         N = popn.N
         n_hi = N if n_hi is None else n_hi
         lo, hi, active = self._slices(x)
         if hi == lo:
-            return x
+            return P
         own = np.zeros((N, 1))
         own[n_lo:n_hi] = 1.0                               # a neuron-sharded rank moves only its own neurons
         active = active * own
+        if not active.any():
+            return P
         if self.step_sz is None:
             self.step_sz = np.full(N, 0.1)
             self.avg_accept_rate = np.full(N, 0.9)
-        full0 = np.stack([popn.glm_param_vector(x['glms'][n]) for n in range(N)])
 
         def U_and_grad(Q):
-            for n in range(n_lo, n_hi):
-                v = full0[n].copy()
-                v[lo:hi] = Q[n]
-                popn.set_glm_param_vector(x['glms'][n], v)
-            lp, g = popn.glms_log_p_grad(x)
+            Pq = P.copy()
+            Pq[n_lo:n_hi, lo:hi] = Q[n_lo:n_hi]
+            lp, g = popn.glms_log_p_grad_dense(Pq, x)
             return -lp, -g[:, lo:hi]
 
-        q, self.step_sz, self.avg_accept_rate = hmc_batched(U_and_grad, self.step_sz, self.n_steps, full0[:, lo:hi],
+        q, self.step_sz, self.avg_accept_rate = hmc_batched(U_and_grad, self.step_sz, self.n_steps, P[:, lo:hi],
                                                             active=active, avg_accept_rate=self.avg_accept_rate)
-        for n in range(n_lo, n_hi):
-            v = full0[n].copy()
-            v[lo:hi] = q[n]
-            popn.set_glm_param_vector(x['glms'][n], v)
+        P[n_lo:n_hi, lo:hi] = q[n_lo:n_hi]
+        return P
+
+    def update(self, x, n_lo=0, n_hi=None):
+        P = self.update_dense(self.population.dense_glm_params(x), x, n_lo, n_hi)
+        self.population.set_dense_glm_params(x, P, n_lo, n_hi)
         return x
 
 
@@ -206,11 +208,14 @@ class BatchedDirichletImpulseUpdate(MetropolisHastingsUpdate):
         imp = popn.glm.imp_model
         n_hi = popn.N if n_hi is None else n_hi
         A = x['net']['graph']['A']
+        P = popn.dense_glm_params(x)
         for k, blk in enumerate(self.blocks):
-            blk.update(x, n_lo, n_hi)
+            blk.update_dense(P, x, n_lo, n_hi)
+            lo, hi, _ = blk._slices(x)
             for n in range(n_lo, n_hi):
                 if not A[k, n]:
-                    x['glms'][n]['imp']['g_%d' % k] = np.random.gamma(imp.alpha, np.ones(imp.B))
+                    P[n, lo:hi] = np.random.gamma(imp.alpha, np.ones(imp.B))
+        popn.set_dense_glm_params(x, P, n_lo, n_hi)
         return x
 
 
@@ -285,6 +290,26 @@ class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
             log_pr_noA = -np.inf
         return log_pr_noA, log_pr_A
 
+    def _decide_batch(self, ll, pA, u):
+        """The decision rule of _collapsed_sample_AW (gibbs.py:1002-1039) + log_sum_exp_sample (log_sum_exp.py:4-37)
+        for M edges at once: ll (M, 11) candidate log-likelihoods (10 quadrature nodes, then w = 0), pA (M,) prior edge
+        probabilities, u (M,) uniforms.  Returns A (M,) int8: 0 where u <= p(no edge), as the reference's cumsum rule."""
+        log_L = np.where(np.isnan(ll[:, :10]), -np.inf, ll[:, :10])
+        with np.errstate(divide='ignore'):
+            log_G = logsumexp(log_L + np.log(self.GAUSS_HERMITE_WEIGHTS / np.sqrt(np.pi))[None, :], axis=1)
+            if not np.all(np.isfinite(log_G)):
+                raise Exception("log_G not finie")
+            lp_A = np.log(pA) + log_G
+            lp_no = np.log(1.0 - pA) + ll[:, 10]
+        lp_no = np.where(np.isnan(lp_no), -np.inf, lp_no)
+        tot = np.logaddexp(lp_no, lp_A)
+        if not np.all(np.isfinite(tot)):
+            raise Exception("Total probability is zero")                         # log_sum_exp.py:20-22
+        a_new = (u > np.exp(lp_no - tot)).astype(np.int8)                        # log_sum_exp.py:26-32
+        if np.any(np.isclose(pA, 1.0) & (a_new == 0)):
+            raise Exception("Sampled no self edge")
+        return a_new
+
     def _sample_w(self, ds, n_pre, n_post, mu_w, sigma_w, W_nns, log_L):
         """W | A=1 by adaptive rejection sampling on the exact conditional (:1087-1126); every probe of
         the log posterior is a Q=1 delta-ll call."""
@@ -342,12 +367,26 @@ class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
         p_A = self.network.graph.pA.get_value()
         cols = np.arange(n_lo, n_hi, dtype=np.int32)
         orders = np.stack([np.random.permutation(N) for _ in cols])            # one shuffled order per column
+        A = x['net']['graph']['A']
+        W = x['net']['weights']['W'].reshape(N, N)
         for s in range(N):
             pres = orders[:, s].astype(np.int32)
-            cand = np.stack([self._candidates(pres[i], n) for i, n in enumerate(cols)])
-            ll = ds.gibbs_delta_ll(cols, pres, cand)                            # one edge per column x 11 candidates, one launch
-            for i, n in enumerate(cols):
-                self._resample_edge(ds, x, int(pres[i]), int(n), ll[i], p_A)
+            diag = pres == cols
+            mu = np.where(diag, self.mu_w_ref, self.mu_w)
+            sig = np.where(diag, self.sigma_w_ref, self.sigma_w)
+            W_nns = np.sqrt(2) * sig[:, None] * self.GAUSS_HERMITE_ABSCISSAE[None, :] + mu[:, None]     # (M, 10)
+            ll = ds.gibbs_delta_ll(cols, pres, np.concatenate([W_nns, np.zeros((len(cols), 1))], axis=1))
+            log_L = np.where(np.isnan(ll[:, :10]), -np.inf, ll[:, :10])
+            pA = p_A[pres, cols]
+            a_new = self._decide_batch(ll, pA, np.random.rand(len(cols)))
+            w_new = mu + sig * np.random.randn(len(cols))                        # :1063 (kept where A = 0 or ARS is off)
+            if self.sample_w_with_ars:
+                for i in np.nonzero(a_new)[0]:                                   # W | A = 1: ARS on the exact conditional
+                    w_new[i] = self._sample_w(ds, int(pres[i]), int(cols[i]), mu[i], sig[i], W_nns[i], log_L[i])
+            A[pres, cols] = a_new
+            W[pres, cols] = w_new
+            ds.gibbs_commit(cols, pres, a_new, w_new)                           # one rank-1 update launch for the step
+        x['net']['weights']['W'] = W.ravel()
         return x
 
 

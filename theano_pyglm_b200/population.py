@@ -261,6 +261,41 @@ class Population:
             grads.append(np.concatenate(parts))
         return np.array(lps), np.stack(grads)
 
+    # -- the same, on dense arrays (no per-neuron dict traffic): what the lock-step HMC updates call ------------------
+    def dense_glm_params(self, x):
+        """P (N, D): row n = glm_param_vector(x['glms'][n])."""
+        return np.stack([self.glm_param_vector(x['glms'][n]) for n in range(self.N)])
+
+    def set_dense_glm_params(self, x, P, n_lo=0, n_hi=None):
+        for n in range(n_lo, self.N if n_hi is None else n_hi):
+            self.set_glm_param_vector(x['glms'][n], P[n])
+
+    def glms_log_p_grad_dense(self, P, x):
+        """glms_log_p_grad for the parameter matrix P (N, D) and the network of state x, with the priors, the
+        Dirichlet normalisation and its chain rule evaluated for all neurons at once."""
+        glm = self.glm
+        F = glm.bkgd_model.n_vars
+        b = P[:, 0]
+        ws = P[:, 1:1 + F] if F else None
+        V = P[:, 1 + F:]
+        w = glm.imp_model.batch_weights(V)
+        A, W = self.network.A(x['net']), self.network.W(x['net'])
+        scale = glm.lkhd_scale.get_value()
+        ll, gb, gw, gs = 0.0, 0.0, 0.0, 0.0
+        for data in self.data_sequences:
+            l, b_, g, s_ = self._ll_grad_blocks(data, b, w, A, W, ws)
+            ll, gb, gw, gs = ll + scale * l, gb + scale * b_, gw + scale * g, gs + scale * s_
+        bm = glm.bias_model
+        lp = ll - 0.5 / bm.sig_bias ** 2 * (b - bm.mu_bias) ** 2 + glm.imp_model.batch_log_p(V)
+        grad = np.empty_like(P)
+        grad[:, 0] = gb - (b - bm.mu_bias) / bm.sig_bias ** 2
+        if F:
+            sig = glm.bkgd_model.prior_sigma
+            lp = lp + np.sum(-0.5 / sig ** 2 * ws ** 2, axis=1)
+            grad[:, 1:1 + F] = gs - ws / sig ** 2
+        grad[:, 1 + F:] = glm.imp_model.batch_chain_rule(V, gw) + glm.imp_model.batch_grad_log_p(V)
+        return lp, grad
+
     def eval_state(self, vars):
         """Firing rates and currents for the current state (population.py:88-123), engine-side lam."""
         bias, w, A, W = self.glm.engine_params(vars)
