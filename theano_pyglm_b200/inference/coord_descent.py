@@ -44,9 +44,7 @@ def fit_glms_batched(population, x, maxiter=225, gtol=1e-5, history=20, verbose=
     N = population.N
 
     def evaluate(P):
-        for n in range(N):
-            population.set_glm_param_vector(x['glms'][n], P[n])
-        lp, g = population.glms_log_p_grad(x)
+        lp, g = population.glms_log_p_grad_dense(P, x)     # all neurons, priors included, no per-neuron dict traffic
         f = np.where(np.isnan(lp), 1e16, -lp)              # same guards as fit_glm
         g = -g
         g[np.any(np.isnan(g), axis=1)] = 0.0
