@@ -149,6 +149,10 @@ PYGLM_B200_API int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* str
  * out_ll      float64 [n_hi-n_lo]
  * out_g_bias  float64 [n_hi-n_lo]          d ll_n / d bias_n            (may be NULL => ll only)
  * out_g_w     float64 [n_hi-n_lo][N*B+F]   d ll_n / d w[n][j]           (may be NULL => ll only)
+ *
+ * Host buffers may be pageable (they are staged through page-locked memory owned by the
+ * handle) or page-locked (used in place).  From the second call with the same signature the
+ * uploads, kernels and downloads replay as one CUDA graph.
  * ---------------------------------------------------------------------------------- */
 PYGLM_B200_API int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
                        const double* bias, const double* w, const int8_t* A, const double* W,

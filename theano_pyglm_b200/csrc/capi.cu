@@ -78,7 +78,7 @@ struct pyglm_b200_dataset {
         double *bias = nullptr, *w = nullptr, *W = nullptr, *ll = nullptr, *gb = nullptr, *gw = nullptr;
         int8_t* A = nullptr;
         size_t cap_w = 0, cap_gw = 0;                 // doubles allocated for w / gw
-        int key[8] = {-1, -1, -1, -1, -1, -1, -1, -1};     // nlin, n_lo, n_hi, path, hasA, hasW, want_gb, want_gw
+        long long key[16] = {-1};                     // nlin, n_lo, n_hi, path, hasA, hasW, want_gb, want_gw, direct, 7 pointers
         int seen = 0;                                 // calls with this key so far
         cudaGraphExec_t exec = nullptr;
         unsigned long long epoch = 0;                 // allocation_epoch() when `exec` was captured
@@ -389,25 +389,36 @@ static int stage_params(pyglm_b200_dataset* ds, const double* bias, const double
     return PYGLM_B200_OK;
 }
 
-// everything one host-buffer call enqueues: parameter upload from the pinned staging, the evaluation, result download
-static int enqueue_host_call(pyglm_b200_dataset* ds, bool hasA, bool hasW, int nlin, int n_lo, int n_hi, int path,
-                             bool want_gb, bool want_gw, cudaStream_t st)
+// everything one host-buffer call enqueues: parameter upload from pinned host memory, the evaluation, result download
+struct HostPtrs {
+    const double* bias; const double* w; const int8_t* A; const double* W;
+    double* ll; double* gb; double* gw;
+};
+
+static int enqueue_host_call(pyglm_b200_dataset* ds, const HostPtrs& hp, int nlin, int n_lo, int n_hi, int path, cudaStream_t st)
 {
-    auto& h = ds->hc;
     const size_t N = ds->N, NF = (size_t)ds->NF();
     const int ncols = n_hi - n_lo;
-    const bool grad = want_gb || want_gw;
-    PYGLM_CUDA(cudaMemcpyAsync(ds->p_bias.p, h.bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
-    PYGLM_CUDA(cudaMemcpyAsync(ds->p_w.p, h.w, N * NF * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (hasA) PYGLM_CUDA(cudaMemcpyAsync(ds->p_A.p, h.A, N * N, cudaMemcpyHostToDevice, st));
-    if (hasW) PYGLM_CUDA(cudaMemcpyAsync(ds->p_W.p, h.W, N * N * sizeof(double), cudaMemcpyHostToDevice, st));
-    TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, hasA ? ds->p_A.p : nullptr, hasW ? ds->p_W.p : nullptr,
+    const bool grad = hp.gb || hp.gw;
+    PYGLM_CUDA(cudaMemcpyAsync(ds->p_bias.p, hp.bias, N * sizeof(double), cudaMemcpyHostToDevice, st));
+    PYGLM_CUDA(cudaMemcpyAsync(ds->p_w.p, hp.w, N * NF * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (hp.A) PYGLM_CUDA(cudaMemcpyAsync(ds->p_A.p, hp.A, N * N, cudaMemcpyHostToDevice, st));
+    if (hp.W) PYGLM_CUDA(cudaMemcpyAsync(ds->p_W.p, hp.W, N * N * sizeof(double), cudaMemcpyHostToDevice, st));
+    TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, hp.A ? ds->p_A.p : nullptr, hp.W ? ds->p_W.p : nullptr,
                          nlin, n_lo, n_hi, path, ds->o_ll.p, grad ? ds->o_gb.p : nullptr, grad ? ds->o_gw.p : nullptr,
                          nullptr, nullptr, st));
-    PYGLM_CUDA(cudaMemcpyAsync(h.ll, ds->o_ll.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (want_gb) PYGLM_CUDA(cudaMemcpyAsync(h.gb, ds->o_gb.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (want_gw) PYGLM_CUDA(cudaMemcpyAsync(h.gw, ds->o_gw.p, (size_t)ncols * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PYGLM_CUDA(cudaMemcpyAsync(hp.ll, ds->o_ll.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (hp.gb) PYGLM_CUDA(cudaMemcpyAsync(hp.gb, ds->o_gb.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (hp.gw) PYGLM_CUDA(cudaMemcpyAsync(hp.gw, ds->o_gw.p, (size_t)ncols * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
     return PYGLM_B200_OK;
+}
+
+static bool is_pinned_host(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
 }
 
 int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
@@ -426,27 +437,40 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
     auto& h = ds->hc;
     const bool want_gb = out_g_bias != nullptr, want_gw = out_g_w != nullptr, grad = want_gb || want_gw;
 
-    // device and pinned staging (grow only)
     TRY(ds->p_bias.ensure(N)); TRY(ds->p_w.ensure(N * NF));
     if (A) TRY(ds->p_A.ensure(N * N));
     if (W) TRY(ds->p_W.ensure(N * N));
     TRY(ds->o_ll.ensure(ds->N));
     if (grad) { TRY(ds->o_gb.ensure(ds->N)); TRY(ds->o_gw.ensure(N * NF)); }
-    if (!h.bias) {
-        PYGLM_CUDA(cudaMallocHost(&h.bias, N * sizeof(double)));
-        PYGLM_CUDA(cudaMallocHost(&h.ll, N * sizeof(double)));
-        PYGLM_CUDA(cudaMallocHost(&h.gb, N * sizeof(double)));
-        PYGLM_CUDA(cudaMallocHost(&h.W, N * N * sizeof(double)));
-        PYGLM_CUDA(cudaMallocHost(&h.A, N * N));
-        PYGLM_CUDA(cudaMallocHost(&h.w, N * NF * sizeof(double)));
-        PYGLM_CUDA(cudaMallocHost(&h.gw, N * NF * sizeof(double)));
-    }
-    memcpy(h.bias, bias, N * sizeof(double));
-    memcpy(h.w, w, N * NF * sizeof(double));
-    if (A) memcpy(h.A, A, N * N);
-    if (W) memcpy(h.W, W, N * N * sizeof(double));
 
-    const int key[8] = {nlin, n_lo, n_hi, path, A != nullptr, W != nullptr, want_gb, want_gw};
+    // Caller buffers that are page-locked (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory) are used as they
+    // are; pageable ones go through the handle's own pinned staging.
+    const bool direct = is_pinned_host(bias) && is_pinned_host(w) && is_pinned_host(A) && is_pinned_host(W) &&
+                        is_pinned_host(out_ll) && is_pinned_host(out_g_bias) && is_pinned_host(out_g_w);
+    HostPtrs hp{bias, w, A, W, out_ll, out_g_bias, out_g_w};
+    if (!direct) {
+        if (!h.bias) {
+            PYGLM_CUDA(cudaMallocHost(&h.bias, N * sizeof(double)));
+            PYGLM_CUDA(cudaMallocHost(&h.ll, N * sizeof(double)));
+            PYGLM_CUDA(cudaMallocHost(&h.gb, N * sizeof(double)));
+            PYGLM_CUDA(cudaMallocHost(&h.W, N * N * sizeof(double)));
+            PYGLM_CUDA(cudaMallocHost(&h.A, N * N));
+            PYGLM_CUDA(cudaMallocHost(&h.w, N * NF * sizeof(double)));
+            PYGLM_CUDA(cudaMallocHost(&h.gw, N * NF * sizeof(double)));
+        }
+        memcpy(h.bias, bias, N * sizeof(double));
+        memcpy(h.w, w, N * NF * sizeof(double));
+        if (A) memcpy(h.A, A, N * N);
+        if (W) memcpy(h.W, W, N * N * sizeof(double));
+        hp = HostPtrs{h.bias, h.w, A ? h.A : nullptr, W ? h.W : nullptr, h.ll, want_gb ? h.gb : nullptr, want_gw ? h.gw : nullptr};
+    }
+
+    // the whole call is a CUDA graph from the second call with the same signature (and, for caller-pinned buffers,
+    // the same addresses) on
+    const long long key[16] = {nlin, n_lo, n_hi, path, A != nullptr, W != nullptr, want_gb, want_gw, direct,
+                               (long long)(uintptr_t)hp.bias, (long long)(uintptr_t)hp.w, (long long)(uintptr_t)hp.A,
+                               (long long)(uintptr_t)hp.W, (long long)(uintptr_t)hp.ll, (long long)(uintptr_t)hp.gb,
+                               (long long)(uintptr_t)hp.gw};
     if (memcmp(key, h.key, sizeof(key)) != 0) {
         if (h.exec) { cudaGraphExecDestroy(h.exec); h.exec = nullptr; }
         memcpy(h.key, key, sizeof(key));
@@ -466,7 +490,7 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
         int rc = PYGLM_B200_OK;
         cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
         if (e == cudaSuccess) {
-            rc = enqueue_host_call(ds, A != nullptr, W != nullptr, nlin, n_lo, n_hi, path, want_gb, want_gw, st);
+            rc = enqueue_host_call(ds, hp, nlin, n_lo, n_hi, path, st);
             e = cudaStreamEndCapture(st, &graph);
         }
         if (e == cudaSuccess && rc == PYGLM_B200_OK && graph) e = cudaGraphInstantiate(&h.exec, graph, 0);
@@ -475,18 +499,20 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
             cudaGetLastError();
             h.exec = nullptr;
             h.disabled = true;
-            TRY(enqueue_host_call(ds, A != nullptr, W != nullptr, nlin, n_lo, n_hi, path, want_gb, want_gw, st));
+            TRY(enqueue_host_call(ds, hp, nlin, n_lo, n_hi, path, st));
         } else {
             h.epoch = allocation_epoch();
             PYGLM_CUDA(cudaGraphLaunch(h.exec, st));
         }
     } else {
-        TRY(enqueue_host_call(ds, A != nullptr, W != nullptr, nlin, n_lo, n_hi, path, want_gb, want_gw, st));
+        TRY(enqueue_host_call(ds, hp, nlin, n_lo, n_hi, path, st));
     }
     PYGLM_CUDA(cudaStreamSynchronize(st));
-    memcpy(out_ll, h.ll, ncols * sizeof(double));
-    if (want_gb) memcpy(out_g_bias, h.gb, ncols * sizeof(double));
-    if (want_gw) memcpy(out_g_w, h.gw, (size_t)ncols * NF * sizeof(double));
+    if (!direct) {
+        memcpy(out_ll, h.ll, ncols * sizeof(double));
+        if (want_gb) memcpy(out_g_bias, h.gb, ncols * sizeof(double));
+        if (want_gw) memcpy(out_g_w, h.gw, (size_t)ncols * NF * sizeof(double));
+    }
     return PYGLM_B200_OK;
 }
 

@@ -231,6 +231,14 @@ class Dataset:
             return ll, gb, np.ascontiguousarray(gw[:, :NB]), np.ascontiguousarray(gw[:, NB:])
         return ll, gb, gw
 
+    def ll_grad_host_ptrs(self, bias, w, A, W, nlin, n_lo, n_hi, path, out_ll, out_gb, out_gw):
+        """pyglm_b200_ll_grad on raw host addresses (integers; 0 = NULL), e.g. data_ptr() of pinned torch tensors:
+        page-locked caller buffers are used in place, and the whole call replays as one CUDA graph."""
+        vp = C.c_void_p
+        _check(load_library().pyglm_b200_ll_grad(self._h, vp(bias), vp(w), vp(A) if A else None, vp(W) if W else None,
+                                                 nlin_code(nlin), n_lo, n_hi, _PATHS.get(path, path), vp(out_ll),
+                                                 vp(out_gb) if out_gb else None, vp(out_gw) if out_gw else None))
+
     def ll(self, bias, w, A=None, W=None, nlin="explinear", n_lo=0, n_hi=None, path="auto", w_stim=None):
         return self.ll_grad(bias, w, A, W, nlin, n_lo, n_hi, path, grad=False, w_stim=w_stim)
 
