@@ -39,3 +39,25 @@ def test_sass_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", engine.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
     assert archs == {"100a"}, archs
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under theano_pyglm_b200/ may import it (no CPU fallback in the product)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "theano_pyglm_b200")
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|from\s+\.+oracle)", re.M)
+    for dirpath, _dirs, files in os.walk(root):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), os.path.join(dirpath, f)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from theano_pyglm_b200 import engine
+    monkeypatch.setattr(engine, "_lib", None)
+    monkeypatch.setattr(engine, "LIB_PATH", str(tmp_path / "libpyglm_b200.so"))
+    import pytest
+    with pytest.raises(engine.EngineError, match="no CPU fallback"):
+        engine.load_library()
