@@ -19,7 +19,7 @@ d_bias = torch.from_numpy(inp["bias"]).to(dev)
 d_w = torch.from_numpy(inp["w"]).to(dev)
 d_ll = torch.zeros(N, dtype=torch.float64, device=dev)
 st = torch.cuda.current_stream()
-for mode in (0,):
+for mode in (0, 3):
     for dbg in (0, 1):
         os.environ["PYGLM_GEMM_MODE"] = str(mode)
         os.environ["PYGLM_GEMM_DEBUG"] = str(dbg)

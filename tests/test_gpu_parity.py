@@ -116,10 +116,10 @@ def test_ll_grad_tensor_core_path(eng, T, N, B, network, nlin):
     ds.close()
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_forward_cluster_variants(eng, mode, monkeypatch):
-    """The forward GEMM kernel's two cluster variants (X multicast over a pair of column blocks; cta_group::2
-    MMAs over 256 bins) are experiments that stay off by default, but they must stay correct: same tolerances,
+    """The forward GEMM kernel's other variants (32-feature chunks in 64-byte rows; X multicast over a pair of column
+    blocks; cta_group::2 MMAs over 256 bins) stay off by default, but they must stay correct: same tolerances,
     shapes with even / odd numbers of time tiles and column blocks, several K segments."""
     monkeypatch.setenv("PYGLM_GEMM_MODE", str(mode))
     for (T, N, B) in ((2100, 130, 5), (900, 300, 8)):
@@ -129,7 +129,7 @@ def test_gemm_forward_cluster_variants(eng, mode, monkeypatch):
         ll_g, gb_g, gw_g = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=orc.NLIN_SOFTPLUS, path="tc")
         assert np.max(np.abs(ll_g - ll) / np.abs(ll)) < LL_RTOL, (mode, T, N, B)
         assert rel_err(gb_g, gb) < GRAD_RTOL and rel_err(gw_g, gw) < GRAD_RTOL
-        monkeypatch.setenv("PYGLM_GEMM_MODE", "0")
+        monkeypatch.delenv("PYGLM_GEMM_MODE")                          # the default variant
         ll_0 = ds.ll(p['bias'], p['w'], p['A'], p['W'], nlin=orc.NLIN_SOFTPLUS, path="tc")
         monkeypatch.setenv("PYGLM_GEMM_MODE", str(mode))
         assert np.max(np.abs(ll_0 - ll_g) / np.abs(ll)) < 2e-7          # same arithmetic, different tiling of the work

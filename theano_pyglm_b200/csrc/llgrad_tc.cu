@@ -644,7 +644,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D FP16 tensor map with 64B swizzle: dim0 fastest (elements), row pitch in elements, box {box0, box1}
-int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1)
+int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1,
+                   bool swizzle128)
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -662,7 +663,8 @@ int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, 
     cuuint32_t box[2] = {(cuuint32_t)box0, (cuuint32_t)box1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for dims %lld x %lld pitch %lld box %d x %d", (int)r,

@@ -152,6 +152,8 @@ struct GemmFwdArgs {
 //         the leader's full barrier; the leader's commits release the stages and publish the accumulators in both
 //         CTAs; both CTAs' epilogue warps arrive on the leader's accumulator-empty barrier.  (M maps: 64-row boxes.)
 constexpr int kFwdStages2 = 9;
+constexpr int kFwdStages3 = 3;               // MODE 3: 64-feature chunks with 128-byte rows (SWIZZLE_128B)
+constexpr int kFwdStageBytes3 = 4 * kGT * 128;
 constexpr int kFwdStageBytes2 = 2 * kGT * 64 + 2 * (kGN / 2) * 64;       // X1, X2 [128 rows], M1, M2 halves [64 rows]
 static_assert(kFwdStages2 * kFwdStageBytes2 <= kFwdStages * kFwdStageBytes, "the pair layout fits in the same shared memory");
 
@@ -162,12 +164,16 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
 {
     constexpr bool PAIR = MODE == 1;
     constexpr bool DUO = MODE == 2;
-    constexpr int kStages = DUO ? kFwdStages2 : kFwdStages;
-    constexpr int kStageBytes = DUO ? kFwdStageBytes2 : kFwdStageBytes;
-    const uint32_t crank = MODE ? cluster_ctarank() : 0u;
+    constexpr bool WIDE = MODE == 3;             // one CTA per tile like MODE 0, K chunks of 64 features in 128-byte rows
+    constexpr bool CLUSTER = PAIR || DUO;
+    constexpr int kStages = DUO ? kFwdStages2 : WIDE ? kFwdStages3 : kFwdStages;
+    constexpr int kStageBytes = DUO ? kFwdStageBytes2 : WIDE ? kFwdStageBytes3 : kFwdStageBytes;
+    constexpr int kRowB = WIDE ? 128 : 64;       // bytes per operand row in a stage
+    constexpr int kChunkFeat = WIDE ? 64 : 32;
+    const uint32_t crank = CLUSTER ? cluster_ctarank() : 0u;
     // work items of this CTA: w = first, first + stride, ...; item -> (time tile, column block)
-    const int64_t w_first = MODE ? blockIdx.x / 2 : blockIdx.x;
-    const int64_t w_stride = MODE ? gridDim.x / 2 : gridDim.x;
+    const int64_t w_first = CLUSTER ? blockIdx.x / 2 : blockIdx.x;
+    const int64_t w_stride = CLUSTER ? gridDim.x / 2 : gridDim.x;
     const int cbw = PAIR ? a.ncb / 2 : a.ncb;                    // column-block work items per time tile (pair)
     const int64_t nwork = (DUO ? (a.ntt + 1) / 2 : a.ntt) * cbw;
     auto tile_tt = [&](int64_t w) { return DUO ? 2 * (w / cbw) + crank : w / cbw; };
@@ -198,7 +204,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (MODE) cluster_sync_all();            // the peer's barriers and TMEM exist before anything is sent to them
+    if (CLUSTER) cluster_sync_all();         // the peer's barriers and TMEM exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -228,11 +234,11 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                             tma_load_2d_multicast(st + half * 64, &mapX1, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
                             tma_load_2d_multicast(st + kGT * 64 + half * 64, &mapX2, &bar_full[s], kc * 32, row0 + half, (uint16_t)3);
                         } else {
-                            tma_load_2d(st, &mapX1, &bar_full[s], kc * 32, row0);
-                            tma_load_2d(st + kGT * 64, &mapX2, &bar_full[s], kc * 32, row0);
+                            tma_load_2d(st, &mapX1, &bar_full[s], kc * kChunkFeat, row0);
+                            tma_load_2d(st + kGT * kRowB, &mapX2, &bar_full[s], kc * kChunkFeat, row0);
                         }
-                        tma_load_2d(st + 2 * kGT * 64, &mapM1, &bar_full[s], kc * 32, col0);
-                        tma_load_2d(st + 3 * kGT * 64, &mapM2, &bar_full[s], kc * 32, col0);
+                        tma_load_2d(st + 2 * kGT * kRowB, &mapM1, &bar_full[s], kc * kChunkFeat, col0);
+                        tma_load_2d(st + 3 * kGT * kRowB, &mapM2, &bar_full[s], kc * kChunkFeat, col0);
                     }
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
@@ -254,7 +260,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
             // this one thread feeds the tensor pipe, a K chunk every ~400 cycles: the loop carries its stage / phase /
             // segment counters and descriptor bases instead of recomputing them with divisions
             uint32_t sgc = 0, s = 0, ph = 0;
-            const uint64_t d_stage0 = umma_desc(smem_u32(smem), 16, 512);
+            const uint64_t d_stage0 = WIDE ? umma_desc_sw128(smem_u32(smem)) : umma_desc(smem_u32(smem), 16, 512);
             for (int64_t w = w_first; w < nwork; w += w_stride) {
                 int in_seg = 0;
                 for (int kc = 0; kc < a.nkc; ++kc) {
@@ -267,8 +273,8 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     mbar_wait(&bar_full[s], ph);
                     tc_fence_after();
                     const uint64_t dx1 = d_stage0 + (uint64_t)(s * (kStageBytes >> 4));
-                    const uint64_t dx2 = dx1 + ((kGT * 64) >> 4);
-                    const uint64_t dm1 = dx1 + ((2 * kGT * 64) >> 4);               // MODE 0/1: rows 128..255 of this tile are M2
+                    const uint64_t dx2 = dx1 + ((kGT * kRowB) >> 4);
+                    const uint64_t dm1 = dx1 + ((2 * kGT * kRowB) >> 4);            // MODE 0/1/3: rows 128..255 of this tile are M2
                     const bool seg_end = in_seg == a.seg - 1 || kc == a.nkc - 1;
                     if constexpr (DUO) {
                         const uint64_t dm2 = dm1 + (((kGN / 2) * 64) >> 4);
@@ -283,7 +289,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                         if (seg_end) umma_commit_pair(&bar_acc_full[ab], (uint16_t)3);
                     } else {
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
+                        for (int ks = 0; ks < kChunkFeat / 16; ++ks) {
                             if (a.debug & 1) break;
                             const uint32_t acc = (in_seg | ks) ? 1u : 0u;
                             umma_f16(t_a, dx1 + 2 * ks, dm1 + 2 * ks, idesc2, acc);    // X1 [M1 | M2]
@@ -398,7 +404,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (MODE) cluster_sync_all();            // neither CTA leaves while the other may still signal its barriers / TMEM
+    if (CLUSTER) cluster_sync_all();         // neither CTA leaves while the other may still signal its barriers / TMEM
     if (warp == 0) {
         if (DUO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -584,8 +590,15 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if (!ws.gemm) ws.gemm = new GemmWorkspace();
     GemmWorkspace& g = *static_cast<GemmWorkspace*>(ws.gemm);
     const int NB = a.N * a.B + a.F;
-    const int nkc = (int)ceil_div(NB, 32);
-    const int Kp = nkc * 32;
+    // Forward kernel variant.  3 (default): single CTAs, 64-feature K chunks in 128-byte rows (SWIZZLE_128B), three
+    // 64 KB stages.  0: the same with 32-feature chunks in 64-byte rows (SWIZZLE_64B), seven 32 KB stages -- its MMAs
+    // fetch their operands half as efficiently (C3 forward: 2.20 ms against 1.91 ms).  1 / 2: the cluster experiments.
+    int mode = 3;
+    if (const char* env = getenv("PYGLM_GEMM_MODE")) mode = atoi(env);
+    if (mode < 0 || mode > 3) mode = 3;
+    const int chunkf = mode == 3 ? 64 : 32;                      // features per K chunk
+    const int nkc = (int)ceil_div(NB, chunkf);
+    const int Kp = nkc * chunkf;
     const int Npr = (int)round_up(a.ncols, kGN);
     const int ncb = Npr / kGN;
     const int64_t ntt = ceil_div(a.T, kGT);
@@ -596,17 +609,15 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if ((rc = ensure((void**)&g.Mp, &g.Mp_elems, (size_t)2 * Npr * Kp, sizeof(__half)))) return rc;
     if ((rc = ensure((void**)&g.colpar, &g.colpar_elems, (size_t)2 * Npr, sizeof(float)))) return rc;
     if ((rc = ensure((void**)&g.R, &g.R_elems, (size_t)2 * a.T * Npr, sizeof(__half)))) return rc;
-    // mode 0 (default): single CTAs.  Modes 1 (X multicast over a cluster of two) and 2 (cta_group::2 pairs) are
-    // parity-tested experiments selected with PYGLM_GEMM_MODE; measured at C3 (forward only): 2.47 / 2.6 / 2.75 ms.
-    // With the MMAs removed the TMA pipeline alone takes 1.7 ms (20 GB at the ~12 TB/s L2-to-SM cap) in mode 0 and
-    // 2.8 ms in mode 2: the pair's cross-SM barrier traffic costs more than its 25 % fewer bytes save.
-    int mode = 0;
-    if (const char* env = getenv("PYGLM_GEMM_MODE")) mode = atoi(env);
+    // Modes 1 (X multicast over a cluster of two) and 2 (cta_group::2 pairs) are parity-tested experiments on top of the
+    // 32-feature layout; measured at C3 (forward only) when mode 0 took 2.47 ms: 2.6 / 2.75 ms.  With the MMAs removed the
+    // TMA pipeline alone takes 1.7 ms (20 GB at the ~12 TB/s L2-to-SM cap) in mode 0 and 2.8 ms in mode 2: the pair's
+    // cross-SM barrier traffic costs more than its 25 % fewer bytes save.
     if (mode == 1 && (ncb % 2 != 0)) mode = 0;
-    if (mode != 0 && ws.num_sms < 2) mode = 0;
+    if ((mode == 1 || mode == 2) && ws.num_sms < 2) mode = 0;
     const int64_t nwork = mode == 2 ? ceil_div(ntt, 2) * ncb * 2 : ntt * ncb;            // in CTAs
     int nctas = (int)std::min<int64_t>(nwork, ws.num_sms);
-    if (mode) nctas &= ~1;
+    if (mode == 1 || mode == 2) nctas &= ~1;
     if ((rc = ensure((void**)&g.part, &g.part_elems, (size_t)nctas * 4 * Npr * 2, sizeof(double)))) return rc;
 
     PYGLM_CUDA(cudaMemsetAsync(g.part, 0, (size_t)nctas * 4 * Npr * 2 * sizeof(double), stream));
@@ -615,15 +626,15 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
 
     const CUtensorMap* xmaps = static_cast<const CUtensorMap*>(ws.tmaps);
     CUtensorMap mM1, mM2, mR1, mR2;
-    if ((rc = tc_make_map_2d(&mM1, g.Mp, Kp, Npr, Kp, 32, kGN))) return rc;
-    if ((rc = tc_make_map_2d(&mM2, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, 32, kGN))) return rc;
+    if ((rc = tc_make_map_2d(&mM1, g.Mp, Kp, Npr, Kp, chunkf, kGN, mode == 3))) return rc;
+    if ((rc = tc_make_map_2d(&mM2, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, chunkf, kGN, mode == 3))) return rc;
 
     GemmFwdArgs f{};
     f.Sp = ws.Sp; f.Nps = ws.Np; f.T = a.T; f.n_lo = a.n_lo; f.ncols = a.ncols; f.Npr = Npr; f.nkc = nkc;
     // up to ~1500 features one segment is accurate enough (measured: 7e-7 on ll, 2e-6 on gradients at 1280 features,
     // exp model) and costs nothing; beyond that the K loop is cut into 256-feature segments (~9 % slower, 70x more accurate
     // at 10240 features)
-    f.seg = nkc <= kFwdSingleSegmentChunks ? nkc : kFwdSegChunks;
+    f.seg = nkc * chunkf <= kFwdSingleSegmentChunks * 32 ? nkc : kFwdSegChunks * 32 / chunkf;
     if (const char* env = getenv("PYGLM_GEMM_DEBUG")) f.debug = atoi(env);
     if (const char* env = getenv("PYGLM_GEMM_SEG")) f.seg = std::max(1, atoi(env));      // precision experiments
     f.ntt = ntt; f.ncb = ncb; f.colpar = g.colpar; f.R = g.R; f.plane = (int64_t)a.T * Npr; f.part = g.part; f.dt = (float)a.dt;
@@ -633,7 +644,15 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
         if ((rc = tc_make_map_2d(&g.mapX64[1], ws.X2, ws.ldp, a.T, ws.ldp, 32, kBwdRows))) return rc;
         g.mapX64_ready = true;
     }
-    if (mode) {
+    if (mode == 3) {
+        CUtensorMap mX1w, mX2w;                                   // 64 features x 128 bins boxes, 128-byte swizzle
+        if ((rc = tc_make_map_2d(&mX1w, ws.X1, ws.ldp, a.T, ws.ldp, 64, kGT, true))) return rc;
+        if ((rc = tc_make_map_2d(&mX2w, ws.X2, ws.ldp, a.T, ws.ldp, 64, kGT, true))) return rc;
+        auto kf = a.nlin == PYGLM_B200_NLIN_EXP ? tc_gemm_fwd_kernel<PYGLM_B200_NLIN_EXP, 3>
+                                                : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, 3>;
+        PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+        kf<<<nctas, kGThreads, smem_f, stream>>>(mX1w, mX2w, mM1, mM2, f);
+    } else if (mode) {
         CUtensorMap mM1h, mM2h;                                   // 64-column boxes of the weight planes (mode 2)
         if ((rc = tc_make_map_2d(&mM1h, g.Mp, Kp, Npr, Kp, 32, kGN / 2))) return rc;
         if ((rc = tc_make_map_2d(&mM2h, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, 32, kGN / 2))) return rc;

@@ -10,6 +10,7 @@ namespace pyglm {
 constexpr float kLoScale = 2048.0f;         // 2^11 between the two planes
 constexpr float kRScale = 64.0f;            // residual planes carry r * 2^6
 constexpr uint32_t kSw64 = 4;               // UMMA LayoutType::SWIZZLE_64B
+constexpr uint32_t kSw128 = 2;              // UMMA LayoutType::SWIZZLE_128B
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -121,6 +122,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64)
+// same descriptor for a 128-byte-swizzled K-major operand: rows of 128 B, SBO = 1024 (8 rows), LBO unused
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
+{
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)kSw128 << 61;
+    return d;
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
