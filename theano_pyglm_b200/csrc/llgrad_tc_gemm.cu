@@ -421,10 +421,19 @@ struct GemmBwdArgs {
     double* Gp;                        // [splits][NBp][Npr]
 };
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kGThreads, 1)
 tc_gemm_bwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
                    const __grid_constant__ CUtensorMap mapR1, const __grid_constant__ CUtensorMap mapR2, GemmBwdArgs a)
 {
+    // WIDE: operands as 64-element blocks in 128-byte rows (SWIZZLE_128B), two blocks per 128 features / neurons;
+    // otherwise 32-element blocks in 64-byte rows (SWIZZLE_64B), four blocks.  Same bytes per stage either way.
+    constexpr int kBlk = WIDE ? 64 : 32;                        // elements per block along M / N
+    constexpr int kNBlk = 128 / kBlk;                           // blocks per operand plane
+    constexpr int kBlkBytes = kBwdRows * kBlk * 2;              // one block: 64 bins x kBlk elements
+    constexpr uint32_t kLayout = WIDE ? kSw128 : kSw64;
+    constexpr uint32_t kSbo = 8 * kBlk * 2;                     // eight bins
+    constexpr uint32_t kStepBytes = 16 * kBlk * 2;              // one k16 step: sixteen bins
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kBwdStages * kBwdStageBytes);
@@ -463,11 +472,11 @@ tc_gemm_bwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                 unsigned char* st = smem + s * kBwdStageBytes;
                 const int row0 = (int)(tile_lo * kGT) + h * kBwdRows;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    tma_load_2d(st + (0 + c) * kBwdChunkBytes, &mapX1, &bar_full[s], fb * kGF + c * 32, row0);
-                    tma_load_2d(st + (4 + c) * kBwdChunkBytes, &mapX2, &bar_full[s], fb * kGF + c * 32, row0);
-                    tma_load_2d(st + (8 + c) * kBwdChunkBytes, &mapR1, &bar_full[s], cb * kGN + c * 32, row0);
-                    tma_load_2d(st + (12 + c) * kBwdChunkBytes, &mapR2, &bar_full[s], cb * kGN + c * 32, row0);
+                for (int c = 0; c < kNBlk; ++c) {
+                    tma_load_2d(st + (0 * kNBlk + c) * kBlkBytes, &mapX1, &bar_full[s], fb * kGF + c * kBlk, row0);
+                    tma_load_2d(st + (1 * kNBlk + c) * kBlkBytes, &mapX2, &bar_full[s], fb * kGF + c * kBlk, row0);
+                    tma_load_2d(st + (2 * kNBlk + c) * kBlkBytes, &mapR1, &bar_full[s], cb * kGN + c * kBlk, row0);
+                    tma_load_2d(st + (3 * kNBlk + c) * kBlkBytes, &mapR2, &bar_full[s], cb * kGN + c * kBlk, row0);
                 }
             }
         }
@@ -485,13 +494,13 @@ tc_gemm_bwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     mbar_wait(&bar_full[s], (h / kBwdStages) & 1);
                     tc_fence_after();
                     const uint32_t base = smem_u32(smem + s * kBwdStageBytes);
-                    const uint64_t dx1 = umma_desc(base, kBwdChunkBytes, 512);
-                    const uint64_t dx2 = umma_desc(base + 4 * kBwdChunkBytes, kBwdChunkBytes, 512);
-                    const uint64_t dr1 = umma_desc(base + 8 * kBwdChunkBytes, kBwdChunkBytes, 512);
+                    const uint64_t dx1 = umma_desc_layout(base, kBlkBytes, kSbo, kLayout);
+                    const uint64_t dx2 = umma_desc_layout(base + 1 * kNBlk * kBlkBytes, kBlkBytes, kSbo, kLayout);
+                    const uint64_t dr1 = umma_desc_layout(base + 2 * kNBlk * kBlkBytes, kBlkBytes, kSbo, kLayout);
 #pragma unroll
                     for (int ks = 0; ks < kBwdRows / 16; ++ks) {
                         const uint32_t acc = (hh | ks) ? 1u : 0u;
-                        const uint64_t off = (uint64_t)(ks * 1024 >> 4);
+                        const uint64_t off = (uint64_t)(ks * kStepBytes >> 4);
                         umma_f16(t_a, dx1 + off, dr1 + off, idesc2, acc);         // X1^T [r1 | r2]
                         umma_f16(t_b, dx2 + off, dr1 + off, idesc, 1u);           // X2^T r1
                     }
@@ -679,8 +688,14 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     PYGLM_CUDA(cudaGetLastError());
     if (!grad) return PYGLM_B200_OK;
 
-    if ((rc = tc_make_map_2d(&mR1, g.R, Npr, a.T, Npr, 32, kBwdRows))) return rc;
-    if ((rc = tc_make_map_2d(&mR2, g.R + (size_t)a.T * Npr, Npr, a.T, Npr, 32, kBwdRows))) return rc;
+    bool bwd_wide = true;                                        // 128-byte-swizzled operand blocks (64 elements)
+    if (const char* env = getenv("PYGLM_GEMM_BWD_WIDE")) bwd_wide = atoi(env) != 0;
+    const int blk = bwd_wide ? 64 : 32;
+    if ((rc = tc_make_map_2d(&mR1, g.R, Npr, a.T, Npr, blk, kBwdRows, bwd_wide))) return rc;
+    if ((rc = tc_make_map_2d(&mR2, g.R + (size_t)a.T * Npr, Npr, a.T, Npr, blk, kBwdRows, bwd_wide))) return rc;
+    CUtensorMap mXb1, mXb2;
+    if ((rc = tc_make_map_2d(&mXb1, ws.X1, ws.ldp, a.T, ws.ldp, blk, kBwdRows, bwd_wide))) return rc;
+    if ((rc = tc_make_map_2d(&mXb2, ws.X2, ws.ldp, a.T, ws.ldp, blk, kBwdRows, bwd_wide))) return rc;
     int64_t splits = std::max<int64_t>(1, (int64_t)ws.num_sms / ((int64_t)nfb * ncb));
     splits = std::min<int64_t>(splits, ntt);
     const int64_t tps = ceil_div(ntt, splits);
@@ -689,9 +704,10 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     GemmBwdArgs b{};
     b.ntt = ntt; b.tiles_per_split = tps; b.Npr = Npr; b.NBp = NBp; b.Gp = g.Gp;
     const int smem_b = kBwdStages * kBwdStageBytes + 256 + 1024;
-    PYGLM_CUDA(cudaFuncSetAttribute(tc_gemm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
+    auto kb = bwd_wide ? tc_gemm_bwd_kernel<true> : tc_gemm_bwd_kernel<false>;
+    PYGLM_CUDA(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_b));
     dim3 gridb((unsigned)nfb, (unsigned)ncb, (unsigned)splits);
-    tc_gemm_bwd_kernel<<<gridb, kGThreads, smem_b, stream>>>(g.mapX64[0], g.mapX64[1], mR1, mR2, b);
+    kb<<<gridb, kGThreads, smem_b, stream>>>(mXb1, mXb2, mR1, mR2, b);
     PYGLM_CUDA(cudaGetLastError());
     tc_gemm_final_G_kernel<<<(unsigned)ceil_div((int64_t)NB * a.ncols, 256), 256, 0, stream>>>(
         g.Gp, (int)splits, NBp, Npr, a.N, a.B, a.F, a.n_lo, a.ncols, ws.sx, a.A, a.W, a.out_gw);

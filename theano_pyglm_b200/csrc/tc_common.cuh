@@ -132,6 +132,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
     d |= (uint64_t)kSw128 << 61;
     return d;
 }
+// general form with an explicit layout type (kSw64 / kSw128)
+__device__ __forceinline__ uint64_t umma_desc_layout(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout)
+{
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
 {
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu);
