@@ -213,9 +213,14 @@ constexpr int kGradBase = kFwdCols;          // forward accumulators are single-
 constexpr int kGradBuf = 2 * kFwdCols;       // one gradient buffer = two 128-feature tiles; double-buffered
 constexpr int kTmemAlloc = 512;
 
-template <int NLIN>
+// WIDE (4 or 5 chunks, i.e. 97..160 features): features 0..127 travel as two 64-feature chunks in 128-byte rows
+// (SWIZZLE_128B) -- the tensor core fetches those with full shared-memory wavefronts, 64-byte-swizzled operands with
+// half-empty ones -- and only the tail chunk (features 128..159) keeps the 32-feature / 64-byte layout.  Stage size,
+// TMEM layout and epilogue are the same in both variants.
+template <int NLIN, bool WIDE>
 __global__ void __launch_bounds__(kThreads, 1)
-tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2, TcKernelArgs a)
+tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant__ CUtensorMap tmap2,
+                const __grid_constant__ CUtensorMap tmapW1, const __grid_constant__ CUtensorMap tmapW2, TcKernelArgs a)
 {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -264,7 +269,13 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             const int row = w >> 2, q = w & 3;               // row n (64 B), 16-byte unit within the row
             const uint4 val = *reinterpret_cast<const uint4*>(
                 a.Mp + ((int64_t)(plane * kNcol + row) * a.Kp + c * kChunkF + q * 8));
-            *reinterpret_cast<uint4*>(sM + c * 2 * kMChunkBytes + plane * kMChunkBytes + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = val;
+            if (WIDE && c < 4) {
+                // wide chunk c/2: 64 rows [M1 | M2] of 128 B, this narrow chunk is its half (c & 1); 128-byte swizzle
+                const int r = plane * kNcol + row, q8 = (c & 1) * 4 + q;
+                *reinterpret_cast<uint4*>(sM + (c >> 1) * 4 * kMChunkBytes + r * 128 + ((q8 ^ (r & 7)) << 4)) = val;
+            } else {
+                *reinterpret_cast<uint4*>(sM + c * 2 * kMChunkBytes + plane * kMChunkBytes + row * 64 + ((q ^ ((row >> 1) & 3)) << 4)) = val;
+            }
         }
         fence_proxy_async();
         if (threadIdx.x < kNcol) {
@@ -291,6 +302,26 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 unsigned char* st = smem + s * L.stage_bytes;
                 const int row0 = (int)((first + (int64_t)it * step) * kTileT);
                 const uint32_t par = ((it >> 1) & 1) ^ 1;
+                if constexpr (WIDE) {
+                    // load units: two wide chunks (64 features x 128 bins per plane), then the tail chunk if there is one
+                    const int nu = 2 + (nch - 4);
+                    for (int u = 0; u < nu; ++u) {
+                        if (u == 0) mbar_wait_relaxed(&bar_empty[2 * s], par, a.producer_sleep_ns);
+                        if (u == 2) mbar_wait_relaxed(&bar_empty[2 * s + 1], par, a.producer_sleep_ns);
+                        uint64_t* fb = &bar_full[s * kMaxChunks + u];
+                        if (u == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
+                        if (u < 2) {
+                            mbar_arrive_expect_tx(fb, 4 * kChunkBytes);
+                            tma_load_2d(st + u * 2 * kChunkBytes, &tmapW1, fb, u * 64, row0);
+                            tma_load_2d(st + (nch + u * 2) * kChunkBytes, &tmapW2, fb, u * 64, row0);
+                        } else {
+                            mbar_arrive_expect_tx(fb, 2 * kChunkBytes);
+                            tma_load_2d(st + 4 * kChunkBytes, &tmap1, fb, 4 * kChunkF, row0);
+                            tma_load_2d(st + (nch + 4) * kChunkBytes, &tmap2, fb, 4 * kChunkF, row0);
+                        }
+                    }
+                    continue;
+                }
                 for (int c = 0; c < nch; ++c) {
                     if (c == 0) mbar_wait_relaxed(&bar_empty[2 * s], par, a.producer_sleep_ns);
                     if (c == 4) mbar_wait_relaxed(&bar_empty[2 * s + 1], par, a.producer_sleep_ns);
@@ -314,6 +345,32 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 const int s = it & 1;
                 const uint32_t sX1 = smem_u32(smem + s * L.stage_bytes), sX2 = sX1 + nch * kChunkBytes;
                 mbar_wait(bar_fwd_empty, (it & 1) ^ 1);
+                if constexpr (WIDE) {
+                    for (int u = 0; u < 2; ++u) {                                  // wide chunks: four k16 steps each
+                        mbar_wait(&bar_full[s * kMaxChunks + u], (it >> 1) & 1);
+                        if (u == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
+                        tc_fence_after();
+                        const uint64_t wx1 = umma_desc_sw128(sX1 + u * 2 * kChunkBytes);
+                        const uint64_t wx2 = umma_desc_sw128(sX2 + u * 2 * kChunkBytes);
+                        const uint64_t wm = umma_desc_sw128(sMb + u * 4 * kMChunkBytes);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t acc = (u | ks) ? 1u : 0u;
+                            umma_f16(t_f, wx1 + 2 * ks, wm + 2 * ks, idesc_f64, acc);          // X1 [M1 | M2]
+                            umma_f16(t_f + 64, wx2 + 2 * ks, wm + 2 * ks, idesc_f32, acc);     // X2 M1
+                        }
+                    }
+                    if (nch > 4) {                                                 // tail chunk, 64-byte layout
+                        mbar_wait(&bar_full[s * kMaxChunks + 2], (it >> 1) & 1);
+                        tc_fence_after();
+                        const uint64_t dx1 = umma_desc(sX1 + 4 * kChunkBytes, 16, 512), dx2 = umma_desc(sX2 + 4 * kChunkBytes, 16, 512);
+                        const uint64_t dm = umma_desc(sMb + 8 * kMChunkBytes, 16, 512);
+                        umma_f16(t_f, dx1, dm, idesc_f64, 1u);
+                        umma_f16(t_f + 64, dx2, dm, idesc_f32, 1u);
+                        umma_f16(t_f, dx1 + 2, dm + 2, idesc_f64, 1u);
+                        umma_f16(t_f + 64, dx2 + 2, dm + 2, idesc_f32, 1u);
+                    }
+                } else {
                 uint64_t dx1 = umma_desc(sX1, 16, 512), dx2 = umma_desc(sX2, 16, 512), dm = umma_desc(sMb, 16, 512);
                 for (int c = 0; c < nch; ++c) {
                     mbar_wait(&bar_full[s * kMaxChunks + c], (it >> 1) & 1);
@@ -325,6 +382,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                     umma_f16(t_f, dx1 + 2, dm + 2, idesc_f64, 1u);             // features 16..31 (+32 bytes)
                     umma_f16(t_f + 64, dx2 + 2, dm + 2, idesc_f32, 1u);
                     dx1 += kChunkBytes >> 4; dx2 += kChunkBytes >> 4; dm += (2 * kMChunkBytes) >> 4;
+                }
                 }
                 umma_commit(bar_fwd_full);
                 if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 1] = clock64();
@@ -343,7 +401,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 const int s = j & 1, b = j & 1, gb = j & 1;
                 const uint32_t sX1 = smem_u32(smem + s * L.stage_bytes), sX2 = sX1 + nch * kChunkBytes;
                 const uint32_t sR1 = smem_u32(sR + b * 2 * kRBytes);
-                for (int c = 0; c < nch; ++c) mbar_wait(&bar_full[s * kMaxChunks + c], (j >> 1) & 1);   // landed long ago
+                for (int c = 0; c < (WIDE ? 2 + (nch - 4) : nch); ++c) mbar_wait(&bar_full[s * kMaxChunks + c], (j >> 1) & 1);   // landed long ago
                 mbar_wait(&bar_r_ready[b], (j >> 1) & 1);
                 mbar_wait(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
                 if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
@@ -356,14 +414,18 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                     // LBO = 0 all four 32-row groups of its M = 128 alias that chunk, so every TMEM lane quarter holds
                     // a copy of the same 32 gradient rows and the epilogue warps can take turns folding them.
                     const uint32_t lbo = mt ? 0u : (uint32_t)kChunkBytes;
-                    const uint64_t dx1_0 = umma_desc(sX1 + mt * 4 * kChunkBytes, lbo, 512);
-                    const uint64_t dx2_0 = umma_desc(sX2 + mt * 4 * kChunkBytes, lbo, 512);
+                    const bool wide_tile = WIDE && mt == 0;       // two 64-feature blocks in 128-byte rows: LBO = one wide chunk
+                    const uint64_t dx1_0 = wide_tile ? umma_desc_layout(sX1, 2 * kChunkBytes, 1024, kSw128)
+                                                     : umma_desc(sX1 + mt * 4 * kChunkBytes, lbo, 512);
+                    const uint64_t dx2_0 = wide_tile ? umma_desc_layout(sX2, 2 * kChunkBytes, 1024, kSw128)
+                                                     : umma_desc(sX2 + mt * 4 * kChunkBytes, lbo, 512);
+                    const uint32_t xstep = wide_tile ? 2048u : 1024u;             // sixteen bins of the X operand
 #pragma unroll
                     for (int ks = 0; ks < kTileT / 16; ++ks) {                    // 16 bins per step
                         const uint32_t acc = ks ? 1u : 0u;
-                        const uint64_t off = (uint64_t)(ks * 1024 >> 4);
-                        umma_f16(t_g, dx1_0 + off, dr0 + off, idesc_b64, acc);       // X1^T [r1 | r2]
-                        umma_f16(t_g + 64, dx2_0 + off, dr0 + off, idesc_b32, acc);  // X2^T r1
+                        const uint64_t off = (uint64_t)(ks * 1024 >> 4), offx = (uint64_t)(ks * xstep >> 4);
+                        umma_f16(t_g, dx1_0 + offx, dr0 + off, idesc_b64, acc);      // X1^T [r1 | r2]
+                        umma_f16(t_g + 64, dx2_0 + offx, dr0 + off, idesc_b32, acc); // X2^T r1
                     }
                     if (mt == 0) umma_commit(&bar_empty[2 * s]);                 // chunks 0-3 can be refilled
                 }
@@ -694,12 +756,14 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)T * ws.Np, stream));
     PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
     PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, NB * sizeof(unsigned), stream));
-    ws.tmaps = malloc(2 * sizeof(CUtensorMap));
+    ws.tmaps = malloc(4 * sizeof(CUtensorMap));
     if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
     CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
     int rc;
     if ((rc = tc_make_map_2d(&maps[0], ws.X1, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
     if ((rc = tc_make_map_2d(&maps[1], ws.X2, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
+    if ((rc = tc_make_map_2d(&maps[2], ws.X1, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;      // wide chunks, 128B swizzle
+    if ((rc = tc_make_map_2d(&maps[3], ws.X2, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;
     return PYGLM_B200_OK;
 }
 
@@ -781,7 +845,11 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     }
     const TcSmem L = tc_smem_layout(nch);
     const int smem_bytes = L.total + 1024;
-    auto kern = a.nlin == PYGLM_B200_NLIN_EXP ? tc_fused_kernel<PYGLM_B200_NLIN_EXP> : tc_fused_kernel<PYGLM_B200_NLIN_SOFTPLUS>;
+    bool wide = nch >= 4;
+    if (const char* env = getenv("PYGLM_TC_WIDE")) wide = wide && atoi(env) != 0;
+    auto kern = a.nlin == PYGLM_B200_NLIN_EXP
+                    ? (wide ? tc_fused_kernel<PYGLM_B200_NLIN_EXP, true> : tc_fused_kernel<PYGLM_B200_NLIN_EXP, false>)
+                    : (wide ? tc_fused_kernel<PYGLM_B200_NLIN_SOFTPLUS, true> : tc_fused_kernel<PYGLM_B200_NLIN_SOFTPLUS, false>);
     PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const CUtensorMap* maps = static_cast<const CUtensorMap*>(ws.tmaps);
     for (int c0 = 0; c0 < a.ncols; c0 += kNcol) {
@@ -801,7 +869,7 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         const bool want_trace = getenv("PYGLM_TC_TRACE") != nullptr;
         if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, (384 + 32 * 32 + 32 * 16) * sizeof(long long)));
         k.trace = want_trace ? d_trace : nullptr;
-        kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], k);
+        kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], k);
         PYGLM_CUDA(cudaGetLastError());
         if (want_trace) {
             static int dumped = 0;
