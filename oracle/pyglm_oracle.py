@@ -162,8 +162,12 @@ def nlin_and_derivative(x, nlin_type):
     e = np.exp(-np.abs(x))
     lam = np.where(x > 0, x + np.log1p(e), np.log1p(e))
     sig = np.where(x > 0, 1.0 / (1.0 + e), e / (1.0 + e))
-    with np.errstate(divide='ignore'):
-        loglam = np.log(lam)
+    # log(lam): for x < 0, lam = e q with q = log1p(e)/e -> log lam = x + log q, finite however negative x is.
+    # (The reference's literal log(log(1+exp(x))) is -inf below x ~ -37 and its ll NaN there; its callers map that NaN
+    # to -inf, gibbs.py:1011-1012.  The finite limit kept here is > 700 below any competing term, so it decides nothing.)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        q = np.where(e > 1e-5, np.log1p(e) / np.where(e > 0, e, 1.0), 1.0 - e * (0.5 - e / 3.0))
+        loglam = np.where(x > 0, np.log(lam), x + np.log(q))
     return lam, sig, loglam
 
 
