@@ -171,6 +171,21 @@ def nlin_and_derivative(x, nlin_type):
     return lam, sig, loglam
 
 
+def poisson_residual(x, S_n, dt, nlin_type):
+    """r_t = d/dx_t of (-dt*lam + S log lam) = S * f'/lam - dt * f'  (what T.grad propagates through glm.py:52).
+    f'/lam is formed without dividing by an underflowed lam: exp -> 1; softplus, x <= 0 -> 1/((1+e^x) q) with
+    q = log1p(e^x)/e^x (-> 1), so the residual stays finite however negative the activation is."""
+    x = np.asarray(x, dtype=np.float64)
+    lam, dlam, _ = nlin_and_derivative(x, nlin_type)
+    if nlin_type == NLIN_EXP:
+        return S_n - dt * lam
+    e = np.exp(-np.abs(x))
+    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
+        q = np.where(e > 1e-5, np.log1p(e) / np.where(e > 0, e, 1.0), 1.0 - e * (0.5 - e / 3.0))
+        ratio = np.where(x > 0, dlam / np.where(lam > 0, lam, 1.0), 1.0 / ((1.0 + e) * q))
+    return S_n * ratio - dt * dlam
+
+
 def dirichlet_beta(g):
     """beta = |g| / sum|g| per presynaptic neuron.  components/impulse.py:286-291.
     g: (N_pre, B) -> (N_pre, B)."""
@@ -218,7 +233,7 @@ def glm_ll_grad(fS, S, dt, n, bias_n, w_n, A, W, nlin_type, I_stim=0.0):
     lam, dlam, loglam = nlin_and_derivative(x, nlin_type)
     Sn = S[:, n].astype(np.float64)
     ll = float(np.sum(-dt * lam + loglam * Sn))
-    r = (Sn / lam - dt) * dlam
+    r = poisson_residual(x, Sn, dt, nlin_type)
     g_bias = float(np.sum(r))
     G = np.tensordot(r, fS, axes=(0, 0))                  # (N_pre, B)
     g_w = weff[:, None] * G
@@ -247,7 +262,7 @@ def population_ll_grad(fS, S, dt, bias, w, A, W, nlin_type, fstim=None, w_stim=N
     lam, dlam, loglam = nlin_and_derivative(x, nlin_type)
     Sf = S.astype(np.float64)
     ll = np.sum(-dt * lam + loglam * Sf, axis=0)
-    r = (Sf / lam - dt) * dlam
+    r = poisson_residual(x, Sf, dt, nlin_type)
     g_bias = np.sum(r, axis=0)
     G = (X.T @ r).reshape(N, B, N)                        # [(pre,b), post]
     Weff = A.astype(np.float64) * W

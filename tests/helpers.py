@@ -45,3 +45,12 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def grad_errors(got, ref, floor=1e-3):
+    """(max-norm relative error, element-wise relative error over the entries with |ref| > floor * max|ref|)."""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    mx = max(np.max(np.abs(ref)), 1e-300)
+    big = np.abs(ref) > floor * mx
+    return float(np.max(np.abs(got - ref)) / mx), float(np.max(np.abs(got - ref)[big] / np.abs(ref)[big]))

@@ -142,6 +142,64 @@ def test_collapsed_column_update_reproduces_reference_decisions_for_the_same_ran
     upd.end()
 
 
+def test_collapsed_column_update_conditions_on_every_data_sequence():
+    """gibbs.py:931-935 sums `_glm_ll` over population.data_sequences.  With two sequences of different lengths the
+    mirror's candidate log-likelihoods must be the sum of the oracle's per-sequence values, its decisions those of the
+    summed log-likelihoods, and both resident states must receive every commit."""
+    from theano_pyglm_b200.inference.gibbs import CollapsedGibbsNetworkColumnUpdate
+    model, popn, data, x = synth_network_glm(N=5, nT=3000, seed=5)
+    N = model['N']
+    rng = np.random.default_rng(17)
+    data2 = {'S': (rng.random((1700, N)) < 0.03).astype(np.float64), 'N': N, 'dt': 0.001, 'T': 1.7, 'stim': None, 'dt_stim': 0.1}
+    popn.add_data(data2, set_as_current_data=False)        # `current` stays the first one: must not matter
+    upd = CollapsedGibbsNetworkColumnUpdate()
+    upd.preprocess(popn)
+    upd.sample_w_with_ars = False
+    bias, w, A0, W0 = popn.glm.engine_params(copy.deepcopy(x))
+    ib = popn.glm.imp_model.ibasis
+    seqs = [(orc.convolve_with_basis(d['S'], ib), d['S']) for d in (data, data2)]
+    p_A = popn.network.graph.pA.get_value()
+    ds = upd.begin(x)
+    n_post, n_pre = 3, 1
+    cand = upd._candidates(n_pre, n_post)
+    got = ds.gibbs_delta_ll([n_post], [n_pre], cand[None, :])[0]
+    ref = np.zeros(11)
+    for fS, S in seqs:
+        I_imp = orc.impulse_current(fS, w[n_post].reshape(N, -1))
+        A1 = A0.copy(); A1[n_pre, n_post] = 0
+        I_other = I_imp @ orc.effective_weights(A1, W0, n_post)
+        ref += [orc.gibbs_glm_ll(bias[n_post], 0.0, I_other, I_imp[:, n_pre], wq, S[:, n_post], 0.001, orc.NLIN_SOFTPLUS)
+                for wq in cand]
+    assert rel_err(got, ref) < 1e-10
+    # a whole column, replayed on the oracle with summed log-likelihoods
+    np.random.seed(42)
+    upd.update(x, n_post)
+    np.random.seed(42)
+    order = np.arange(N)
+    np.random.shuffle(order)
+    A_ref, W_ref = A0.copy(), W0.copy()
+    for pre in order:
+        u, z = np.random.rand(), np.random.randn()
+        mu, sig = (-0.2, 0.5) if pre == n_post else (0.0, 1.0)
+        W_nns = orc.gh_candidates(mu, sig)
+        ll = np.zeros(11)
+        for fS, S in seqs:
+            I_imp = orc.impulse_current(fS, w[n_post].reshape(N, -1))
+            A1 = A_ref.copy(); A1[pre, n_post] = 0
+            I_other = I_imp @ orc.effective_weights(A1, W_ref, n_post)
+            ll += [orc.gibbs_glm_ll(bias[n_post], 0.0, I_other, I_imp[:, pre], wq, S[:, n_post], 0.001, orc.NLIN_SOFTPLUS)
+                   for wq in list(W_nns) + [0.0]]
+        lp_no, lp_a = orc.collapsed_edge_log_odds(ll[:10], ll[10], p_A[pre, n_post])
+        A_ref[pre, n_post] = orc.log_sum_exp_sample([lp_no, lp_a], u)
+        W_ref[pre, n_post] = mu + sig * z
+    assert np.array_equal(x['net']['graph']['A'], A_ref)
+    assert np.allclose(x['net']['weights']['W'].reshape(N, N), W_ref, rtol=0, atol=1e-12)
+    for d in (data, data2):
+        A_dev, W_dev = popn._handle(d).gibbs_state()
+        assert np.array_equal(A_dev, A_ref) and np.allclose(W_dev, W_ref, atol=1e-12)
+    upd.end()
+
+
 def test_gibbs_sample_runs_and_keeps_a_valid_state():
     from theano_pyglm_b200.inference.gibbs import gibbs_sample
     model, popn, data, x = synth_network_glm(N=4, nT=4000, seed=5)

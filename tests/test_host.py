@@ -244,3 +244,63 @@ def test_make_synth_dataset_packages_the_reference_data_dict():
     for n in range(3):
         act = x_true['glms'][n]['bias']['bias'][0] + orc.impulse_current(fS, x_true['glms'][n]['imp']['w_ir'].reshape(3, -1)).sum(axis=1)
         assert np.allclose(act, data['X'][:, n], atol=1e-8)
+
+
+def test_sta_and_stimulus_initialisation():
+    """utils/sta.py:6-84 and smart_init.py:30-99 (temporal branch): the spike-triggered average against its definition,
+    and the projected initial w_stim recovering a planted stimulus filter."""
+    from theano_pyglm_b200.inference.smart_init import initialize_with_data
+    from theano_pyglm_b200.models.model_factory import make_model
+    from theano_pyglm_b200.population import Population
+    from theano_pyglm_b200.utils.sta import project_onto_basis, sta
+    rng = np.random.default_rng(3)
+    nt, N, D, L = 400, 2, 2, 7
+    data = {'S': (rng.random((nt, N)) < 0.2).astype(np.float64), 'dt': 0.001, 'dt_stim': 0.002}
+    stim = rng.standard_normal((nt // 2, D))
+    A = sta(stim, data, L, Ns=[1, 0])
+    t = 0.001 * np.arange(nt)
+    ist = np.stack([np.interp(t, 0.002 * np.arange(nt // 2), stim[:, d]) for d in range(D)], axis=1) / 2.0
+    for i, n in enumerate([1, 0]):
+        for l in range(L):
+            ref = sum(data['S'][tt, n] * ist[tt - l] for tt in range(l, nt)) / data['S'][:, n].sum()
+            assert np.allclose(A[i, l], ref, rtol=1e-12, atol=1e-14)
+    basis = rng.standard_normal((L, 3))
+    coef = rng.standard_normal(3)
+    assert np.allclose(project_onto_basis(basis @ coef, basis).ravel(), coef)
+    # smart_init on a BasisStimulus model: the STA of white noise driving a Poisson neuron points along its filter
+    model = make_model('standard_glm', N=2, dt=0.001)
+    model['bkgd'].update(type='basis', D_stim=1, dt_stim=0.001)
+    popn = Population(model)
+    ib = popn.glm.bkgd_model.ibasis
+    nt = 60000
+    stim = rng.standard_normal((nt, 1))
+    w_true = np.array([[3.0, -1.0, 0.5], [-2.0, 2.0, 0.0]])
+    drive = np.stack([np.convolve(stim[:, 0], np.concatenate([[0.0], ib @ w_true[n]]))[:nt] for n in range(2)], axis=1)
+    S = (rng.random((nt, 2)) < 0.02 * np.exp(np.clip(drive, -3, 3))).astype(np.float64)
+    data = {'S': S, 'dt': 0.001, 'dt_stim': 0.001, 'stim': stim, 'T': nt * 0.001}
+    np.random.seed(0)
+    x0 = popn.sample()
+    x0['net']['graph']['A'] = np.zeros((2, 2), dtype=np.int8)
+    initialize_with_data(popn, data, x0)
+    assert np.all(x0['net']['graph']['A'] == 1)
+    for n in range(2):
+        w0 = x0['glms'][n]['bkgd']['w_stim']
+        c = np.dot(ib @ w0, ib @ w_true[n]) / np.linalg.norm(ib @ w0) / np.linalg.norm(ib @ w_true[n])
+        assert w0.shape == (3,) and c > 0.8
+
+
+def test_fit_network_sets_gaussian_weights_to_the_prior_mean():
+    from theano_pyglm_b200.inference.coord_descent import fit_network
+    from theano_pyglm_b200.models.model_factory import make_model
+    from theano_pyglm_b200.population import Population
+    model = make_model('sparse_weighted_model', N=4, dt=0.001)
+    popn = Population(model)
+    np.random.seed(1)
+    x = popn.sample()
+    lp0 = popn.network.log_p(x['net'])
+    fit_network(popn, x)
+    W = x['net']['weights']['W'].reshape(4, 4)
+    assert np.all(np.diag(W) == -0.2) and np.all(W[~np.eye(4, dtype=bool)] == 0.0)
+    assert popn.network.log_p(x['net']) >= lp0
+    x2 = Population(make_model('standard_glm', N=3, dt=0.001)).sample()
+    assert fit_network(Population(make_model('standard_glm', N=3, dt=0.001)), x2) is x2      # constant weights: untouched

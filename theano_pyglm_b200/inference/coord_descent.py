@@ -113,8 +113,19 @@ def fit_glms_batched(population, x, maxiter=225, gtol=1e-5, history=20, verbose=
 
 
 def fit_network(population, x):
-    """The reference fits differentiable network variables with Newton-CG (:129-159); for the models on
-    the accelerated path (constant weights / MCMC-only Gaussian weights) there is nothing to fit (:141)."""
+    """Fit the differentiable network variables against the network prior (coord_descent.py:84-159: Newton-CG on
+    `-network.log_prior`; the data never enter).  Constant weights: nothing to fit (:141).  Gaussian weights: the
+    maximiser of the Gaussian prior is its mean, written here in closed form -- off-diagonal `prior.mu`, diagonal
+    `refractory_prior.mu` (weights.py:47-71).  (The reference itself stops with an AttributeError on this branch:
+    `Network` has `log_p`, not the `log_prior` that coord_descent.py:113 evaluates; SURVEY.md appendix A.)"""
+    wm = population.network.weights
+    if 'W' not in x['net']['weights'] or not hasattr(wm, 'prior'):
+        return x
+    N = population.N
+    W = np.full((N, N), float(wm.prior.mu.get_value()))
+    if hasattr(wm, 'refractory_prior'):
+        W[np.diag_indices(N)] = float(wm.refractory_prior.mu.get_value())
+    x['net']['weights']['W'] = W.ravel()
     return x
 
 

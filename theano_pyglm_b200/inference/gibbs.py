@@ -232,6 +232,28 @@ def initialize_batched_updates(population):
 # ------------------------------------------------------------------------------------------------
 # Collapsed Gibbs over one column of A / W
 # ------------------------------------------------------------------------------------------------
+class _ResidentSequences:
+    """The Gibbs state of every data sequence of the population, driven as one: candidate log-likelihoods are summed
+    over the sequences (gibbs.py:931-935 loops `for data in self.population.data_sequences`), commits go to all."""
+
+    def __init__(self, handles):
+        self.handles = list(handles)
+
+    def gibbs_delta_ll(self, cols, pres, w_cand):
+        out = self.handles[0].gibbs_delta_ll(cols, pres, w_cand)
+        for h in self.handles[1:]:
+            out = out + h.gibbs_delta_ll(cols, pres, w_cand)
+        return out
+
+    def gibbs_commit(self, cols, pres, a_new, w_new):
+        for h in self.handles:
+            h.gibbs_commit(cols, pres, a_new, w_new)
+
+    def gibbs_end(self):
+        for h in self.handles:
+            h.gibbs_end()
+
+
 class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
     def __init__(self):
         self.DEG_GAUSS_HERMITE = 10
@@ -253,15 +275,18 @@ class CollapsedGibbsNetworkColumnUpdate(ParallelMetropolisHastingsUpdate):
 
     # -- engine residency ------------------------------------------------------------------------
     def begin(self, x, n_lo=0, n_hi=None):
-        """Upload the state and build I_net for the columns [n_lo, n_hi) (seval(glm.I_net), gibbs.py:812-864);
-        a neuron-sharded rank makes only its own columns resident."""
+        """Upload the state and build I_net for the columns [n_lo, n_hi) (seval(glm.I_net), gibbs.py:812-864) on EVERY
+        data sequence of the population -- the conditional of A/W is the product of the sequences' likelihoods, as the
+        HMC updates of the same sweep already assume; a neuron-sharded rank makes only its own columns resident."""
         popn = self.population
         bias, w, A, W = popn.glm.engine_params(x)
-        ds = popn._handle()
-        ds.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
-                       w_stim=popn.glm.stim_weights(x))
-        self._resident = ds
-        return ds
+        seqs = popn.data_sequences if popn.data_sequences else [popn._current]
+        handles = [popn._handle(d) for d in seqs]
+        for h in handles:
+            h.gibbs_begin(bias, w, A, W, nlin=popn.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
+                          w_stim=popn.glm.stim_weights(x))
+        self._resident = _ResidentSequences(handles)
+        return self._resident
 
     def end(self):
         if self._resident is not None:

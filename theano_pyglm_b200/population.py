@@ -25,6 +25,8 @@ class Population:
         self.latent = LatentVariables(model)
         self.network = Network(model, self.latent)
         self.glm = Glm(model, self.network, self.latent)
+        if hasattr(self.glm.bkgd_model, 'device'):
+            self.glm.bkgd_model.device = device                     # the stimulus projection runs on this rank's GPU
         # MCMC compares differences of log-likelihood sums against uniforms: keep X in FP64 there.
         stochastic = model['network']['graph']['type'].lower() != 'complete'
         self.x_dtype = x_dtype or ("f64" if stochastic else "f32")
