@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PYGLM_B200_ABI_VERSION 2
+#define PYGLM_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define PYGLM_B200_API __attribute__((visibility("default")))
@@ -62,10 +62,19 @@ extern "C" {
  * recordings whose FP32 X would not fit next to the planes (configs C4/C5 shards). */
 #define PYGLM_B200_X_PLANES 2
 
-/* arithmetic path for ll / gradient */
+/* arithmetic path for ll / gradient
+ *   PATH_FP64  FP64 CUDA-core contractions over X as stored (exact path: 1e-11 on a float64 dataset).
+ *   PATH_TC    tcgen05 `kind::f16` contractions on error-free FP16 splits of every operand
+ *              (v*s = v1 + v2*2^-11, s a power of two: 22 significant bits, three products per contraction),
+ *              FP32 accumulation per 128-bin tile in TMEM, FP32 epilogue (nonlinearity, Poisson terms), FP64 sums
+ *              across tiles.  Holds 1e-6 (ll) / 1e-5 (gradient, max-norm) against the reference's float64.
+ *   PATH_AUTO  PATH_TC where the dataset has it (FP32 X or planes), else PATH_FP64.  With the exp nonlinearity
+ *              the epilogue flags every neuron whose activation leaves x <= 16 (e^x in FP32 no longer holds the
+ *              tolerance there and overflows at 88); the host entry point re-evaluates flagged neurons on PATH_FP64
+ *              before returning, the _dev entry point leaves the flags for pyglm_b200_range_flags(). */
 #define PYGLM_B200_PATH_AUTO   0
-#define PYGLM_B200_PATH_FP64   1   /* FP64 CUDA-core contractions (exact path)                 */
-#define PYGLM_B200_PATH_TC     2   /* tcgen05 3xTF32 contractions, FP32 epilogue, FP64 sums    */
+#define PYGLM_B200_PATH_FP64   1
+#define PYGLM_B200_PATH_TC     2
 
 typedef struct pyglm_b200_dataset pyglm_b200_dataset;
 
@@ -153,6 +162,8 @@ PYGLM_B200_API int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* str
  * Host buffers may be pageable (they are staged through page-locked memory owned by the
  * handle) or page-locked (used in place).  From the second call with the same signature the
  * uploads, kernels and downloads replay as one CUDA graph.
+ * Host and _dev entry points share the handle's workspaces: each use is ordered after the previous one with an
+ * event, so the two may be mixed on one handle from one host thread without a device synchronise in between.
  * ---------------------------------------------------------------------------------- */
 PYGLM_B200_API int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
                        const double* bias, const double* w, const int8_t* A, const double* W,
@@ -169,6 +180,10 @@ PYGLM_B200_API int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
 /* which arithmetic path a call with `path` would take on this dataset: returns
  * PYGLM_B200_PATH_FP64 / PYGLM_B200_PATH_TC, or PYGLM_B200_EUNSUPPORTED. */
 PYGLM_B200_API int pyglm_b200_resolve_path(const pyglm_b200_dataset* ds, int32_t path);
+
+/* range flags of the last tensor-core evaluation: out_flags int32 [N], 1 = the neuron's activation left the range in
+ * which the FP32 epilogue of the exp nonlinearity holds the tolerance (see PATH_AUTO).  Synchronises the device. */
+PYGLM_B200_API int pyglm_b200_range_flags(const pyglm_b200_dataset* ds, int32_t* out_flags);
 
 /* firing rate lam[t][n] for n in [n_lo,n_hi): host float64 [T][n_hi-n_lo].
  * Replaces seval(glm.lam, ...) in Population.eval_state (population.py:88-123); this is

@@ -29,15 +29,23 @@ def run(name, nlin=orc.NLIN_SOFTPLUS, x_dtype="f32"):
     t0 = time.time()
     fS = orc.convolve_with_basis(p['S'].astype(np.float64), p['ibasis'])
     ll, gb, gw = orc.population_ll_grad(fS, p['S'], p['dt'], p['bias'], p['w'], p['A'], p['W'], nlin)
+    x = orc.population_activation(fS, p['bias'], p['w'], p['A'], p['W'])
+    lam, _d, loglam = orc.nlin_and_derivative(x, nlin)
+    terms = np.sum(np.abs(p['dt'] * lam) + np.abs(loglam * p['S']), axis=0)       # size of each neuron's sum
     t_cpu = time.time() - t0
-    del fS
+    del fS, x, lam, loglam
     ds = pg.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype=x_dtype)
     out = {"case": name, "T": T, "N": N, "B": B, "cpu_s": round(t_cpu, 1), "path": ds.path_info("auto")["name"]}
     for path in ("tc", "fp64") if x_dtype == "f32" else ("tc",):
         if path == "fp64" and N * B > 6000:
             continue
         l, b, g = ds.ll_grad(p['bias'], p['w'].reshape(N, -1), p['A'], p['W'], nlin=nlin, path=path)
-        out[path] = {"ll": float(np.max(np.abs(l - ll) / np.abs(ll))), "g_bias": grad_errors(b, gb), "g_w": grad_errors(g, gw.reshape(N, -1))}
+        gn = np.concatenate([gb[:, None], gw.reshape(N, -1)], axis=1)                 # each neuron's gradient vector
+        gg = np.concatenate([b[:, None], g], axis=1)
+        out[path] = {"ll_rel": float(np.max(np.abs(l - ll) / np.abs(ll))), "ll_total": float(abs(l.sum() - ll.sum()) / abs(ll.sum())),
+                     "ll_vs_terms": float(np.max(np.abs(l - ll) / terms)),
+                     "g_bias": grad_errors(b, gb), "g_w": grad_errors(g, gw.reshape(N, -1)),
+                     "g_per_neuron_maxnorm": float(np.max(np.max(np.abs(gg - gn), axis=1) / np.max(np.abs(gn), axis=1)))}
     ds.close()
     print(json.dumps(out), flush=True)
 

@@ -28,21 +28,27 @@ def test_engine_reproduces_golden_ll_and_gradient(eng, name):
     g = load(name)
     N = g['S'].shape[1]
     gw = g['g_w'].reshape(N, -1)
-    for x_dtype, path, lt, gt in (("f64", "fp64", 1e-11, 1e-9), ("f32", "fp64", 1e-6, 1e-5), ("f32", "tc", 1e-6, 1e-5)):
+    for x_dtype, path, lt, gt in (("f64", "fp64", 1e-11, 1e-9), ("f64", "auto", 1e-11, 1e-9), ("f32", "fp64", 1e-6, 1e-5),
+                                  ("f32", "auto", 1e-6, 1e-5), ("f32", "tc", 1e-6, 1e-5)):
         ds = eng.Dataset(g['S'], float(g['dt']), g['ibasis'], x_dtype=x_dtype)
         fS = ds.fS()
         tol = 1e-12 if x_dtype == "f64" else 2e-7 * np.max(np.abs(g['fS_rows']))
         assert np.max(np.abs(fS[::100] - g['fS_rows'])) <= tol
         ll, gb, gwe = ds.ll_grad(g['bias'], g['w'], g['A'], g['W'], nlin=int(g['nlin']), path=path)
         # The exp fixture drives some neurons to activations of several hundred (unit-area impulses times N(0,1)
-        # weights under exp): lam = e^240.  Float64 follows the reference there; anything that stores X or
-        # evaluates exp in FP32 cannot (e^x carries |x| 2^-24 relative error and overflows at x = 88), so those
-        # neurons are held to "same sign, -inf or within 1e-4" and the physical ones to the north-star bound.
+        # weights under exp): lam = e^240.  A float64 dataset follows the reference there on every path choice.  With X
+        # STORED in FP32 the activation itself carries |x| 2^-24, so e^x is good to ~1e-5 at best for those neurons:
+        # path="auto" notices them in the epilogue (range flags) and re-evaluates them on the FP64 path -- finite, within
+        # 1e-4 of the reference, never -inf -- while an explicit path="tc" keeps the FP32 epilogue's overflow.
         sane = np.abs(g['ll']) < 1e6 if x_dtype == "f32" else np.ones(N, dtype=bool)
         assert sane.sum() >= 2
         assert np.max(np.abs(ll - g['ll'])[sane] / np.abs(g['ll'])[sane]) < lt, (name, x_dtype, path)
         wild = ~sane
-        assert np.all(np.isneginf(ll[wild]) | (np.abs(ll[wild] - g['ll'][wild]) < 1e-4 * np.abs(g['ll'][wild])))
+        close = np.abs(ll[wild] - g['ll'][wild]) < 1e-4 * np.abs(g['ll'][wild])
+        assert np.all(close | np.isneginf(ll[wild])) if path == "tc" else np.all(close), (name, x_dtype, path, ll[wild])
+        if path == "auto" and x_dtype == "f32" and wild.any():
+            flags = ds.range_flags()
+            assert np.all(flags[wild] == 1) and rel_err(gwe[wild], gw[wild]) < 1e-4
         assert rel_err(gb[sane], g['g_bias'][sane]) < gt and rel_err(gwe[sane], gw[sane]) < gt, (name, x_dtype, path)
         ds.close()
 

@@ -77,13 +77,20 @@ struct pyglm_b200_dataset {
     struct HostCall {
         double *bias = nullptr, *w = nullptr, *W = nullptr, *ll = nullptr, *gb = nullptr, *gw = nullptr;
         int8_t* A = nullptr;
-        size_t cap_w = 0, cap_gw = 0;                 // doubles allocated for w / gw
+        unsigned* flags = nullptr;                    // [N] range flags of the last call (always page-locked)
+        bool staging_ready = false;                   // all seven staging buffers exist
         long long key[16] = {-1};                     // nlin, n_lo, n_hi, path, hasA, hasW, want_gb, want_gw, direct, 7 pointers
         int seen = 0;                                 // calls with this key so far
         cudaGraphExec_t exec = nullptr;
         unsigned long long epoch = 0;                 // allocation_epoch() when `exec` was captured
         bool disabled = false;                        // capture failed once: plain stream calls from then on
     } hc;
+
+    // The workspaces above are shared by every entry point.  The host entry points run on `stream`, the _dev ones on
+    // the caller's: `ws_done` is recorded after each use and the next user's stream waits on it when it is another one.
+    cudaEvent_t ws_done = nullptr;
+    cudaStream_t ws_stream = nullptr;
+    bool ws_used = false;
 
     // Gibbs state
     bool gibbs_active = false;
@@ -99,6 +106,20 @@ struct pyglm_b200_dataset {
 
 #define TRY(expr)                                                      \
     do { int rc_ = (expr); if (rc_ != PYGLM_B200_OK) return rc_; } while (0)
+
+// order this use of the handle's workspaces after the previous one when that ran on another stream
+static int ws_acquire(pyglm_b200_dataset* ds, cudaStream_t st)
+{
+    if (ds->ws_used && ds->ws_stream != st) PYGLM_CUDA(cudaStreamWaitEvent(st, ds->ws_done, 0));
+    return PYGLM_B200_OK;
+}
+static int ws_release(pyglm_b200_dataset* ds, cudaStream_t st)
+{
+    PYGLM_CUDA(cudaEventRecord(ds->ws_done, st));
+    ds->ws_stream = st;
+    ds->ws_used = true;
+    return PYGLM_B200_OK;
+}
 
 extern "C" {
 
@@ -173,6 +194,8 @@ int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, in
 
     cudaError_t e = cudaStreamCreateWithFlags(&ds->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); return fail(PYGLM_B200_ECUDA); }
+    e = cudaEventCreateWithFlags(&ds->ws_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error("cudaEventCreate: %s", cudaGetErrorString(e)); return fail(PYGLM_B200_ECUDA); }
 
     const size_t nS = (size_t)(T + halo) * N;
     const size_t esz = x_dtype == PYGLM_B200_X_F64 ? 8 : 4;
@@ -221,7 +244,8 @@ int pyglm_b200_dataset_destroy(pyglm_b200_dataset* ds)
     ds->tc.release();
     if (ds->hc.exec) cudaGraphExecDestroy(ds->hc.exec);
     cudaFreeHost(ds->hc.bias); cudaFreeHost(ds->hc.w); cudaFreeHost(ds->hc.W); cudaFreeHost(ds->hc.A);
-    cudaFreeHost(ds->hc.ll); cudaFreeHost(ds->hc.gb); cudaFreeHost(ds->hc.gw);
+    cudaFreeHost(ds->hc.ll); cudaFreeHost(ds->hc.gb); cudaFreeHost(ds->hc.gw); cudaFreeHost(ds->hc.flags);
+    if (ds->ws_done) cudaEventDestroy(ds->ws_done);
     if (ds->stream) cudaStreamDestroy(ds->stream);
     delete ds;
     return PYGLM_B200_OK;
@@ -321,6 +345,12 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
         t.B = ds->B; t.F = ds->F; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
         t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
         t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
+        t.flags = nullptr;
+        if (nlin == PYGLM_B200_NLIN_EXP) {          // range flags of this call's columns (kExpSafe, tc_common.cuh)
+            if (!ds->tc.planes_ready) { int rc = tc_ensure_planes(t, ds->tc, stream); if (rc) return rc; }
+            PYGLM_CUDA(cudaMemsetAsync(ds->tc.colflag + n_lo, 0, (size_t)ncols * sizeof(unsigned), stream));
+            t.flags = ds->tc.colflag;
+        }
         return launch_tc_ll_grad(t, ds->tc, stream);
     }
 
@@ -363,8 +393,21 @@ int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
                            double* d_out_ll, double* d_out_g_bias, double* d_out_g_w, void* stream)
 {
     DS_GUARD(ds);
-    return ll_grad_dev_impl(ds, d_bias, d_w, d_A, d_W, nlin, n_lo, n_hi, path, d_out_ll, d_out_g_bias, d_out_g_w,
-                            nullptr, nullptr, (cudaStream_t)stream);
+    TRY(ws_acquire(ds, (cudaStream_t)stream));
+    TRY(ll_grad_dev_impl(ds, d_bias, d_w, d_A, d_W, nlin, n_lo, n_hi, path, d_out_ll, d_out_g_bias, d_out_g_w,
+                         nullptr, nullptr, (cudaStream_t)stream));
+    return ws_release(ds, (cudaStream_t)stream);
+}
+
+int pyglm_b200_range_flags(const pyglm_b200_dataset* ds, int32_t* out_flags)
+{
+    DS_GUARD(ds);
+    PYGLM_REQUIRE(out_flags != nullptr, "range_flags: out is null");
+    for (int n = 0; n < ds->N; ++n) out_flags[n] = 0;
+    if (!ds->tc.colflag) return PYGLM_B200_OK;
+    PYGLM_CUDA(cudaDeviceSynchronize());
+    PYGLM_CUDA(cudaMemcpy(out_flags, ds->tc.colflag, (size_t)ds->N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return PYGLM_B200_OK;
 }
 
 // upload the parameter block of a host call into the handle's staging buffers
@@ -393,6 +436,7 @@ static int stage_params(pyglm_b200_dataset* ds, const double* bias, const double
 struct HostPtrs {
     const double* bias; const double* w; const int8_t* A; const double* W;
     double* ll; double* gb; double* gw;
+    unsigned* flags;
 };
 
 static int enqueue_host_call(pyglm_b200_dataset* ds, const HostPtrs& hp, int nlin, int n_lo, int n_hi, int path, cudaStream_t st)
@@ -410,6 +454,8 @@ static int enqueue_host_call(pyglm_b200_dataset* ds, const HostPtrs& hp, int nli
     PYGLM_CUDA(cudaMemcpyAsync(hp.ll, ds->o_ll.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (hp.gb) PYGLM_CUDA(cudaMemcpyAsync(hp.gb, ds->o_gb.p, ncols * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (hp.gw) PYGLM_CUDA(cudaMemcpyAsync(hp.gw, ds->o_gw.p, (size_t)ncols * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (hp.flags)   // range flags of the FP32 epilogues (exp nonlinearity on the tensor-core path)
+        PYGLM_CUDA(cudaMemcpyAsync(hp.flags + n_lo, ds->tc.colflag + n_lo, ncols * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     return PYGLM_B200_OK;
 }
 
@@ -447,22 +493,37 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
     // are; pageable ones go through the handle's own pinned staging.
     const bool direct = is_pinned_host(bias) && is_pinned_host(w) && is_pinned_host(A) && is_pinned_host(W) &&
                         is_pinned_host(out_ll) && is_pinned_host(out_g_bias) && is_pinned_host(out_g_w);
-    HostPtrs hp{bias, w, A, W, out_ll, out_g_bias, out_g_w};
+    // PATH_AUTO with the exp nonlinearity on the tensor-core path: the epilogue flags every column whose activation
+    // leaves the range in which FP32 e^x holds the tolerance; those columns are re-evaluated on the FP64 path below
+    const bool heal = path == PYGLM_B200_PATH_AUTO && nlin == PYGLM_B200_NLIN_EXP && ds->T > 0 &&
+                      ds->x_dtype != PYGLM_B200_X_PLANES && resolve_path(ds, path, false) == PYGLM_B200_PATH_TC;
+    if (heal && !h.flags) {
+        PYGLM_CUDA(cudaMallocHost(&h.flags, N * sizeof(unsigned)));
+        memset(h.flags, 0, N * sizeof(unsigned));
+    }
+    HostPtrs hp{bias, w, A, W, out_ll, out_g_bias, out_g_w, heal ? h.flags : nullptr};
     if (!direct) {
-        if (!h.bias) {
-            PYGLM_CUDA(cudaMallocHost(&h.bias, N * sizeof(double)));
-            PYGLM_CUDA(cudaMallocHost(&h.ll, N * sizeof(double)));
-            PYGLM_CUDA(cudaMallocHost(&h.gb, N * sizeof(double)));
-            PYGLM_CUDA(cudaMallocHost(&h.W, N * N * sizeof(double)));
-            PYGLM_CUDA(cudaMallocHost(&h.A, N * N));
-            PYGLM_CUDA(cudaMallocHost(&h.w, N * NF * sizeof(double)));
-            PYGLM_CUDA(cudaMallocHost(&h.gw, N * NF * sizeof(double)));
+        if (!h.staging_ready) {     // all or nothing: a failed allocation must not leave a half-built set behind
+            void** bufs[7] = {(void**)&h.bias, (void**)&h.ll, (void**)&h.gb, (void**)&h.W, (void**)&h.A, (void**)&h.w, (void**)&h.gw};
+            const size_t sizes[7] = {N * sizeof(double), N * sizeof(double), N * sizeof(double), N * N * sizeof(double), N * N,
+                                     N * NF * sizeof(double), N * NF * sizeof(double)};
+            for (int i = 0; i < 7; ++i) {
+                cudaError_t e = cudaMallocHost(bufs[i], sizes[i]);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    for (int j = 0; j < 7; ++j) { if (*bufs[j]) cudaFreeHost(*bufs[j]); *bufs[j] = nullptr; }
+                    set_error("ll_grad: page-locked staging allocation (%zu bytes) failed: %s", sizes[i], cudaGetErrorString(e));
+                    return PYGLM_B200_ENOMEM;
+                }
+            }
+            h.staging_ready = true;
         }
         memcpy(h.bias, bias, N * sizeof(double));
         memcpy(h.w, w, N * NF * sizeof(double));
         if (A) memcpy(h.A, A, N * N);
         if (W) memcpy(h.W, W, N * N * sizeof(double));
-        hp = HostPtrs{h.bias, h.w, A ? h.A : nullptr, W ? h.W : nullptr, h.ll, want_gb ? h.gb : nullptr, want_gw ? h.gw : nullptr};
+        hp = HostPtrs{h.bias, h.w, A ? h.A : nullptr, W ? h.W : nullptr, h.ll, want_gb ? h.gb : nullptr, want_gw ? h.gw : nullptr,
+                      heal ? h.flags : nullptr};
     }
 
     // the whole call is a CUDA graph from the second call with the same signature (and, for caller-pinned buffers,
@@ -471,6 +532,7 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
                                (long long)(uintptr_t)hp.bias, (long long)(uintptr_t)hp.w, (long long)(uintptr_t)hp.A,
                                (long long)(uintptr_t)hp.W, (long long)(uintptr_t)hp.ll, (long long)(uintptr_t)hp.gb,
                                (long long)(uintptr_t)hp.gw};
+    TRY(ws_acquire(ds, st));
     if (memcmp(key, h.key, sizeof(key)) != 0) {
         if (h.exec) { cudaGraphExecDestroy(h.exec); h.exec = nullptr; }
         memcpy(h.key, key, sizeof(key));
@@ -507,7 +569,26 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
     } else {
         TRY(enqueue_host_call(ds, hp, nlin, n_lo, n_hi, path, st));
     }
+    TRY(ws_release(ds, st));
     PYGLM_CUDA(cudaStreamSynchronize(st));
+    if (heal) {
+        for (int lo = n_lo; lo < n_hi;) {
+            if (!h.flags[lo]) { ++lo; continue; }
+            int hi = lo;
+            while (hi < n_hi && h.flags[hi]) ++hi;          // a run of flagged columns: one FP64 evaluation
+            const int off = lo - n_lo, nrun = hi - lo;
+            TRY(ll_grad_dev_impl(ds, ds->p_bias.p, ds->p_w.p, hp.A ? ds->p_A.p : nullptr, hp.W ? ds->p_W.p : nullptr,
+                                 nlin, lo, hi, PYGLM_B200_PATH_FP64, ds->o_ll.p + off, grad ? ds->o_gb.p + off : nullptr,
+                                 grad ? ds->o_gw.p + (size_t)off * NF : nullptr, nullptr, nullptr, st));
+            PYGLM_CUDA(cudaMemcpyAsync(hp.ll + off, ds->o_ll.p + off, nrun * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (hp.gb) PYGLM_CUDA(cudaMemcpyAsync(hp.gb + off, ds->o_gb.p + off, nrun * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (hp.gw) PYGLM_CUDA(cudaMemcpyAsync(hp.gw + (size_t)off * NF, ds->o_gw.p + (size_t)off * NF,
+                                                  (size_t)nrun * NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+            lo = hi;
+        }
+        TRY(ws_release(ds, st));
+        PYGLM_CUDA(cudaStreamSynchronize(st));
+    }
     if (!direct) {
         memcpy(out_ll, h.ll, ncols * sizeof(double));
         if (want_gb) memcpy(out_g_bias, h.gb, ncols * sizeof(double));

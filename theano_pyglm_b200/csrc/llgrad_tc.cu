@@ -66,6 +66,7 @@ constexpr int kFlushTiles = 8;              // TMEM gradient accumulators are fo
 void TcWorkspace::release()
 {
     cudaFree(Sp); Sp = nullptr;
+    cudaFree(colflag); colflag = nullptr;
     cudaFree(X1); cudaFree(X2); cudaFree(sx); cudaFree(colmax); cudaFree(Mp); cudaFree(colpar); cudaFree(part);
     X1 = X2 = nullptr; sx = nullptr; colmax = nullptr; Mp = nullptr; colpar = nullptr; part = nullptr;
     part_elems = 0; planes_ready = false;
@@ -185,6 +186,7 @@ struct TcKernelArgs {
     int debug;                     // timing experiments only (PYGLM_TC_DEBUG): skip phases
     unsigned producer_sleep_ns;
     long long* trace;              // optional [3][32][4] clock64 stamps of CTA 0 (PYGLM_TC_TRACE)
+    unsigned* flags;               // [N] range flags, or nullptr
 };
 
 struct TcSmem {
@@ -519,6 +521,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
             }
         };
         load_spikes(0, sb_next);
+        unsigned badmask = 0;                            // exp: columns of this warp whose activation left the FP32-safe range
 
         for (int it = 0; it < ntl; ++it) {
             const int b = it & 1;
@@ -551,6 +554,7 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
                 const float2 cp = cpar[c0 + c];
                 xs[c] = fmaf(fmaf(d1[c] + d2[c], 1.0f / kLoScale, d0[c]), cp.x, cp.y);
                 if (c0 + c < a.ncols) xmin = fminf(xmin, xs[c]);
+                if (NLIN == PYGLM_B200_NLIN_EXP && c0 + c < a.ncols && lv != 0.f && !(xs[c] <= kExpSafe)) badmask |= 1u << c;
             }
             const float dtl = a.dt * lv;                 // bins past the end of the recording contribute nothing
             if (NLIN == PYGLM_B200_NLIN_SOFTPLUS && __all_sync(0xffffffffu, xmin > 17.5f)) {
@@ -627,6 +631,10 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
         }
 
         if (ntl > 0) fold_gradient(ntl - 1);
+        if (NLIN == PYGLM_B200_NLIN_EXP && a.flags) {
+            badmask = __reduce_or_sync(0xffffffffu, badmask);
+            if (lane < kColsPerWarp && ((badmask >> lane) & 1u)) a.flags[a.n_lo + c0 + lane] = 1u;
+        }
 #pragma unroll
         for (int c = 0; c < kColsPerWarp; ++c) gp[(int64_t)row * kNcol + c0 + c] = gacc[c];
         if (a.nmt > 1) {
@@ -752,6 +760,8 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMalloc(&ws.Mp, (size_t)2 * kNcol * kMaxChunks * kChunkF * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.colpar, 2 * kNcol * sizeof(float)));
     ws.Np = (int)round_up(N, 32) + 32;            // slack: a column group may start anywhere below N
+    PYGLM_CUDA(cudaMalloc(&ws.colflag, (size_t)N * sizeof(unsigned)));
+    PYGLM_CUDA(cudaMemsetAsync(ws.colflag, 0, (size_t)N * sizeof(unsigned), stream));
     PYGLM_CUDA(cudaMalloc(&ws.Sp, (size_t)T * ws.Np));
     PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)T * ws.Np, stream));
     PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
@@ -861,7 +871,7 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         k.S = a.S; k.T = a.T; k.N = a.N; k.halo = a.halo; k.dt = (float)a.dt; k.nlin = a.nlin;
         k.n_lo = n_lo; k.ncols = nc; k.nch = nch; k.nmt = nmt; k.ntiles = ntiles; k.nfeat = NB;
         k.Sp = ws.Sp; k.Np = ws.Np;
-        k.Mp = ws.Mp; k.Kp = Kp; k.colpar = ws.colpar; k.part = ws.part;
+        k.Mp = ws.Mp; k.Kp = Kp; k.colpar = ws.colpar; k.part = ws.part; k.flags = a.flags;
         { const char* dbg = getenv("PYGLM_TC_DEBUG"); k.debug = dbg ? atoi(dbg) : 0; }
         { const char* sl = getenv("PYGLM_TC_SLEEP"); k.producer_sleep_ns = sl ? (unsigned)atoi(sl) : 0u; }
         { const char* fl = getenv("PYGLM_TC_FLUSH"); k.flush = fl ? std::max(1, atoi(fl)) : kFlushTiles; }

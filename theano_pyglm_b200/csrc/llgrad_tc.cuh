@@ -16,6 +16,7 @@ struct TcWorkspace {
     unsigned* colmax = nullptr;   // [NB] scratch for the scale search
     uint8_t* Sp = nullptr;        // [T][Np] zero-padded copy of the spikes (Np % 32 == 0)
     int Np = 0;
+    unsigned* colflag = nullptr;  // [N] range flags raised by the FP32 epilogues (exp nonlinearity, see kExpSafe)
     bool planes_ready = false;
     // per-call operands
     __half* Mp = nullptr;         // [2][32][Kp] split planes of the scaled weight matrix
@@ -35,6 +36,7 @@ struct TcArgs {
     int n_lo, ncols;
     const double* bias; const double* w; const int8_t* A; const double* W;
     double* out_ll; double* out_gb; double* out_gw;
+    unsigned* flags;              // [N] range flags (index = neuron) or nullptr
 };
 
 bool tc_supported(int64_t T, int N, int B, int x_dtype);

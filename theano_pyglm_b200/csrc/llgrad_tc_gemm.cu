@@ -139,6 +139,7 @@ struct GemmFwdArgs {
     __half* R; int64_t plane;          // residual planes: R1 at R, R2 at R + plane; row pitch Npr
     double* part;                      // [nctas][4 quarters][Npr][2]
     float dt;
+    unsigned* flags;                   // [N] range flags (exp nonlinearity, kExpSafe) or nullptr
 };
 
 // MODE 0: one CTA per 128 x 128 tile.
@@ -358,6 +359,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     else mbar_arrive(&bar_acc_empty[ab]);
                 }
             }
+            unsigned badmask = 0;
             __half* r1row = a.R + (t < a.T ? t : 0) * a.Npr + col0;
             __half* r2row = r1row + a.plane;
 #pragma unroll
@@ -371,6 +373,7 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     float term = 0.f, r = 0.f;
                     if (col0 + cc < a.ncols && !(a.debug & 4)) {                     // warp-uniform
                         const float x = fmaf(act[cc], ism, bc);
+                        if (NLIN == PYGLM_B200_NLIN_EXP && lv != 0.f && !(x <= kExpSafe)) badmask |= 1u << cc;
                         poisson_terms<NLIN>(x, (float)((sp[cc >> 2] >> ((cc & 3) * 8)) & 0xffu), a.dt, term, r);
                         term *= lv;
                         r *= lv;
@@ -399,6 +402,10 @@ tc_gemm_fwd_kernel(const __grid_constant__ CUtensorMap mapX1, const __grid_const
                     slot[0] += (double)sl;
                     slot[1] += (double)sg;
                 }
+            }
+            if (NLIN == PYGLM_B200_NLIN_EXP && a.flags) {
+                badmask = __reduce_or_sync(0xffffffffu, badmask);
+                if (((badmask >> lane) & 1u) && col0 + lane < a.ncols) a.flags[a.n_lo + col0 + lane] = 1u;
             }
         }
     }
@@ -639,6 +646,7 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     if ((rc = tc_make_map_2d(&mM2, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, chunkf, kGN, mode == 3))) return rc;
 
     GemmFwdArgs f{};
+    f.flags = a.flags;
     f.Sp = ws.Sp; f.Nps = ws.Np; f.T = a.T; f.n_lo = a.n_lo; f.ncols = a.ncols; f.Npr = Npr; f.nkc = nkc;
     // up to ~1500 features one segment is accurate enough (measured: 7e-7 on ll, 2e-6 on gradients at 1280 features,
     // exp model) and costs nothing; beyond that the K loop is cut into 256-feature segments (~9 % slower, 70x more accurate

@@ -9,6 +9,10 @@ namespace pyglm {
 
 constexpr float kLoScale = 2048.0f;         // 2^11 between the two planes
 constexpr float kRScale = 64.0f;            // residual planes carry r * 2^6
+// exp nonlinearity, FP32 epilogue: e^x carries a relative error |x| 2^-24 and the residual planes saturate near
+// lam = 10^6, so a column whose activation leaves x <= 16 (a rate of e^16 = 9e6 Hz) is flagged and the caller
+// re-evaluates it on the FP64 path (pyglm_b200_ll_grad, PATH_AUTO); NaN / +inf activations are flagged too
+constexpr float kExpSafe = 16.0f;
 constexpr uint32_t kSw64 = 4;               // UMMA LayoutType::SWIZZLE_64B
 constexpr uint32_t kSw128 = 2;              // UMMA LayoutType::SWIZZLE_128B
 

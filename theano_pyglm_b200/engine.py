@@ -25,7 +25,8 @@ EXPORTS = [
     "pyglm_b200_dataset_num_stim", "pyglm_b200_filter_dense", "pyglm_b200_dataset_info",
     "pyglm_b200_dataset_get_fS", "pyglm_b200_dataset_device_X", "pyglm_b200_dataset_device_S",
     "pyglm_b200_dataset_refilter",
-    "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_firing_rate",
+    "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_range_flags",
+    "pyglm_b200_firing_rate",
     "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_delta_ll_dev", "pyglm_b200_gibbs_commit",
     "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
     "pyglm_b200_comm_create", "pyglm_b200_comm_export", "pyglm_b200_comm_connect", "pyglm_b200_allreduce_sum_dev",
@@ -69,6 +70,7 @@ def load_library():
     lib.pyglm_b200_ll_grad.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p]
     lib.pyglm_b200_ll_grad_dev.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p, p]
     lib.pyglm_b200_resolve_path.argtypes = [p, i32]
+    lib.pyglm_b200_range_flags.argtypes = [p, p]
     lib.pyglm_b200_firing_rate.argtypes = [p, p, p, p, p, i32, i32, i32, p]
     lib.pyglm_b200_gibbs_begin.argtypes = [p, p, p, p, p, i32, i32, i32]
     lib.pyglm_b200_gibbs_delta_ll.argtypes = [p, i32, p, p, i32, p, p]
@@ -249,6 +251,13 @@ class Dataset:
                                                      vp(d_W) if d_W else None, nlin_code(nlin), n_lo, n_hi,
                                                      _PATHS.get(path, path), vp(d_ll), vp(d_gb) if d_gb else None,
                                                      vp(d_gw) if d_gw else None, vp(stream)))
+
+    def range_flags(self):
+        """int32 (N,): 1 for every neuron whose activation left the FP32-safe range of the exp nonlinearity in the last
+        tensor-core evaluation (the host call with path="auto" has already re-evaluated those in FP64)."""
+        out = np.zeros(self.N, dtype=np.int32)
+        _check(load_library().pyglm_b200_range_flags(self._h, _ptr(out)))
+        return out
 
     def path_info(self, path="auto"):
         """What a call with `path` runs on this dataset (used by bench.py's roofline bookkeeping)."""
