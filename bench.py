@@ -11,7 +11,10 @@ With --gpus G (torchrun, one rank per GPU) every rank owns its own T=10^6-bin se
 one-shot all-reduce over NVLink peer memory (csrc/allreduce.cu; --allreduce nccl uses NCCL instead) --
 exactly as the reference sums ll over data sequences (coord_descent.py:52-57).
 
-Prints ONE JSON line on rank 0 (contract in the task statement).
+Prints ONE JSON line on rank 0 (contract in the task statement).  At one GPU the line also carries an `extra`
+array -- the other half of BASELINE.json's metric and the larger configurations, each with its own roofline, e2e,
+clocks and cpu_baseline: the K1 filter, C3 ll+grad (tensor-bound GEMM path), C3 Gibbs edge-sweeps/s, and one of eight
+time shards of C4 (`--no-extra` skips them).
 """
 from __future__ import annotations
 
@@ -129,6 +132,16 @@ def load_tensor_peak():
     return 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_config(wl):
+    """The `config` object of the JSON line: the workload and nothing measured, identical in both arms."""
+    return {"workload": wl["desc"], "N": wl["N"], "T_bins_per_gpu": wl["T"], "B": wl["B"], "R": 200, "nlin": "explinear",
+            "l2": "inputs_exceed_l2"}
+
+
+def median_block(times):
+    return float(np.median(np.asarray(times, dtype=np.float64)))
+
+
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle port timed on the host cores (bench.py may execute oracle/ only here)
 # --------------------------------------------------------------------------------------
@@ -164,11 +177,13 @@ def cpu_eval_time(inp, wl, T_sample, budget_s, shape="gemm"):
 
 
 def run_reference(args, wl):
+    """The CPU arm: the float64 oracle port of the reference's path, whole-population BLAS form, ALL bins of the
+    workload every step (no extrapolation), all host cores.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     inp = make_inputs(wl, seed=1234)
-    T_sample = min(wl["T"], 500_000 if wl["N"] <= 64 else 50_000)
+    T_sample = wl["T"] if wl["N"] <= 64 else min(wl["T"], 50_000)
     scale = wl["T"] / T_sample
     cores = os.cpu_count() or 1
     fn = cpu_prepare(inp, wl, T_sample, "gemm")
@@ -179,13 +194,14 @@ def run_reference(args, wl):
         fn()
     dt_step = (time.perf_counter() - t0) / args.steps
     value = 1.0 / (dt_step * scale)
-    sample = ("first %d of %d bins per step, whole-population BLAS GEMM form of the float64 oracle "
-              "(filter excluded, like our arm); evals/s scaled by %d/%d" % (T_sample, wl["T"], T_sample, wl["T"]))
+    sample = ("every step evaluates all %d bins" % wl["T"] if scale == 1 else
+              "first %d of %d bins per step, evals/s scaled by %d/%d" % (T_sample, wl["T"], T_sample, wl["T"])) + \
+             "; float64 oracle port, whole-population BLAS GEMM form (filter excluded: resident data in both arms)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt_step * scale * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"]},
+        "config": workload_config(wl),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -195,6 +211,105 @@ def run_reference(args, wl):
 # --------------------------------------------------------------------------------------
 # Our arm
 # --------------------------------------------------------------------------------------
+class Timer:
+    """Device timing of K-step blocks: barrier + synchronize on both sides, CUDA events on the launching stream, max
+    over ranks.  `blocks()` repeats the K-step block until the timed total reaches `min_total_s` and reports the
+    median block (each block is exactly K steps)."""
+
+    def __init__(self, torch, dist, world, dev, stream):
+        self.torch, self.dist, self.world, self.dev, self.stream = torch, dist, world, dev, stream
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def block(self, fn, steps):
+        torch = self.torch
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(self.stream)
+        for _ in range(steps):
+            fn()
+        ev1.record(self.stream)
+        self.barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def blocks(self, fn, steps, min_total_s=0.5, max_blocks=400):
+        times = [self.block(fn, steps)]
+        n = int(min(max_blocks, max(1, np.ceil(min_total_s * 1e3 / max(times[0], 1e-3)))))
+        if self.world > 1:                   # every rank must run the same number of blocks
+            nt = self.torch.tensor([n], device=self.dev)
+            self.dist.all_reduce(nt, op=self.dist.ReduceOp.MAX)
+            n = int(nt.item())
+        for _ in range(n - 1):
+            times.append(self.block(fn, steps))
+        return median_block(times), times
+
+
+def wall_blocks(fn, steps, sync, min_total_s=0.5, max_blocks=400):
+    """Wall-clock timing of K-step blocks of a call that synchronises itself; median block in ms."""
+    times = []
+    while len(times) < max_blocks and (not times or sum(times) < min_total_s * 1e3):
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        sync()
+        times.append((time.perf_counter() - t0) * 1e3)
+    return median_block(times), times
+
+
+def llgrad_roofline(ds, wl, ms_kernel, path, workload_key):
+    """roofline object of the ll+grad launch sequence: algorithmic bytes (HBM-bound fused kernel) or flops (GEMM path)."""
+    N, T, B = wl["N"], wl["T"], wl["B"]
+    NB = N * B
+    peak, peak_src = load_peaks()
+    info = ds.path_info(path)
+    x_bytes = T * ds.ldx * 4
+    passes = info.get("x_passes", 2)
+    alg_bytes = passes * x_bytes + T * N + 16 * N * NB          # X once per contraction pass + S once + params/outputs
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    traffic = None          # dram__bytes_read+write of the dominant kernel, from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(info.get("kernel", ""), {}).get(workload_key)
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": info.get("kernel"), "peak_source": peak_src, "kernel_ms": ms_kernel,
+            "algorithmic_bytes": alg_bytes}
+    if info.get("bound") == "tensor":
+        # algorithmic flops of one eval: two contractions, 2 flop per MAC (SURVEY 8d); the split executes 3x as many
+        tpeak, tsrc = load_tensor_peak()
+        alg_flops = 4.0 * T * N * N * B
+        tf = alg_flops / (ms_kernel * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                "traffic": traffic, "kernel": info.get("kernel"), "peak_source": tsrc, "kernel_ms": ms_kernel,
+                "algorithmic_flops": alg_flops, "executed_over_algorithmic": 3.0,
+                "note": "each contraction runs as 3 FP16 products of the error-free operand splits"}
+    return roof, info
+
+
+def llgrad_cpu_baseline(inp, wl, budget_s):
+    """The float64 oracle on the host cores, bounded sample; BLAS-GEMM form plus the reference-shaped per-neuron loop."""
+    N, T = wl["N"], wl["T"]
+    T_s = min(T, 500_000 if N <= 64 else (50_000 if N <= 256 else 8_000))
+    t_gemm, n_gemm = cpu_eval_time(inp, wl, T_s, budget_s, "gemm")
+    t_gemm *= T / T_s
+    T_r = min(T, 100_000 if N <= 64 else (10_000 if N <= 256 else 2_000))
+    t_ref, n_ref = cpu_eval_time(inp, wl, T_r, budget_s / 2, "reference") if N <= 256 else (float("nan"), 0)
+    t_ref *= T / T_r
+    return {"value": 1.0 / t_gemm, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": "float64 oracle, whole-population BLAS GEMM form: mean of %d evals on the first %d of %d bins "
+                      "(~%d s of CPU work), scaled to the full recording; reference-shaped per-neuron loop "
+                      "(impulse.py:58 style, %d evals on %d bins, scaled): %.4g evals/s"
+                      % (n_gemm, T_s, T, budget_s, n_ref, T_r, 1.0 / t_ref),
+            "reference_shaped_value": None if n_ref == 0 else 1.0 / t_ref}
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -227,12 +342,30 @@ def run_ours(args, wl):
             else:
                 collective = "one-shot all-reduce over NVLink peer memory (allreduce_kernel)"
 
+    stream = torch.cuda.current_stream()
+    timer = Timer(torch, dist, world, dev, stream)
+    rec = llgrad_record(args, wl, args.workload, pg, torch, dist, timer, world, rank, local_rank, comm, collective,
+                        min_total_s=0.5, cpu_budget_s=0.0 if args.no_cpu else 10.0)
+    if rank == 0:
+        line = rec
+        if world == 1 and not args.no_extra and args.workload == "c2":
+            line["extra"] = run_extras(args, pg, torch, dist, timer, local_rank)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, local_rank, comm, collective,
+                  min_total_s, cpu_budget_s):
+    """One ll+grad workload measured three ways: device-resident steps (`value`), the reference-facing host-buffer call
+    (`e2e`), and the launch sequence alone (roofline).  Returns the JSON record on rank 0 (None elsewhere)."""
+    dev = timer.dev
+    stream = timer.stream
     N, T, B = wl["N"], wl["T"], wl["B"]
     NB = N * B
     inp = make_inputs(wl, seed=1234 + rank)      # every rank owns its own sequence (time shard)
     t_ing0 = time.perf_counter()
     ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank, x_dtype=wl.get("x_dtype", "f32"))
-    ingest_s = time.perf_counter() - t_ing0
     path = args.path
     nlin = "explinear"
 
@@ -241,15 +374,21 @@ def run_ours(args, wl):
     d_w = torch.from_numpy(inp["w"]).to(dev)
     d_out = torch.zeros(N * (2 + NB), dtype=torch.float64, device=dev)    # [ll | g_bias | g_w]
     d_ll, d_gb, d_gw = d_out[:N], d_out[N:2 * N], d_out[2 * N:]
-    stream = torch.cuda.current_stream()
 
-    def step_dev():
+    def step_kernel():
         ds.ll_grad_dev(d_bias.data_ptr(), d_w.data_ptr(), 0, 0, nlin, 0, N, path,
                        d_ll.data_ptr(), d_gb.data_ptr(), d_gw.data_ptr(), stream.cuda_stream)
+
+    def step_dev():
+        step_kernel()
         if comm is not None:                # sum of the time shards' partial ll / gradients
             comm.allreduce_sum_dev(d_out.data_ptr(), d_out.data_ptr(), d_out.numel(), stream.cuda_stream)
         elif world > 1:
             dist.all_reduce(d_out)
+
+    step_kernel()                            # first call builds the split planes (part of ingest)
+    torch.cuda.synchronize()
+    ingest_s = time.perf_counter() - t_ing0
 
     # host-buffer path (e2e): pinned parameter upload, eval, result download every step
     h_bias = torch.from_numpy(inp["bias"]).pin_memory()
@@ -279,43 +418,23 @@ def run_ours(args, wl):
         h_out.copy_(e_out, non_blocking=True)
         stream.synchronize()                # the caller reads ll / gradient on the host every step
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        for _ in range(steps):
-            fn()
-        ev1.record(stream)
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
-
     for _ in range(max(args.warmup, 3)):
         step_dev()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_dev = timed(step_dev, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_dev, dev_blocks = timer.blocks(step_dev, args.steps, min_total_s)
+    # dominant-kernel timing for the roofline: the ll+grad launch sequence alone (no collective), same clock window
+    ms_kernel = (timer.blocks(step_kernel, args.steps, min_total_s)[0] if world > 1 else ms_dev) / args.steps
     for _ in range(3):
         step_e2e()
     if world == 1:                          # the call synchronises on the handle's own stream: wall clock is the measure
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
-        ms_e2e = (time.perf_counter() - t0) * 1e3
+        ms_e2e, e2e_blocks = wall_blocks(step_e2e, args.steps, torch.cuda.synchronize, min_total_s)
         if not np.array_equal(h_out[:N].numpy(), d_ll.cpu().numpy()):
             raise SystemExit("host-buffer call and device-resident call disagree")
     else:
-        ms_e2e = timed(step_e2e, args.steps)
+        ms_e2e, e2e_blocks = timer.blocks(step_e2e, args.steps, min_total_s)
+    clocks = sampler.stop() if rank == 0 else None
 
     # the same evaluation through the host-buffer C-ABI call a Python user makes (numpy in, numpy out; the library
     # stages through its own pinned buffers and replays a CUDA graph): wall clock, single GPU only
@@ -323,46 +442,17 @@ def run_ours(args, wl):
     if world == 1:
         for _ in range(3):
             ds.ll_grad(inp["bias"], inp["w"], nlin=nlin, path=path)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            ds.ll_grad(inp["bias"], inp["w"], nlin=nlin, path=path)
-        host_entry = args.steps / (time.perf_counter() - t0)
-
-    # dominant-kernel timing for the roofline: the ll+grad launch sequence alone (no collective)
-    def step_kernel():
-        ds.ll_grad_dev(d_bias.data_ptr(), d_w.data_ptr(), 0, 0, nlin, 0, N, path,
-                       d_ll.data_ptr(), d_gb.data_ptr(), d_gw.data_ptr(), stream.cuda_stream)
-    ms_kernel = timed(step_kernel, args.steps) / args.steps
+        ms_he, _ = wall_blocks(lambda: ds.ll_grad(inp["bias"], inp["w"], nlin=nlin, path=path), args.steps,
+                               torch.cuda.synchronize, min(min_total_s, 0.3))
+        host_entry = args.steps / (ms_he * 1e-3)
 
     ll_host = d_ll.cpu().numpy()
     if not np.all(np.isfinite(ll_host)):
         raise SystemExit("non-finite log-likelihood in the benchmark run")
 
+    line = None
     if rank == 0:
-        peak, peak_src = load_peaks()
-        info = ds.path_info(path) if hasattr(ds, "path_info") else {}
-        x_bytes = T * ds.ldx * 4
-        # algorithmic bytes per eval: X read once per contraction pass + S once + params/outputs
-        passes = info.get("x_passes", 2)
-        alg_bytes = passes * x_bytes + T * N + 16 * N * NB
-        achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
-        traffic = None          # dram__bytes_read+write of the dominant kernel, from the committed ncu capture
-        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(info.get("kernel", ""), {}).get(args.workload)
-        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": info.get("kernel"), "peak_source": peak_src, "kernel_ms": ms_kernel,
-                "algorithmic_bytes": alg_bytes}
-        if info.get("bound") == "tensor":
-            # algorithmic flops of one eval: two contractions, 2 flop per MAC; the split executes 3x as many
-            tpeak, tsrc = load_tensor_peak()
-            alg_flops = 4.0 * T * N * N * B
-            tf = alg_flops / (ms_kernel * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                    "traffic": traffic, "kernel": info.get("kernel"), "peak_source": tsrc, "kernel_ms": ms_kernel,
-                    "algorithmic_flops": alg_flops, "executed_over_algorithmic": 3.0,
-                    "note": "each contraction runs as 3 FP16 products of the error-free operand splits"}
+        roof, info = llgrad_roofline(ds, wl, ms_kernel, path, workload_key)
         per_step = ms_dev / args.steps
         h2d = (N + N * NB) * 8
         d2h = N * (2 + NB) * 8
@@ -371,12 +461,14 @@ def run_ours(args, wl):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": info.get("dtype", "f64"), "data": "synthetic",
-            "config": {"workload": wl["desc"], "N": N, "T_bins_per_gpu": T, "B": B, "R": 200, "nlin": "explinear",
-                       "path": info.get("name", path), "l2": "inputs_exceed_l2 (X is %d MB per GPU)" % (x_bytes >> 20),
-                       "sharding": "time-sharded: one T-bin sequence per GPU, allreduce(sum) of ll/grad partials"
-                       if world > 1 else "single GPU",
-                       "collective": collective,
-                       "ingest_s_incl_filter": ingest_s},
+            "config": workload_config(wl),
+            "details": {"path": info.get("name", path), "x_bytes_per_gpu": T * ds.ldx * 4,
+                        "sharding": "time-sharded: one T-bin sequence per GPU, allreduce(sum) of ll/grad partials"
+                        if world > 1 else "single GPU",
+                        "collective": collective, "ingest_s_incl_filter_and_planes": ingest_s,
+                        "timing": "median of %d blocks of %d steps (each block: barrier + synchronize both sides, CUDA events, "
+                                  "max over ranks); timed total %.2f s" % (len(dev_blocks), args.steps, sum(dev_blocks) * 1e-3),
+                        "block_ms_min_max": [min(dev_blocks), max(dev_blocks)]},
             "clocks": clocks,
             "e2e": {"value": world / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -384,30 +476,84 @@ def run_ours(args, wl):
                              "ll / gradients replayed as one CUDA graph, one synchronise per step") if world == 1 else
                             ("pyglm_b200_ll_grad_dev + all-reduce between a pinned-host upload of the parameters and a "
                              "pinned-host download of ll / gradients, one stream synchronise per step"),
-                    "host_entry_value": host_entry,
+                    "blocks": len(e2e_blocks), "host_entry_value": host_entry,
                     "host_entry_call": "pyglm_b200_ll_grad with pageable numpy arrays in and out (staged by the library), wall clock"},
             "gpu_launches": (int(info.get("launches_per_eval", 5)) + (1 if comm is not None else 0)) * args.steps,
             "roofline": roof,
         }
-        # CPU baseline on a bounded sample (rank 0, N=1 only)
-        if world == 1 and not args.no_cpu:
-            T_s = min(T, 500_000 if N <= 64 else 50_000)
-            t_gemm, n_gemm = cpu_eval_time(inp, wl, T_s, 10.0, "gemm")
-            t_gemm *= T / T_s
-            T_r = min(T, 100_000 if N <= 64 else 10_000)
-            t_ref, n_ref = cpu_eval_time(inp, wl, T_r, 5.0, "reference")
-            t_ref *= T / T_r
-            line["cpu_baseline"] = {
-                "value": 1.0 / t_gemm, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                "sample": "float64 oracle, whole-population BLAS GEMM form: mean of %d evals on the first %d of %d bins "
-                          "(~10 s of CPU work), scaled to the full recording; reference-shaped per-neuron loop "
-                          "(impulse.py:58 style, %d evals on %d bins, scaled): %.4g evals/s"
-                          % (n_gemm, T_s, T, n_ref, T_r, 1.0 / t_ref),
-                "reference_shaped_value": 1.0 / t_ref}
-        print(json.dumps(line), flush=True)
+        if world == 1 and cpu_budget_s > 0:              # CPU baseline on a bounded sample (rank 0, N=1 only)
+            line["cpu_baseline"] = llgrad_cpu_baseline(inp, wl, cpu_budget_s)
     ds.close()
-    if world > 1:
-        dist.destroy_process_group()
+    del d_bias, d_w, d_out, e_bias, e_w, e_out
+    torch.cuda.empty_cache()
+    return line
+
+
+def filter_record(args, pg, torch, timer, local_rank):
+    """K1 alone on the C2 recording: spikes resident, X (FP32) rewritten every step."""
+    wl = WORKLOADS["c2"]
+    N, T, B = wl["N"], wl["T"], wl["B"]
+    inp = make_inputs(wl, 1234)
+    ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank)
+    stream = timer.stream
+    step = lambda: ds.refilter(stream.cuda_stream)
+    for _ in range(3):
+        step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, blocks = timer.blocks(step, args.steps, 0.3)
+    clocks = sampler.stop()
+    ms /= args.steps
+    # e2e: host spikes in (pageable numpy), filtered spike train resident on return: dataset_create
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank).close()
+    ms_e2e = (time.perf_counter() - t0) / reps * 1e3
+    peak, peak_src = load_peaks()
+    alg = T * N + T * ds.ldx * 4
+    rec = {"name": "k1-filter-c2", "metric": "spike-history filter passes/sec", "value": 1e3 / ms, "unit": "passes/s",
+           "ms_per_step": ms, "steps": args.steps, "blocks": len(blocks), "dtype": "u8 in, f64 accumulate, f32 out",
+           "config": dict(workload_config(wl), workload="K1 on " + wl["desc"]), "clocks": clocks,
+           "e2e": {"value": 1e3 / ms_e2e, "unit": "passes/s", "h2d_bytes_per_step": int(inp["S"].nbytes), "d2h_bytes_per_step": 0,
+                   "call": "pyglm_b200_dataset_create: upload of the uint8 spikes, K1, spike transpose; synchronous"},
+           "gpu_launches": args.steps,
+           "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "filter_kernel",
+                        "peak_source": peak_src, "kernel_ms": ms, "algorithmic_bytes": alg}}
+    if not args.no_cpu:
+        from oracle import pyglm_oracle as orc
+        T_s = 200_000
+        Ssub = inp["S"][:T_s].astype(np.float64)
+        t0 = time.perf_counter()
+        orc.convolve_with_basis(Ssub, inp["ibasis"])          # the reference's own call (B FFT convolutions)
+        t_cpu = (time.perf_counter() - t0) * T / T_s
+        rec["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": "passes/s", "cores": 1, "kind": "port",
+                               "sample": "scipy.signal.fftconvolve form of utils/basis.py:201-236 on the first %d of %d bins, scaled" % (T_s, T)}
+    ds.close()
+    return rec
+
+
+def run_extras(args, pg, torch, dist, timer, local_rank):
+    """The rest of BASELINE.json's metric in the same line: K1, C3 ll+grad, C3 Gibbs sweeps/s, a C4 time shard."""
+    out = []
+    jobs = [("k1-filter-c2", lambda: filter_record(args, pg, torch, timer, local_rank)),
+            ("c3", lambda: llgrad_record(args, WORKLOADS["c3"], "c3", pg, torch, dist, timer, 1, 0, local_rank, None,
+                                         "none (single GPU)", 0.3, 0.0 if args.no_cpu else 6.0)),
+            ("c3-gibbs", lambda: gibbs_record(args, WORKLOADS["c3-gibbs"], "c3-gibbs", 0.3)),
+            ("c4-shard", lambda: llgrad_record(args, WORKLOADS["c4-shard"], "c4-shard", pg, torch, dist, timer, 1, 0, local_rank,
+                                               None, "none (single GPU)", 0.3, 0.0 if args.no_cpu else 6.0))]
+    for name, job in jobs:
+        t0 = time.perf_counter()
+        try:
+            rec = job()
+            rec["name"] = name
+            rec["wall_s"] = time.perf_counter() - t0
+        except Exception as exc:                          # an extra must never cost the headline line
+            rec = {"name": name, "error": "%s: %s" % (type(exc).__name__, exc)}
+        out.append(rec)
+        torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -433,7 +579,11 @@ def make_gibbs_inputs(wl, seed):
     return dict(S=S, ibasis=ib, bias=bias, w=w, A=A, W=W, dt=0.001, rho=rho)
 
 
-def run_gibbs(args, wl):
+def gibbs_record(args, wl, workload_key, min_total_s=0.5):
+    """Collapsed Gibbs over A/W at one GPU: the batched delta-ll kernel (device-timed `value`), and one lock-step of the
+    sweep through the host-buffer calls (`e2e`: candidates in, 11 log-likelihoods out, host decision rule, commit).
+    ARS probes for W | A = 1 are NOT part of either figure (each is one more Q = 1 delta-ll launch; hips' ARS is
+    un-vendored, so their number per accepted edge is not defined by the reference tree): W comes from the prior."""
     import torch
     import theano_pyglm_b200 as pg
     from scipy.special import logsumexp
@@ -458,9 +608,12 @@ def run_gibbs(args, wl):
         return np.concatenate([np.sqrt(2) * sig * xs[None, :] + mu, np.zeros((N, 1))], axis=1), mu[:, 0], sig[:, 0]
 
     pA = np.where(np.eye(N, dtype=bool), 1.0 - 1e-8, inp["rho"])
+    counter = [0]
 
-    def step_e2e(s):
+    def step_e2e():
         """One lock-step of the sweep: every column resamples its s-th edge (host buffers in and out)."""
+        s = counter[0]
+        counter[0] += 1
         pres = orders[:, s % N].astype(np.int32)
         cand, mu, sig = candidates(pres)
         ll = ds.gibbs_delta_ll(cols, pres, cand)                        # (N, 11)
@@ -479,6 +632,7 @@ def run_gibbs(args, wl):
     d_cand = torch.from_numpy(candidates(pres0)[0]).to(dev)
     d_out = torch.empty((N, Q), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream()
+    timer = Timer(torch, None, 1, dev, stream)
 
     def step_dev():
         ds.gibbs_delta_ll_dev(N, d_cols.data_ptr(), d_pres.data_ptr(), Q, d_cand.data_ptr(), d_out.data_ptr(),
@@ -489,21 +643,13 @@ def run_gibbs(args, wl):
     torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_dev()
-    e1.record(stream)
-    torch.cuda.synchronize()
+    ms_blk, blocks = timer.blocks(step_dev, args.steps, min_total_s, max_blocks=50)
+    ms_dev = ms_blk / args.steps
+    for _ in range(2):
+        step_e2e()
+    ms_e2e_blk, _ = wall_blocks(step_e2e, args.steps, torch.cuda.synchronize, min_total_s, max_blocks=20)
+    ms_e2e = ms_e2e_blk / args.steps
     clocks = sampler.stop()
-    ms_dev = e0.elapsed_time(e1) / args.steps
-    for s in range(2):
-        step_e2e(s)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        step_e2e(2 + s)
-    torch.cuda.synchronize()
-    ms_e2e = (time.perf_counter() - t0) / args.steps * 1e3
 
     peak, peak_src = load_peaks()
     alg_bytes = N * T * (8 + B * 8 + 1)          # per edge and bin: I_net f64 + X slice f64 + spike byte
@@ -512,16 +658,23 @@ def run_gibbs(args, wl):
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            gibbs_traffic = json.load(f).get("gibbs_delta_kernel", {}).get(args.workload)
+            gibbs_traffic = json.load(f).get("gibbs_delta_kernel", {}).get(workload_key)
     # FP64 work per bin: Q softplus evaluations of 21 fused operations + the u / base current (B + 2)
     fp64_flops = 2.0 * N * T * (Q * 21 + B + 2)
+    try:
+        fp64_peak, fp64_src = pg.engine.measure_fp64_peak(0), "measured here: register-resident DFMA loop (pyglm_b200_measure_fp64_peak)"
+    except Exception:
+        fp64_peak, fp64_src = 40.0, "nominal B200 FP64 (probe unavailable)"
     line = {
         "metric": "Gibbs edge-sweeps/sec", "value": 1.0 / (N * ms_dev * 1e-3), "unit": "sweeps/s", "n_gpus": 1,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "N": N, "T_bins": T, "B": B, "candidates_per_edge": Q,
-                   "step": "one lock-step = N edges (one per column) x 11 candidate weights; a sweep is N steps",
-                   "edges_per_s": N / (ms_dev * 1e-3), "l2": "inputs_exceed_l2"},
+        "config": {"workload": wl["desc"], "N": N, "T_bins_per_gpu": T, "B": B, "R": 200, "nlin": "explinear",
+                   "candidates_per_edge": Q, "l2": "inputs_exceed_l2"},
+        "details": {"step": "one lock-step = N edges (one per column) x 11 candidate weights; a sweep is N steps",
+                    "edges_per_s": N / (ms_dev * 1e-3), "blocks": len(blocks),
+                    "ars": "excluded: W | A=1 is drawn from the prior in this benchmark (hips ARS is un-vendored; each probe "
+                           "would be one more Q=1 launch of the same kernel)"},
         "clocks": clocks,
         "e2e": {"value": 1.0 / (N * ms_e2e * 1e-3), "unit": "sweeps/s",
                 "h2d_bytes_per_step": N * (4 + 4 + Q * 8) + N * (4 + 4 + 1 + 8), "d2h_bytes_per_step": N * Q * 8,
@@ -531,9 +684,8 @@ def run_gibbs(args, wl):
                      "traffic": gibbs_traffic, "kernel": "gibbs_delta_kernel", "peak_source": peak_src, "kernel_ms": ms_dev,
                      "algorithmic_bytes": alg_bytes,
                      "note": "FP64-ALU bound, not HBM (SURVEY.md 8d): the second figure is the FP64 rate",
-                     "fp64": {"achieved": fp64_flops / (ms_dev * 1e-3) / 1e12, "peak": 40.0, "unit": "TFLOP/s",
-                              "frac": fp64_flops / (ms_dev * 1e-3) / 1e12 / 40.0,
-                              "peak_source": "nominal B200 FP64 (not in MEASURED_PEAKS.json)"}},
+                     "fp64": {"achieved": fp64_flops / (ms_dev * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                              "frac": fp64_flops / (ms_dev * 1e-3) / 1e12 / fp64_peak, "peak_source": fp64_src}},
     }
     if not args.no_cpu:
         from oracle import pyglm_oracle as orc
@@ -550,9 +702,14 @@ def run_gibbs(args, wl):
         line["cpu_baseline"] = {"value": 1.0 / (t_edge * N * N), "unit": "sweeps/s", "cores": 1, "kind": "port",
                                 "sample": "11 delta-ll evaluations (gibbs.py:910-937 restated, numpy float64) for one "
                                           "edge on the first %d of %d bins, scaled to N^2 edges" % (T_s, T)}
-    print(json.dumps(line), flush=True)
     ds.gibbs_end()
     ds.close()
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_gibbs(args, wl):
+    print(json.dumps(gibbs_record(args, wl, args.workload)), flush=True)
 
 
 def main():
@@ -564,6 +721,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--path", default="auto", choices=["auto", "fp64", "tc"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra workloads of the default (c2, one GPU) line")
     ap.add_argument("--allreduce", default="p2p", choices=["p2p", "nccl"],
                     help="collective of the time-sharded run: peer-memory one-shot kernel (default) or NCCL")
     args = ap.parse_args()

@@ -250,6 +250,12 @@ PYGLM_B200_API int pyglm_b200_allreduce_sum_dev(pyglm_b200_comm* comm, const dou
                                  int64_t n, void* stream);
 PYGLM_B200_API int pyglm_b200_comm_destroy(pyglm_b200_comm* comm);
 
+/* ------------------------------------------------------------------------------------
+ * Measurement helper (bench.py): FP64 FMA throughput of this GPU's CUDA cores in TFLOP/s, from a register-resident
+ * DFMA loop -- the roofline denominator of the Gibbs delta-ll kernel, which MEASURED_PEAKS.json does not carry.
+ * ---------------------------------------------------------------------------------- */
+PYGLM_B200_API int pyglm_b200_measure_fp64_peak(int32_t device, double* out_tflops);
+
 #ifdef __cplusplus
 }
 #endif

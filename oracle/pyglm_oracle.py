@@ -153,37 +153,55 @@ def nlin(x, nlin_type):
     return nlin_and_derivative(x, nlin_type)[0]
 
 
+def _softplus_parts(x):
+    """lam = log(1+e^x), f' = sigmoid(x), log lam and f'/lam, each formed stably.  For x < -30, lam = e q with
+    q = log1p(e)/e = 1 - e/2 + e^2/3 - ..., so log lam = x + log q and f'/lam = 1/((1+e) q) stay finite however negative
+    x is.  (The reference's literal log(log(1+exp(x))) is -inf below x ~ -37 and its ll NaN there; its callers map
+    that NaN to -inf, gibbs.py:1011-1012.  The finite limit kept here is > 700 below any competing term.)"""
+    e = np.exp(-np.abs(x))
+    l1p = np.log1p(e)
+    pos = x > 0
+    lam = np.where(pos, x + l1p, l1p)
+    sig = np.where(pos, 1.0, e) / (1.0 + e)
+    with np.errstate(divide='ignore', invalid='ignore'):
+        loglam = np.log(lam)
+        ratio = sig / lam
+    far = x < -30.0                                   # rare: patch only those entries
+    if np.any(far):
+        ef = e[far]
+        q = 1.0 - ef * (0.5 - ef / 3.0)
+        loglam[far] = x[far] + np.log(q)
+        ratio[far] = 1.0 / ((1.0 + ef) * q)
+    return lam, sig, loglam, ratio
+
+
 def nlin_and_derivative(x, nlin_type):
     """Returns (lam, dlam/dx, log lam)."""
     x = np.asarray(x, dtype=np.float64)
     if nlin_type == NLIN_EXP:
         lam = np.exp(x)
         return lam, lam, x.copy()
-    e = np.exp(-np.abs(x))
-    lam = np.where(x > 0, x + np.log1p(e), np.log1p(e))
-    sig = np.where(x > 0, 1.0 / (1.0 + e), e / (1.0 + e))
-    # log(lam): for x < 0, lam = e q with q = log1p(e)/e -> log lam = x + log q, finite however negative x is.
-    # (The reference's literal log(log(1+exp(x))) is -inf below x ~ -37 and its ll NaN there; its callers map that NaN
-    # to -inf, gibbs.py:1011-1012.  The finite limit kept here is > 700 below any competing term, so it decides nothing.)
-    with np.errstate(divide='ignore', invalid='ignore'):
-        q = np.where(e > 1e-5, np.log1p(e) / np.where(e > 0, e, 1.0), 1.0 - e * (0.5 - e / 3.0))
-        loglam = np.where(x > 0, np.log(lam), x + np.log(q))
-    return lam, sig, loglam
+    return _softplus_parts(x)[:3]
 
 
 def poisson_residual(x, S_n, dt, nlin_type):
-    """r_t = d/dx_t of (-dt*lam + S log lam) = S * f'/lam - dt * f'  (what T.grad propagates through glm.py:52).
-    f'/lam is formed without dividing by an underflowed lam: exp -> 1; softplus, x <= 0 -> 1/((1+e^x) q) with
-    q = log1p(e^x)/e^x (-> 1), so the residual stays finite however negative the activation is."""
+    """r_t = d/dx_t of (-dt*lam + S log lam) = S * f'/lam - dt * f'  (what T.grad propagates through glm.py:52), with
+    f'/lam formed without dividing by an underflowed lam (exp: f'/lam = 1)."""
     x = np.asarray(x, dtype=np.float64)
-    lam, dlam, _ = nlin_and_derivative(x, nlin_type)
     if nlin_type == NLIN_EXP:
-        return S_n - dt * lam
-    e = np.exp(-np.abs(x))
-    with np.errstate(divide='ignore', invalid='ignore', over='ignore'):
-        q = np.where(e > 1e-5, np.log1p(e) / np.where(e > 0, e, 1.0), 1.0 - e * (0.5 - e / 3.0))
-        ratio = np.where(x > 0, dlam / np.where(lam > 0, lam, 1.0), 1.0 / ((1.0 + e) * q))
-    return S_n * ratio - dt * dlam
+        return S_n - dt * np.exp(x)
+    _lam, sig, _ll, ratio = _softplus_parts(x)
+    return S_n * ratio - dt * sig
+
+
+def _ll_and_residual(x, S_n, dt, nlin_type):
+    """(per-bin ll terms summed over t, residual r) in one pass over the nonlinearity."""
+    x = np.asarray(x, dtype=np.float64)
+    if nlin_type == NLIN_EXP:
+        lam = np.exp(x)
+        return np.sum(-dt * lam + x * S_n, axis=0), S_n - dt * lam
+    lam, sig, loglam, ratio = _softplus_parts(x)
+    return np.sum(-dt * lam + loglam * S_n, axis=0), S_n * ratio - dt * sig
 
 
 def dirichlet_beta(g):
@@ -230,10 +248,9 @@ def glm_ll_grad(fS, S, dt, n, bias_n, w_n, A, W, nlin_type, I_stim=0.0):
     weff = effective_weights(A, W, n)
     I_imp = impulse_current(fS, w_n)
     x = bias_n + I_stim + I_imp @ weff
-    lam, dlam, loglam = nlin_and_derivative(x, nlin_type)
     Sn = S[:, n].astype(np.float64)
-    ll = float(np.sum(-dt * lam + loglam * Sn))
-    r = poisson_residual(x, Sn, dt, nlin_type)
+    ll, r = _ll_and_residual(x, Sn, dt, nlin_type)
+    ll = float(ll)
     g_bias = float(np.sum(r))
     G = np.tensordot(r, fS, axes=(0, 0))                  # (N_pre, B)
     g_w = weff[:, None] * G
@@ -259,10 +276,8 @@ def population_ll_grad(fS, S, dt, bias, w, A, W, nlin_type, fstim=None, w_stim=N
     x = population_activation(fS, bias, w, A, W)
     if fstim is not None:
         x = x + fstim @ w_stim.T
-    lam, dlam, loglam = nlin_and_derivative(x, nlin_type)
     Sf = S.astype(np.float64)
-    ll = np.sum(-dt * lam + loglam * Sf, axis=0)
-    r = poisson_residual(x, Sf, dt, nlin_type)
+    ll, r = _ll_and_residual(x, Sf, dt, nlin_type)
     g_bias = np.sum(r, axis=0)
     G = (X.T @ r).reshape(N, B, N)                        # [(pre,b), post]
     Weff = A.astype(np.float64) * W

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include", "pyglm_b200.h")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libpyglm_b200.so")
-SOURCES = ["capi.cu", "filter.cu", "llgrad_simt.cu", "llgrad_tc.cu", "llgrad_tc_gemm.cu", "gibbs.cu", "allreduce.cu"]
+SOURCES = ["capi.cu", "filter.cu", "llgrad_simt.cu", "llgrad_tc.cu", "llgrad_tc_gemm.cu", "gibbs.cu", "allreduce.cu", "peak.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -30,7 +30,7 @@ EXPORTS = [
     "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_delta_ll_dev", "pyglm_b200_gibbs_commit",
     "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
     "pyglm_b200_comm_create", "pyglm_b200_comm_export", "pyglm_b200_comm_connect", "pyglm_b200_allreduce_sum_dev",
-    "pyglm_b200_comm_destroy",
+    "pyglm_b200_comm_destroy", "pyglm_b200_measure_fp64_peak",
 ]
 
 _lib = None
@@ -83,6 +83,7 @@ def load_library():
     lib.pyglm_b200_comm_connect.argtypes = [p, p]
     lib.pyglm_b200_allreduce_sum_dev.argtypes = [p, p, p, i64, p]
     lib.pyglm_b200_comm_destroy.argtypes = [p]
+    lib.pyglm_b200_measure_fp64_peak.argtypes = [i32, p]
     for name in EXPORTS:      # every declared symbol must resolve
         getattr(lib, name)
     _lib = lib
@@ -135,6 +136,13 @@ def filter_dense(stim, ibasis, device=0):
     out = np.empty((T, D * B))
     _check(load_library().pyglm_b200_filter_dense(_ptr(stim), T, D, _ptr(ibasis), R, B, int(device), _ptr(out)))
     return out.reshape(T, D, B)
+
+
+def measure_fp64_peak(device=0):
+    """FP64 FMA throughput of the GPU's CUDA cores, TFLOP/s (a DFMA loop; K4's roofline denominator)."""
+    out = C.c_double()
+    _check(load_library().pyglm_b200_measure_fp64_peak(int(device), C.addressof(out)))
+    return float(out.value)
 
 
 class Dataset:
