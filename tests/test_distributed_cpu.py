@@ -59,3 +59,56 @@ def test_time_and_neuron_sharding_world2():
     ll0, gb0, gw0 = orc.population_ll_grad(fS, S, p['dt'], p['bias'], p['w'], p['A'], p['W'], orc.NLIN_SOFTPLUS)
     assert rel_err(ll, ll0) < 1e-12 and rel_err(gb, gb0) < 1e-10 and rel_err(gw, gw0) < 1e-10
     assert rel_err(ll_gathered, ll0) < 1e-12
+
+
+def _splice_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from theano_pyglm_b200.inference.parallel_gibbs import concatenate_parallel_updates
+        from theano_pyglm_b200.models.model_factory import make_model, stabilize_sparsity
+        from theano_pyglm_b200.population import Population
+        N = 5
+        model = make_model('sparse_weighted_model', N=N, dt=0.001)
+        stabilize_sparsity(model)
+        popn = Population(model)                                      # components only: no GPU is touched
+        np.random.seed(4)
+        x = popn.sample()                                             # the same start on both ranks
+        n_lo, n_hi = neuron_shard(N, world, rank)
+        W = x['net']['weights']['W'].reshape(N, N)
+        for n in range(n_lo, n_hi):                                   # every rank rewrites its own columns only
+            x['glms'][n]['bias']['bias'] = np.array([100.0 * rank + n])
+            x['glms'][n]['imp']['g_%d' % n] = np.full(5, 1.0 + rank + 0.1 * n)
+            x['net']['graph']['A'][:, n] = (np.arange(N) + n + rank) % 2
+            W[:, n] = 10.0 * rank + n + 0.01 * np.arange(N)
+        x['net']['weights']['W'] = W.ravel()
+        x = concatenate_parallel_updates(popn, x, n_lo, n_hi)
+        q.put((rank, x))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neuron_sharded_state_splice_world2():
+    """concatenate_parallel_updates (parallel_gibbs.py:24-37 as two tensor all-gathers): after the splice both ranks
+    hold every owner's columns of A / W and every owner's GLM variables."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_splice_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = dict(q.get() for _ in range(world))
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    N = 5
+    for rank in range(world):
+        x = res[rank]
+        W = x['net']['weights']['W'].reshape(N, N)
+        assert x['net']['graph']['A'].dtype == np.int8
+        for n in range(N):
+            owner = 0 if n < neuron_shard(N, world, 0)[1] else 1
+            assert x['glms'][n]['bias']['bias'][0] == 100.0 * owner + n
+            assert np.array_equal(x['glms'][n]['imp']['g_%d' % n], np.full(5, 1.0 + owner + 0.1 * n))
+            assert np.array_equal(x['net']['graph']['A'][:, n], (np.arange(N) + n + owner) % 2)
+            assert np.array_equal(W[:, n], 10.0 * owner + n + 0.01 * np.arange(N))

@@ -145,3 +145,57 @@ def test_neuron_sharded_gibbs_splices_to_one_state(engine_lib):
         assert l0['glms'][n]['n'] == n
         assert not np.array_equal(W0[:, n], Wl[:, n])                # columns of both shards were resampled
         assert np.all(np.diag(l0['net']['graph']['A']) == 1)         # self edges stay (p_A = 1 - 1e-8 on the diagonal)
+
+
+def _map_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from theano_pyglm_b200.inference.coord_descent import coord_descent
+        from theano_pyglm_b200.inference.parallel_coord_descent import parallel_coord_descent, parallel_log_p
+        from theano_pyglm_b200.models.model_factory import make_model
+        from theano_pyglm_b200.population import Population
+        from theano_pyglm_b200.utils.parallel_util import neuron_shard
+        N = 5
+        model = make_model('standard_glm', N=N, dt=0.001)
+        popn = Population(model)
+        rng = np.random.default_rng(11)                              # same data on every rank
+        S = (rng.random((8000, N)) < 0.03).astype(float)
+        popn.add_data({'S': S, 'N': N, 'dt': 0.001, 'T': 8.0, 'stim': None, 'dt_stim': 0.1})
+        np.random.seed(2)
+        x0 = popn.sample()
+        for n in range(N):
+            x0['glms'][n]['imp']['w_ir'] *= 0.01
+        import copy
+        x_par = parallel_coord_descent(popn, x0=copy.deepcopy(x0), maxiter=3)
+        n_lo, n_hi = neuron_shard(N, world, rank)
+        lp_par = parallel_log_p(popn, x_par, n_lo, n_hi)             # a collective
+        x_ser = coord_descent(popn, x0=copy.deepcopy(x0), maxiter=3) if rank == 0 else None
+        q.put((rank, popn.dense_glm_params(x_par), lp_par, popn.compute_log_p(x_par),
+               None if x_ser is None else popn.dense_glm_params(x_ser)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neuron_sharded_map_matches_the_serial_coordinate_descent(engine_lib):
+    """parallel_coord_descent (parallel_coord_descent.py:57-157): two ranks fit their own neurons' GLMs on the engine,
+    all-gather the fitted rows and all-reduce the log posterior; the result is the serial coord_descent's, because the
+    per-neuron problems are independent given the (constant) network."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_map_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        rank, P, lp_par, lp_full, P_ser = q.get(timeout=300)
+        res[rank] = (P, lp_par, lp_full, P_ser)
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    assert np.array_equal(res[0][0], res[1][0])                     # one state on both ranks
+    assert res[0][1] == res[1][1]                                   # the all-reduced log posterior
+    assert abs(res[0][1] - res[0][2]) < 1e-9 * abs(res[0][2])       # ... equals the single-process evaluation
+    assert np.allclose(res[0][0], res[0][3], rtol=1e-6, atol=1e-8)  # and the serial driver's optimum

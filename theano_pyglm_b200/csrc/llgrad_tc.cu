@@ -666,6 +666,499 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
     }
 }
 
+// =============================================================================================
+// V2 of the fused kernel for 97..160 features (the headline config C2: 135).  Same algebra, same arithmetic; what
+// changes is how much of X is in flight and how long a tile's dependency chain is:
+//   * X lives in shared memory as single-PLANE slots (one FP16 plane of one 128-bin tile: two 64-feature blocks in
+//     128-byte-swizzled rows + a 16- or 32-feature tail in 32- / 64-byte rows), in a ring of as many slots as fit
+//     (5 at 129..144 features): 2.5 tiles resident instead of 2 stages, and the next tile's high plane is already
+//     landing while the oldest tile's gradient MMAs still read theirs;
+//   * the two 2^-11-scaled products share ONE accumulator (x1 m2 and x2 m1 are issued into the same TMEM columns,
+//     likewise x1^T r2 and x2^T r1): 64 instead of 96 columns per block, a third fewer tcgen05.ld in the epilogue
+//     and in the gradient fold;
+//   * the residual planes form one 128-byte-swizzled operand [r1 | r2] per bin (a full shared-memory wavefront per
+//     fetch; the old 64-byte layout left them half empty), single-buffered when that buys another slot;
+//   * the gradient block of the tail features (replicated into every TMEM lane group by an LBO = 0 descriptor) is
+//     folded by ALL warps every tile, one or two columns each, instead of by one lane quarter every fourth tile --
+//     no warp trails the others into the residual barrier any more.
+// =============================================================================================
+constexpr uint32_t kSw32 = 6;                // UMMA LayoutType::SWIZZLE_32B
+constexpr int kV2FwdCols = 64;               // [hi | lo] activation accumulators
+constexpr int kV2GradTile = 64;              // [hi | lo] gradient accumulators of one 128-feature tile
+constexpr int kV2GradBuf = 2 * kV2GradTile;  // tile 0 (features 0..127) + tile 1 (tail)
+constexpr int kV2MaxSlots = 6;
+constexpr int kBlockBytes = kTileT * 128;    // one 64-feature block of one plane: 128 rows x 128 B
+
+struct TcV2Args {
+    TcKernelArgs k;
+    int nslots;                    // plane slots in the ring
+    int rbufs;                     // residual buffers (1 or 2)
+};
+
+template <int TAIL> struct V2Geom {
+    static constexpr int kTailRowB = 2 * TAIL;                       // bytes per tail row (32 or 64)
+    static constexpr int kTailBytes = kTileT * kTailRowB;            // X tail block of one plane
+    static constexpr int kSlotBytes = 2 * kBlockBytes + kTailBytes;  // one plane of one tile
+    static constexpr int kMBlock = 64 * 128;                         // [M1 | M2] rows of one 64-feature block
+    static constexpr int kMBytes = 2 * kMBlock + 64 * kTailRowB;
+    static constexpr int kRBuf = kTileT * 128;                       // [r1 | r2]: 128 bins x 128 B
+    static constexpr int kUnits = TAIL ? 3 : 2;
+};
+
+template <int TAIL>
+__host__ __device__ inline int v2_smem_bytes(int nslots, int rbufs)
+{
+    using G = V2Geom<TAIL>;
+    return nslots * G::kSlotBytes + G::kMBytes + rbufs * G::kRBuf + 1024;
+}
+
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v)
+{
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+
+template <int NLIN, int TAIL>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_constant__ CUtensorMap tmapW2,
+                 const __grid_constant__ CUtensorMap tmapT1, const __grid_constant__ CUtensorMap tmapT2, TcV2Args va)
+{
+    using G = V2Geom<TAIL>;
+    const TcKernelArgs& a = va.k;
+    const int NS = va.nslots, RB = va.rbufs;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sM = smem + NS * G::kSlotBytes;        // [block 0: 64 rows x 128 B][block 1][tail: 64 rows x kTailRowB]
+    unsigned char* sR = sM + G::kMBytes;                   // RB buffers of [128 bins][r1 (32 cols) | r2 (32 cols)]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + RB * G::kRBuf);
+    uint64_t* bar_full = bars;                             // [kV2MaxSlots][3]  unit of a slot landed
+    uint64_t* bar_empty = bars + 3 * kV2MaxSlots;          // [kV2MaxSlots]     slot consumed by the gradient MMAs
+    uint64_t* bar_fwd_full = bar_empty + kV2MaxSlots;      // activation accumulators ready
+    uint64_t* bar_fwd_empty = bar_fwd_full + 1;            // ... drained by the epilogue
+    uint64_t* bar_r_ready = bar_fwd_empty + 1;             // [2] residual operand written
+    uint64_t* bar_r_free = bar_r_ready + 2;                // [2] ... consumed by the gradient MMAs
+    uint64_t* bar_g_full = bar_r_free + 2;                 // [2] gradient accumulators of a tile complete
+    uint64_t* bar_g_empty = bar_g_full + 2;                // [2] ... folded into FP64
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_g_empty + 2);
+    float* sPar = reinterpret_cast<float*>(tmem_slot + 2); // [32] x (1/sm, bias)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3 * kV2MaxSlots; ++i) mbar_init(&bar_full[i], 1);
+        for (int i = 0; i < kV2MaxSlots; ++i) mbar_init(&bar_empty[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_g_full[i], 1); mbar_init(&bar_g_empty[i], kEpiWarps);
+            mbar_init(&bar_r_ready[i], kEpiWarps); mbar_init(&bar_r_free[i], 1);
+        }
+        mbar_init(bar_fwd_full, 1); mbar_init(bar_fwd_empty, kEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == kProducerWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemAlloc) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // weight planes -> shared memory, swizzled by hand: per 64-feature block 64 rows [M1 rows | M2 rows] of 128 B
+    // (SWIZZLE_128B), then the tail block with rows of kTailRowB bytes (SWIZZLE_64B / SWIZZLE_32B)
+    {
+        constexpr int kUnitsPerRow = (128 + TAIL) / 8;                // 16-byte units (8 features) per weight row
+        for (int u = threadIdx.x; u < 64 * kUnitsPerRow; u += kThreads) {
+            const int r = u / kUnitsPerRow, f8 = u - r * kUnitsPerRow;            // r = plane * 32 + column
+            const uint4 val = *reinterpret_cast<const uint4*>(a.Mp + ((int64_t)r * a.Kp + f8 * 8));
+            unsigned char* dst;
+            if (f8 < 16) {
+                const int blk = f8 >> 3, q8 = f8 & 7;
+                dst = sM + blk * G::kMBlock + r * 128 + ((q8 ^ (r & 7)) << 4);
+            } else if (TAIL == 32) {
+                const int q = f8 - 16;
+                dst = sM + 2 * G::kMBlock + r * 64 + ((q ^ ((r >> 1) & 3)) << 4);
+            } else {
+                const int q = f8 - 16;
+                dst = sM + 2 * G::kMBlock + r * 32 + ((q ^ ((r >> 2) & 1)) << 4);
+            }
+            *reinterpret_cast<uint4*>(dst) = val;
+        }
+        fence_proxy_async();
+        if (threadIdx.x < kNcol) {
+            sPar[2 * threadIdx.x] = a.colpar[threadIdx.x];
+            sPar[2 * threadIdx.x + 1] = a.colpar[kNcol + threadIdx.x];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t first = blockIdx.x, step = gridDim.x;
+    const int ntl = first < a.ntiles ? (int)((a.ntiles - first + step - 1) / step) : 0;   // tiles of this CTA
+    const int F = a.flush;
+    // fill f (0, 1, 2, ...) = plane f & 1 of tile f >> 1, lands in slot f % NS; its barriers' parity is (f / NS) & 1
+
+    if (warp == kProducerWarp) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int slot = 0; uint32_t par = 1;              // parity on which the slot's empty barrier is waited
+            for (int it = 0; it < ntl; ++it) {
+                const int row0 = (int)((first + (int64_t)it * step) * kTileT);
+                for (int plane = 0; plane < 2; ++plane) {
+                    mbar_wait_relaxed(&bar_empty[slot], par, a.producer_sleep_ns);
+                    if (plane == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
+                    unsigned char* st = smem + slot * G::kSlotBytes;
+                    const CUtensorMap* mw = plane ? &tmapW2 : &tmapW1;
+                    for (int u = 0; u < 2; ++u) {
+                        uint64_t* fb = &bar_full[slot * 3 + u];
+                        mbar_arrive_expect_tx(fb, kBlockBytes);
+                        tma_load_2d(st + u * kBlockBytes, mw, fb, u * 64, row0);
+                    }
+                    if (TAIL) {
+                        uint64_t* fb = &bar_full[slot * 3 + 2];
+                        mbar_arrive_expect_tx(fb, G::kTailBytes);
+                        tma_load_2d(st + 2 * kBlockBytes, plane ? &tmapT2 : &tmapT1, fb, 128, row0);
+                    }
+                    if (++slot == NS) { slot = 0; par ^= 1; }
+                }
+            }
+        }
+    } else if (warp == kFwdWarp) {
+        // ================================ forward MMA issuer ==========================
+        if (lane == 0) {
+            constexpr uint32_t idesc_f64 = umma_idesc(128, 64, 0, 0);     // A: X K-major,  B: [M1|M2] K-major
+            constexpr uint32_t idesc_f32 = umma_idesc(128, 32, 0, 0);
+            const uint32_t sMb = smem_u32(sM);
+            const uint32_t t_f = tmem_base;
+            int slot = 0; uint32_t par = 0;
+            for (int it = 0; it < ntl; ++it) {
+                mbar_wait(bar_fwd_empty, (it & 1) ^ 1);
+                for (int plane = 0; plane < 2; ++plane) {
+                    const uint32_t sX = smem_u32(smem + slot * G::kSlotBytes);
+                    // plane 0: x1 [m1 | m2] -> columns 0..63 (first MMA overwrites); plane 1: x2 m1 -> added to columns 32..63
+                    const uint32_t t_d = plane ? t_f + 32 : t_f;
+                    const uint32_t idesc = plane ? idesc_f32 : idesc_f64;
+                    for (int u = 0; u < 2; ++u) {
+                        mbar_wait(&bar_full[slot * 3 + u], par);
+                        if (plane == 0 && u == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
+                        tc_fence_after();
+                        const uint64_t wx = umma_desc_sw128(sX + u * kBlockBytes);
+                        const uint64_t wm = umma_desc_sw128(sMb + u * G::kMBlock);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_f16(t_d, wx + 2 * ks, wm + 2 * ks, idesc, (plane | u | ks) ? 1u : 0u);
+                    }
+                    if (TAIL) {
+                        mbar_wait(&bar_full[slot * 3 + 2], par);
+                        tc_fence_after();
+                        if (TAIL == 32) {
+                            const uint64_t dx = umma_desc(sX + 2 * kBlockBytes, 16, 512), dm = umma_desc(sMb + 2 * G::kMBlock, 16, 512);
+                            umma_f16(t_d, dx, dm, idesc, 1u);
+                            umma_f16(t_d, dx + 2, dm + 2, idesc, 1u);
+                        } else {
+                            const uint64_t dx = umma_desc_layout(sX + 2 * kBlockBytes, 16, 256, kSw32);
+                            const uint64_t dm = umma_desc_layout(sMb + 2 * G::kMBlock, 16, 256, kSw32);
+                            umma_f16(t_d, dx, dm, idesc, 1u);
+                        }
+                    }
+                    if (++slot == NS) { slot = 0; par ^= 1; }
+                }
+                umma_commit(bar_fwd_full);
+                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 1] = clock64();
+            }
+        }
+    } else if (warp == kBwdWarp) {
+        // ================================ gradient MMA issuer =========================
+        if (lane == 0) {
+            constexpr uint32_t idesc_b64 = umma_idesc(128, 64, 1, 1);     // A: X MN-major, B: [r1|r2] MN-major
+            constexpr uint32_t idesc_b32 = umma_idesc(128, 32, 1, 1);
+            int slot = 0; uint32_t par = 0;
+            for (int j = 0; j < ntl; ++j) {
+                const int b = j % RB, gb = j & 1;
+                const uint32_t rph = (uint32_t)(j / RB) & 1u;
+                const int sA = slot;
+                const int sB = (slot + 1 == NS) ? 0 : slot + 1;
+                const uint32_t parB = (slot + 1 == NS) ? par ^ 1 : par;
+                for (int u = 0; u < G::kUnits; ++u) {                                  // landed long ago
+                    mbar_wait(&bar_full[sA * 3 + u], par);
+                    mbar_wait(&bar_full[sB * 3 + u], parB);
+                }
+                mbar_wait(&bar_r_ready[b], rph);
+                mbar_wait(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
+                if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
+                tc_fence_after();
+                const uint32_t sX1 = smem_u32(smem + sA * G::kSlotBytes), sX2 = smem_u32(smem + sB * G::kSlotBytes);
+                const uint64_t dr = umma_desc_layout(smem_u32(sR + b * G::kRBuf), 16, 1024, kSw128);    // one 64-wide atom
+                const uint32_t t_g = tmem_base + kV2FwdCols + gb * kV2GradBuf;
+                {   // tile 0: features 0..127 = the two 64-feature blocks (LBO steps from one to the other)
+                    const uint64_t d1 = umma_desc_layout(sX1, kBlockBytes, 1024, kSw128);
+                    const uint64_t d2 = umma_desc_layout(sX2, kBlockBytes, 1024, kSw128);
+#pragma unroll
+                    for (int ks = 0; ks < kTileT / 16; ++ks) {                        // 16 bins per step: 2048 B of both operands
+                        const uint64_t off = (uint64_t)(ks * 2048 >> 4);
+                        umma_f16(t_g, d1 + off, dr + off, idesc_b64, ks ? 1u : 0u);   // X1^T [r1 | r2] -> hi, lo
+                        umma_f16(t_g + 32, d2 + off, dr + off, idesc_b32, 1u);        // X2^T r1 -> lo
+                    }
+                }
+                if (TAIL) {
+                    // tail features: LBO = 0 makes every group of TAIL TMEM lanes a copy of the same TAIL gradient rows, so
+                    // the epilogue warps of all four lane quarters can each fold a share of them
+                    const uint32_t kstep = TAIL == 32 ? 1024u : 512u;                 // sixteen bins of the tail block
+                    const uint64_t d1 = TAIL == 32 ? umma_desc(sX1 + 2 * kBlockBytes, 0, 512)
+                                                   : umma_desc_layout(sX1 + 2 * kBlockBytes, 0, 256, kSw32);
+                    const uint64_t d2 = TAIL == 32 ? umma_desc(sX2 + 2 * kBlockBytes, 0, 512)
+                                                   : umma_desc_layout(sX2 + 2 * kBlockBytes, 0, 256, kSw32);
+#pragma unroll
+                    for (int ks = 0; ks < kTileT / 16; ++ks) {
+                        const uint64_t offx = (uint64_t)(ks * kstep >> 4), off = (uint64_t)(ks * 2048 >> 4);
+                        umma_f16(t_g + kV2GradTile, d1 + offx, dr + off, idesc_b64, ks ? 1u : 0u);
+                        umma_f16(t_g + kV2GradTile + 32, d2 + offx, dr + off, idesc_b32, 1u);
+                    }
+                }
+                umma_commit(&bar_empty[sA]);
+                umma_commit(&bar_empty[sB]);
+                umma_commit(&bar_r_free[b]);
+                umma_commit(&bar_g_full[gb]);
+                if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 3] = clock64();
+                slot += 2;
+                if (slot >= NS) { slot -= NS; par ^= 1; }
+            }
+        }
+    } else if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + kEpiWarps) {
+        // ================================ epilogue warps ==============================
+        const int q = warp & 3;
+        const int cg = (warp - kFirstEpiWarp) >> 2;
+        const int c0 = cg * kColsPerWarp;                // first column of this warp
+        const int row = q * 32 + lane;                   // row of the tile == TMEM lane
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + c0;
+        const float2* cpar = reinterpret_cast<const float2*>(sPar);     // (1/sm, bias) per column
+        const int64_t per_cta = (int64_t)(128 + TAIL) * kNcol + 2 * kNcol;
+        double* gp = a.part + (int64_t)blockIdx.x * per_cta;
+        double gacc[kColsPerWarp];                       // gradient tile 0: this thread's feature row x its columns
+        double gtail[2] = {0.0, 0.0};                    // tail: columns c0 + 2q, c0 + 2q + 1 (TAIL 16: one of them)
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; ++c) gacc[c] = 0.0;
+        static_assert(kColsPerWarp == 8, "the tail fold assigns two of eight columns to each lane quarter");
+        auto fold_gradient = [&](int j) {
+            float g0[kColsPerWarp], g1[kColsPerWarp], h0[2], h1[2];
+            const int gb = j & 1;
+            const uint32_t t_g = t_lane + kV2FwdCols + gb * kV2GradBuf;
+            mbar_wait(&bar_g_full[gb], (j >> 1) & 1);
+            tc_fence_after();
+            tmem_ld<kColsPerWarp>(t_g + 0, g0);
+            tmem_ld<kColsPerWarp>(t_g + 32, g1);
+            if (TAIL) {
+                tmem_ld2(t_g + kV2GradTile + 2 * q, h0);
+                tmem_ld2(t_g + kV2GradTile + 32 + 2 * q, h1);
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_g_empty[gb]);
+#pragma unroll
+            for (int c = 0; c < kColsPerWarp; ++c) gacc[c] += (double)fmaf(g1[c], 1.0f / kLoScale, g0[c]);
+            if (TAIL == 32) {
+                gtail[0] += (double)fmaf(h1[0], 1.0f / kLoScale, h0[0]);
+                gtail[1] += (double)fmaf(h1[1], 1.0f / kLoScale, h0[1]);
+            } else if (TAIL == 16) {
+                const bool up = lane >= 16;              // lanes 16..31 hold a second copy of the 16 rows: they take the odd column
+                gtail[0] += (double)fmaf(up ? h1[1] : h1[0], 1.0f / kLoScale, up ? h0[1] : h0[0]);
+            }
+        };
+        double ll_acc = 0.0, gb_acc = 0.0;               // lane l accumulates column c0 + (l % kColsPerWarp)
+        float pll[kColsPerWarp], pgb[kColsPerWarp];
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; ++c) { pll[c] = 0.f; pgb[c] = 0.f; }
+
+        constexpr int kSpWords = kColsPerWarp / 4;
+        uint32_t sb[kSpWords], sb_next[kSpWords];
+        const bool vec_ok = ((a.n_lo + c0) % kColsPerWarp) == 0;
+        auto load_spikes = [&](int it, uint32_t (&dst)[kSpWords]) {
+            const int64_t t = (first + (int64_t)it * step) * kTileT + row;
+            const bool ok = it < ntl && t < a.T;
+#pragma unroll
+            for (int i = 0; i < kSpWords; ++i) dst[i] = 0;
+            if (!ok) return;
+            const uint8_t* src = a.Sp + t * a.Np + a.n_lo + c0;
+            if (vec_ok) {
+                const uint2 v = *reinterpret_cast<const uint2*>(src);
+                dst[0] = v.x; dst[1] = v.y;
+            } else {
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) dst[c >> 2] |= (uint32_t)src[c] << ((c & 3) * 8);
+            }
+        };
+        load_spikes(0, sb_next);
+        unsigned badmask = 0;
+
+        for (int it = 0; it < ntl; ++it) {
+            const int b = it % RB;
+            const uint32_t rph = (uint32_t)(it / RB) & 1u;
+            const int64_t t = (first + (int64_t)it * step) * kTileT + row;
+            const float lv = t < a.T ? 1.0f : 0.0f;
+#pragma unroll
+            for (int i = 0; i < kSpWords; ++i) sb[i] = sb_next[i];
+            load_spikes(it + 1, sb_next);
+            const bool tr = a.trace && blockIdx.x == 0 && warp == kFirstEpiWarp + (a.debug >> 8) && lane == 0 && it < 32;
+            if (tr) a.trace[(2 * 32 + it) * 4 + 0] = clock64();
+            mbar_wait(bar_fwd_full, it & 1);
+            if (tr) a.trace[(2 * 32 + it) * 4 + 1] = clock64();
+            tc_fence_after();
+            float d0[kColsPerWarp], d1[kColsPerWarp];
+            tmem_ld<kColsPerWarp>(t_lane + 0, d0);
+            tmem_ld<kColsPerWarp>(t_lane + 32, d1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_fwd_empty);
+
+            float xs[kColsPerWarp];
+            float xmin = 3.0e38f;
+#pragma unroll
+            for (int c = 0; c < kColsPerWarp; ++c) {
+                const float2 cp = cpar[c0 + c];
+                xs[c] = fmaf(fmaf(d1[c], 1.0f / kLoScale, d0[c]), cp.x, cp.y);
+                if (c0 + c < a.ncols) xmin = fminf(xmin, xs[c]);
+                if (NLIN == PYGLM_B200_NLIN_EXP && c0 + c < a.ncols && lv != 0.f && !(xs[c] <= kExpSafe)) badmask |= 1u << c;
+            }
+            const float dtl = a.dt * lv;                 // bins past the end of the recording contribute nothing
+            if (NLIN == PYGLM_B200_NLIN_SOFTPLUS && __all_sync(0xffffffffu, xmin > 17.5f)) {
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) {
+                    float r = 0.f;
+                    if (c0 + c < a.ncols) {              // warp-uniform: padded columns cost nothing
+                        const float x = xs[c];
+                        const float sv = (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu);     // 0 past the end of the recording
+                        float lg, rc;
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(x));
+                        pll[c] += fmaf(sv * 0.69314718f, lg, -dtl * x);                        // -dt*lam + s*log(lam)
+                        r = fmaf(sv, rc, -dtl);                                                 // (s/lam - dt) * 1
+                        pgb[c] += r;
+                    }
+                    d1[c] = r;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) {
+                    float term = 0.f, r = 0.f;
+                    if (c0 + c < a.ncols) {
+                        poisson_terms<NLIN>(xs[c], (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu), a.dt, term, r);
+                        r *= lv;
+                        pll[c] = fmaf(lv, term, pll[c]);
+                        pgb[c] += r;
+                    }
+                    d1[c] = r;
+                }
+            }
+            // residual operand [r1 | r2] of this bin: one 128-byte row, 16-byte units 0..3 = r1 (8 columns each), 4..7 = r2,
+            // unit index XOR (row & 7) (SWIZZLE_128B); this warp owns unit cg of each half
+            if (tr) a.trace[1408 + it * 4 + 1] = clock64();
+            mbar_wait(&bar_r_free[b], rph ^ 1);
+            if (tr) a.trace[1408 + it * 4 + 2] = clock64();
+            {
+                unsigned char* prow = sR + b * G::kRBuf + row * 128;
+                uint32_t h1[4], h2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float ra = d1[2 * k] * kRScale, rb = d1[2 * k + 1] * kRScale;
+                    const __half2 hi = __floats2half2_rn(ra, rb);
+                    const float2 back = __half22float2(hi);
+                    const __half2 lo = __floats2half2_rn((ra - back.x) * kLoScale, (rb - back.y) * kLoScale);
+                    h1[k] = *reinterpret_cast<const uint32_t*>(&hi);
+                    h2[k] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+                const int sw = row & 7;
+                *reinterpret_cast<uint4*>(prow + ((cg ^ sw) << 4)) = make_uint4(h1[0], h1[1], h1[2], h1[3]);
+                *reinterpret_cast<uint4*>(prow + (((4 + cg) ^ sw) << 4)) = make_uint4(h2[0], h2[1], h2[2], h2[3]);
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_r_ready[b]);
+            if (tr) a.trace[(2 * 32 + it) * 4 + 2] = clock64();
+            if (a.trace && blockIdx.x == 0 && lane == 0 && it < 32) a.trace[384 + warp * 32 + it] = clock64();
+
+            if (((it + 1) % F) == 0 || it == ntl - 1) {
+                ll_acc += (double)warp_column_sums<kColsPerWarp>(pll, lane);
+                gb_acc += (double)warp_column_sums<kColsPerWarp>(pgb, lane);
+#pragma unroll
+                for (int c = 0; c < kColsPerWarp; ++c) { pll[c] = 0.f; pgb[c] = 0.f; }
+            }
+            if (it >= 1) fold_gradient(it - 1);
+            if (tr) a.trace[(2 * 32 + it) * 4 + 3] = clock64();
+        }
+
+        if (ntl > 0) fold_gradient(ntl - 1);
+        if (NLIN == PYGLM_B200_NLIN_EXP && a.flags) {
+            badmask = __reduce_or_sync(0xffffffffu, badmask);
+            if (lane < kColsPerWarp && ((badmask >> lane) & 1u)) a.flags[a.n_lo + c0 + lane] = 1u;
+        }
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; ++c) gp[(int64_t)row * kNcol + c0 + c] = gacc[c];
+        if (TAIL == 32) {
+            gp[((int64_t)128 + lane) * kNcol + c0 + 2 * q] = gtail[0];
+            gp[((int64_t)128 + lane) * kNcol + c0 + 2 * q + 1] = gtail[1];
+        } else if (TAIL == 16) {
+            gp[((int64_t)128 + (lane & 15)) * kNcol + c0 + 2 * q + (lane >> 4)] = gtail[0];
+        }
+        // ---- per-CTA ll / g_bias partials
+        double* sred = reinterpret_cast<double*>(sR);    // the residual operand is idle now: [4 quarters][2][32]
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");   // every epilogue warp is past its last wait
+        if (lane < kColsPerWarp) {
+            sred[(q * 2 + 0) * kNcol + c0 + lane] = ll_acc;
+            sred[(q * 2 + 1) * kNcol + c0 + lane] = gb_acc;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+        if (warp == kFirstEpiWarp) {
+            double l = 0.0, g = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { l += sred[(k * 2 + 0) * kNcol + lane]; g += sred[(k * 2 + 1) * kNcol + lane]; }
+            double* lp = gp + (int64_t)(128 + TAIL) * kNcol;
+            lp[lane] = l;
+            lp[kNcol + lane] = g;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProducerWarp) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTmemAlloc) : "memory");
+    }
+}
+
+// V2 partials: per CTA [128 + TAIL feature rows][32], then [32] ll, [32] g_bias; summed in CTA order (deterministic)
+__global__ void __launch_bounds__(32 * 32)
+tc_final2_kernel(const double* __restrict__ part, int nctas, int nrows, int N, int B, int F, int n_lo, int ncols,
+                 const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
+                 double* __restrict__ out_ll, double* __restrict__ out_gb, double* __restrict__ out_gw)
+{
+    __shared__ double sh[32][2 * kNcol];
+    const int64_t NS = (int64_t)N * B, NB = NS + F;
+    const int64_t per_cta = (int64_t)nrows * kNcol + 2 * kNcol;
+    const int nl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const bool tail = blockIdx.x == NB;                      // the ll / g_bias block
+    const int64_t off = tail ? (int64_t)nrows * kNcol : (int64_t)blockIdx.x * kNcol;
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = slice; c < nctas; c += 32) {
+        const double* pc = part + c * per_cta + off + nl;
+        s0 += pc[0];
+        if (tail) s1 += pc[kNcol];
+    }
+    sh[slice][nl] = s0;
+    sh[slice][kNcol + nl] = s1;
+    __syncthreads();
+    if (slice != 0 || nl >= ncols) return;
+#pragma unroll
+    for (int k = 1; k < 32; ++k) { s0 += sh[k][nl]; s1 += sh[k][kNcol + nl]; }
+    if (tail) {
+        out_ll[nl] = s0;
+        if (out_gb) out_gb[nl] = s1;                         // residual column sums are carried unscaled
+    } else if (out_gw) {
+        const int64_t j = blockIdx.x;
+        const int n = n_lo + nl, pre = (int)(j / B);
+        const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + n] : 1.0;
+        const double ww = (W && j < NS) ? W[(int64_t)pre * N + n] : 1.0;
+        out_gw[(int64_t)nl * NB + j] = (a * ww) * s0 / ((double)sx[j] * (double)kRScale);
+    }
+}
+
 // Sum the per-CTA partials in a fixed order and undo the scales.  One block per feature row j
 // (plus one for ll / g_bias): 32 columns x 32 slices of the CTA range, combined slice 0..31.
 constexpr int kFinalSlices = 32;
@@ -715,7 +1208,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2-D FP16 tensor map with 64B swizzle: dim0 fastest (elements), row pitch in elements, box {box0, box1}
 int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1,
-                   bool swizzle128)
+                   int swizzle)          // 0: SWIZZLE_64B, 1: SWIZZLE_128B, 2: SWIZZLE_32B
 {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
@@ -734,7 +1227,7 @@ int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, 
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(static_cast<CUtensorMap*>(map_out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for dims %lld x %lld pitch %lld box %d x %d", (int)r,
@@ -766,7 +1259,7 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)T * ws.Np, stream));
     PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
     PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, NB * sizeof(unsigned), stream));
-    ws.tmaps = malloc(4 * sizeof(CUtensorMap));
+    ws.tmaps = malloc(6 * sizeof(CUtensorMap));
     if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
     CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
     int rc;
@@ -774,6 +1267,8 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     if ((rc = tc_make_map_2d(&maps[1], ws.X2, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
     if ((rc = tc_make_map_2d(&maps[2], ws.X1, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;      // wide chunks, 128B swizzle
     if ((rc = tc_make_map_2d(&maps[3], ws.X2, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;
+    if ((rc = tc_make_map_2d(&maps[4], ws.X1, ws.ldp, T, ws.ldp, 16, kTileT, 2))) return rc;         // 16-feature tail, 32B swizzle
+    if ((rc = tc_make_map_2d(&maps[5], ws.X2, ws.ldp, T, ws.ldp, 16, kTileT, 2))) return rc;
     return PYGLM_B200_OK;
 }
 
@@ -833,6 +1328,27 @@ int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int 
     return PYGLM_B200_OK;
 }
 
+template <int TAIL>
+static int launch_fused2(const TcArgs& a, TcWorkspace& ws, TcKernelArgs k, const CUtensorMap* maps, int nctas, cudaStream_t stream)
+{
+    using G = V2Geom<TAIL>;
+    const int budget = 232448 - 1024;                     // the kernel aligns its carve-up to 1024 bytes itself
+    auto slots_for = [&](int rb) { return std::min(kV2MaxSlots, (budget - 1024 - G::kMBytes - rb * G::kRBuf) / G::kSlotBytes); };
+    int rbufs = slots_for(1) > slots_for(2) ? 1 : 2;
+    if (const char* env = getenv("PYGLM_TC_RBUFS")) rbufs = atoi(env) == 1 ? 1 : 2;
+    int nslots = slots_for(rbufs);
+    if (const char* env = getenv("PYGLM_TC_SLOTS")) nslots = std::max(4, std::min(nslots, atoi(env)));
+    TcV2Args va{k, nslots, rbufs};
+    const int smem_bytes = v2_smem_bytes<TAIL>(nslots, rbufs) + 1024;
+    auto kern = a.nlin == PYGLM_B200_NLIN_EXP ? tc_fused2_kernel<PYGLM_B200_NLIN_EXP, TAIL> : tc_fused2_kernel<PYGLM_B200_NLIN_SOFTPLUS, TAIL>;
+    PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    const CUtensorMap& t1 = TAIL == 16 ? maps[4] : maps[0];
+    const CUtensorMap& t2 = TAIL == 16 ? maps[5] : maps[1];
+    kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[2], maps[3], t1, t2, va);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
+}
+
 int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
 {
     if (a.T <= 0 || a.ncols <= 0) return PYGLM_B200_OK;
@@ -845,7 +1361,10 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     const int Kp = nch * kChunkF;
     const int64_t ntiles = ceil_div(a.T, kTileT);
     const int nctas = (int)std::min<int64_t>(ntiles, ws.num_sms);
-    const size_t per_cta = (size_t)nmt * 128 * kNcol + 2 * kNcol;
+    bool v2 = nch >= 4;                                   // 97..160 features: the plane-slot ring kernel
+    if (const char* env = getenv("PYGLM_TC_V2")) v2 = v2 && atoi(env) != 0;
+    const int tail2 = NB <= 128 ? 0 : (NB <= 144 ? 16 : 32);
+    const size_t per_cta = v2 ? (size_t)(128 + tail2) * kNcol + 2 * kNcol : (size_t)nmt * 128 * kNcol + 2 * kNcol;
     if (ws.part_elems < per_cta * nctas) {
         cudaFree(ws.part);
         ws.part = nullptr; ws.part_elems = 0;
@@ -879,8 +1398,15 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         const bool want_trace = getenv("PYGLM_TC_TRACE") != nullptr;
         if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, (384 + 32 * 32 + 32 * 16) * sizeof(long long)));
         k.trace = want_trace ? d_trace : nullptr;
-        kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], k);
-        PYGLM_CUDA(cudaGetLastError());
+        if (v2) {
+            const int rc2 = tail2 == 0 ? launch_fused2<0>(a, ws, k, maps, nctas, stream)
+                          : tail2 == 16 ? launch_fused2<16>(a, ws, k, maps, nctas, stream)
+                                        : launch_fused2<32>(a, ws, k, maps, nctas, stream);
+            if (rc2) return rc2;
+        } else {
+            kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], k);
+            PYGLM_CUDA(cudaGetLastError());
+        }
         if (want_trace) {
             static int dumped = 0;
             if (dumped++ == 5) {
@@ -908,6 +1434,11 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
                 }
             }
         }
+        if (v2)
+            tc_final2_kernel<<<(unsigned)(NB + 1), 32 * 32, 0, stream>>>(
+                ws.part, nctas, 128 + tail2, a.N, a.B, a.F, n_lo, nc, ws.sx, a.A, a.W,
+                a.out_ll + c0, a.out_gb ? a.out_gb + c0 : nullptr, a.out_gw ? a.out_gw + (int64_t)c0 * NB : nullptr);
+        else
         tc_final_kernel<<<(unsigned)(NB + 1), 32 * kFinalSlices, 0, stream>>>(
             ws.part, nctas, nmt, a.N, a.B, a.F, n_lo, nc, ws.sx, a.A, a.W,
             a.out_ll + c0, a.out_gb ? a.out_gb + c0 : nullptr, a.out_gw ? a.out_gw + (int64_t)c0 * NB : nullptr);

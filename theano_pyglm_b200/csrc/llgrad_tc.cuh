@@ -46,7 +46,7 @@ int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
                               int R, int B, cudaStream_t stream);
 int tc_make_map_2d(void* map, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1,
-                   bool swizzle128 = false);
+                   int swizzle = 0);        // 0: SWIZZLE_64B, 1: SWIZZLE_128B, 2: SWIZZLE_32B
 int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 void tc_gemm_release(void* w);
 int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);

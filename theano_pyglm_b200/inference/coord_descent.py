@@ -39,18 +39,22 @@ def fit_glm(population, x, n, maxiter=225, disp=False):
     return res
 
 
-def fit_glms_batched(population, x, maxiter=225, gtol=1e-5, history=20, verbose=False):
-    """Lock-step L-BFGS over all neurons; returns the number of iterations taken."""
-    N = population.N
+def fit_glms_batched(population, x, maxiter=225, gtol=1e-5, history=20, verbose=False, n_lo=0, n_hi=None):
+    """Lock-step L-BFGS over the neurons [n_lo, n_hi) (all by default; a neuron-sharded rank passes its own block);
+    returns the number of iterations taken."""
+    n_hi = population.N if n_hi is None else n_hi
+    N = n_hi - n_lo
+    P_all = np.stack([population.glm_param_vector(x['glms'][n]) for n in range(population.N)])
 
     def evaluate(P):
-        lp, g = population.glms_log_p_grad_dense(P, x)     # all neurons, priors included, no per-neuron dict traffic
+        P_all[n_lo:n_hi] = P
+        lp, g = population.glms_log_p_grad_dense(P_all, x, n_lo, n_hi)   # priors included, no per-neuron dict traffic
         f = np.where(np.isnan(lp), 1e16, -lp)              # same guards as fit_glm
         g = -g
         g[np.any(np.isnan(g), axis=1)] = 0.0
         return f, g
 
-    P = np.stack([population.glm_param_vector(x['glms'][n]) for n in range(N)])
+    P = P_all[n_lo:n_hi].copy()
     f, g = evaluate(P)
     S_hist, Y_hist = [], []                                 # lists of (N, D) arrays
     active = np.ones(N, dtype=bool)
@@ -108,7 +112,7 @@ def fit_glms_batched(population, x, maxiter=225, gtol=1e-5, history=20, verbose=
         if verbose:
             print("L-BFGS iter %d: sum LP %.3f, active %d" % (it, -f.sum(), int(active.sum())))
     for n in range(N):
-        population.set_glm_param_vector(x['glms'][n], P[n])
+        population.set_glm_param_vector(x['glms'][n_lo + n], P[n])
     return it
 
 

@@ -179,8 +179,10 @@ class BatchedHmcGlmUpdate(MetropolisHastingsUpdate):
         def U_and_grad(Q):
             Pq = P.copy()
             Pq[n_lo:n_hi, lo:hi] = Q[n_lo:n_hi]
-            lp, g = popn.glms_log_p_grad_dense(Pq, x)
-            return -lp, -g[:, lo:hi]
+            lp, g = popn.glms_log_p_grad_dense(Pq, x, n_lo, n_hi)         # the engine evaluates only this shard's columns
+            U, gU = np.zeros(N), np.zeros((N, hi - lo))
+            U[n_lo:n_hi], gU[n_lo:n_hi] = -lp, -g[:, lo:hi]
+            return U, gU
 
         q, self.step_sz, self.avg_accept_rate = hmc_batched(U_and_grad, self.step_sz, self.n_steps, P[:, lo:hi],
                                                             active=active, avg_accept_rate=self.avg_accept_rate)

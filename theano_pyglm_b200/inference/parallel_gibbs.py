@@ -13,32 +13,34 @@ import copy
 import numpy as np
 import torch.distributed as dist
 
-from ..utils.parallel_util import allgather_columns, neuron_shard
+from ..utils.parallel_util import allgather_columns, collective_device, neuron_shard, world_rank
 from .gibbs import initial_state, initialize_batched_updates, initialize_updates
+from .parallel_coord_descent import parallel_log_p
 
 
 def _world(group=None):
-    if dist.is_available() and dist.is_initialized():
-        return dist.get_world_size(group), dist.get_rank(group)
-    return 1, 0
+    return world_rank(group)
 
 
-def concatenate_parallel_updates(x, n_lo, n_hi, group=None):
-    """Splice the columns every rank resampled into one consistent state on all ranks
-    (parallel_gibbs.py:24-37): x['glms'][n], A[:, n] and W[:, n] come from the owner of neuron n."""
+def concatenate_parallel_updates(population, x, n_lo, n_hi, group=None):
+    """Splice the columns every rank resampled into one consistent state on all ranks (parallel_gibbs.py:24-37):
+    x['glms'][n], A[:, n] and W[:, n] come from the owner of neuron n.  Two tensor collectives on the ranks' own
+    devices (NCCL on GPUs): the float64 rows [GLM parameter vector | W[:, n]] and the int8 rows A[:, n] -- no pickling,
+    no object gather."""
     world, rank = _world(group)
     if world == 1:
         return x
-    N = x['net']['graph']['A'].shape[0]
-    mine = [x['glms'][n] for n in range(n_lo, n_hi)]
-    parts = [None] * world
-    dist.all_gather_object(parts, mine, group=group)
-    x['glms'] = [g for part in parts for g in part]
+    N = population.N
+    dev = collective_device(population.device, group)
     W = x['net']['weights']['W'].reshape(N, N)
-    A_cols = allgather_columns(np.ascontiguousarray(x['net']['graph']['A'][:, n_lo:n_hi].T), N, group=group)
-    W_cols = allgather_columns(np.ascontiguousarray(W[:, n_lo:n_hi].T), N, group=group)
+    P = population.dense_glm_params(x)
+    D = P.shape[1]
+    mine = np.concatenate([P[n_lo:n_hi], W[:, n_lo:n_hi].T], axis=1)                   # (n, D + N) float64
+    full = allgather_columns(np.ascontiguousarray(mine), N, device=dev, group=group)
+    A_cols = allgather_columns(np.ascontiguousarray(x['net']['graph']['A'][:, n_lo:n_hi].T), N, device=dev, group=group)
+    population.set_dense_glm_params(x, full[:, :D])
     x['net']['graph']['A'] = np.ascontiguousarray(A_cols.T).astype(np.int8)
-    x['net']['weights']['W'] = np.ascontiguousarray(W_cols.T).ravel()
+    x['net']['weights']['W'] = np.ascontiguousarray(full[:, D:].T).ravel()
     return x
 
 
@@ -64,8 +66,10 @@ def parallel_gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=Fal
     for smpl in range(N_samples):
         if callback is not None and rank == 0:
             callback(x)
-        if verbose and rank == 0:
-            print("Gibbs iteration %d. Log prob: %.3f" % (smpl, population.compute_log_p(x)))
+        if verbose:                                               # a collective: every rank takes part
+            lp = parallel_log_p(population, x, n_lo, n_hi, group)
+            if rank == 0:
+                print("Gibbs iteration %d. Log prob: %.3f" % (smpl, lp))
         if n_hi > n_lo:
             for upd in batched_updates:                           # this rank's neurons, in lock-step
                 upd.update(x, n_lo, n_hi)
@@ -73,7 +77,7 @@ def parallel_gibbs_sample(population, N_samples=1000, x0=None, init_from_mle=Fal
             net_update.begin(x, n_lo, n_hi)
             net_update.sweep_batched(x, n_lo, n_hi)
             net_update.end()
-        x = concatenate_parallel_updates(x, n_lo, n_hi, group=group)
+        x = concatenate_parallel_updates(population, x, n_lo, n_hi, group=group)
         for upd in serial_updates:                                # none for the supported models
             upd.update(x)
         x_smpls.append(copy.deepcopy(x))

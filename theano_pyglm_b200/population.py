@@ -272,10 +272,13 @@ class Population:
         for n in range(n_lo, self.N if n_hi is None else n_hi):
             self.set_glm_param_vector(x['glms'][n], P[n])
 
-    def glms_log_p_grad_dense(self, P, x):
+    def glms_log_p_grad_dense(self, P, x, n_lo=0, n_hi=None):
         """glms_log_p_grad for the parameter matrix P (N, D) and the network of state x, with the priors, the
-        Dirichlet normalisation and its chain rule evaluated for all neurons at once."""
+        Dirichlet normalisation and its chain rule evaluated for all neurons at once.  With a neuron range the engine
+        evaluates only columns [n_lo, n_hi) (a neuron-sharded rank's share) and the results have n_hi - n_lo rows;
+        P always carries every neuron (the weights of the other neurons are not read by those columns)."""
         glm = self.glm
+        n_hi = self.N if n_hi is None else n_hi
         F = glm.bkgd_model.n_vars
         b = P[:, 0]
         ws = P[:, 1:1 + F] if F else None
@@ -285,16 +288,18 @@ class Population:
         scale = glm.lkhd_scale.get_value()
         ll, gb, gw, gs = 0.0, 0.0, 0.0, 0.0
         for data in self.data_sequences:
-            l, b_, g, s_ = self._ll_grad_blocks(data, b, w, A, W, ws)
+            l, b_, g, s_ = self._ll_grad_blocks(data, b, w, A, W, ws, n_lo=n_lo, n_hi=n_hi)
             ll, gb, gw, gs = ll + scale * l, gb + scale * b_, gw + scale * g, gs + scale * s_
+        sl = slice(n_lo, n_hi)
+        b, V = b[sl], V[sl]
         bm = glm.bias_model
         lp = ll - 0.5 / bm.sig_bias ** 2 * (b - bm.mu_bias) ** 2 + glm.imp_model.batch_log_p(V)
-        grad = np.empty_like(P)
+        grad = np.empty((n_hi - n_lo, P.shape[1]))
         grad[:, 0] = gb - (b - bm.mu_bias) / bm.sig_bias ** 2
         if F:
             sig = glm.bkgd_model.prior_sigma
-            lp = lp + np.sum(-0.5 / sig ** 2 * ws ** 2, axis=1)
-            grad[:, 1:1 + F] = gs - ws / sig ** 2
+            lp = lp + np.sum(-0.5 / sig ** 2 * ws[sl] ** 2, axis=1)
+            grad[:, 1:1 + F] = gs - ws[sl] / sig ** 2
         grad[:, 1 + F:] = glm.imp_model.batch_chain_rule(V, gw) + glm.imp_model.batch_grad_log_p(V)
         return lp, grad
 

@@ -18,6 +18,19 @@ import torch
 import torch.distributed as dist
 
 
+def world_rank(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def collective_device(device_index=0, group=None):
+    """Where a collective's buffers must live: this rank's GPU under NCCL, host memory under gloo (CPU tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_backend(group) == "nccl":
+        return torch.device("cuda", int(device_index))
+    return torch.device("cpu")
+
+
 def neuron_shard(N, world_size, rank):
     """Contiguous block of postsynaptic neurons for `rank` (sizes differ by at most one)."""
     base, extra = divmod(N, world_size)
