@@ -43,6 +43,10 @@ WORKLOADS = {
     # second headline metric: collapsed Gibbs over A/W, batched delta-ll (sparse_weighted_model)
     "c3-gibbs": dict(N=256, T=1_000_000, B=5, gibbs=True, desc="network GLM N=256 T=1e6 bins: collapsed Gibbs over A/W (C3)"),
     "gibbs-small": dict(N=32, T=200_000, B=5, gibbs=True, desc="network GLM N=32 T=2e5 bins: collapsed Gibbs over A/W (smoke size)"),
+    # C5's population (N=4096, B=5) time-sharded: every GPU owns 2^17 bins (10.7 GB of planes; C5 proper is 1.25e6 bins per
+    # GPU = 102 GB), planes-only ingest; the per-step collective is the all-reduce of ll / g_bias / G = 671 MB
+    "c5-shard": dict(N=4096, T=131_072, B=5, x_dtype="planes",
+                     desc="N=4096 B=5, T=2^17 bins per GPU: time shard of the C5 population (ll+grad, 671 MB all-reduce per step)"),
 }
 METRIC = "GLM ll+grad evals/sec"
 UNIT = "evals/s"
@@ -54,7 +58,10 @@ def make_inputs(wl, seed):
     from theano_pyglm_b200.utils.basis import make_standard_ibasis
     N, T, B = wl["N"], wl["T"], wl["B"]
     rng = np.random.default_rng(seed)
-    S = (rng.random((T, N)) < 0.02).astype(np.uint8)
+    if T * N <= 300_000_000:
+        S = (rng.random((T, N)) < 0.02).astype(np.uint8)
+    else:                                   # large shards: one random byte per bin, p = 5/256
+        S = (rng.integers(0, 256, size=(T, N), dtype=np.uint8) < 5).astype(np.uint8)
     ib = make_standard_ibasis(B=B, dt=0.001, dt_max=0.2)
     bias = 20.0 + 0.1 * rng.standard_normal(N)
     w = 0.05 * rng.standard_normal((N, N * B))
@@ -346,10 +353,16 @@ def run_ours(args, wl):
     timer = Timer(torch, dist, world, dev, stream)
     rec = llgrad_record(args, wl, args.workload, pg, torch, dist, timer, world, rank, local_rank, comm, collective,
                         min_total_s=0.5, cpu_budget_s=0.0 if args.no_cpu else 10.0)
+    extra = None
+    if not args.no_extra and args.workload == "c2":
+        if world == 1:
+            extra = run_extras(args, pg, torch, dist, timer, local_rank) if rank == 0 else None
+        else:
+            extra = run_scale_extras(args, pg, torch, dist, timer, world, rank, local_rank)     # collective: every rank
     if rank == 0:
         line = rec
-        if world == 1 and not args.no_extra and args.workload == "c2":
-            line["extra"] = run_extras(args, pg, torch, dist, timer, local_rank)
+        if extra is not None:
+            line["extra"] = extra
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -434,6 +447,14 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
             raise SystemExit("host-buffer call and device-resident call disagree")
     else:
         ms_e2e, e2e_blocks = timer.blocks(step_e2e, args.steps, min_total_s)
+    ms_coll = None
+    if world > 1:                           # the collective alone, same buffer: latency at 29 KB, bandwidth at 671 MB
+        def coll():
+            if comm is not None:
+                comm.allreduce_sum_dev(d_out.data_ptr(), d_out.data_ptr(), d_out.numel(), stream.cuda_stream)
+            else:
+                dist.all_reduce(d_out)
+        ms_coll = timer.blocks(coll, 5, 0.0)[0] / 5
     clocks = sampler.stop() if rank == 0 else None
 
     # the same evaluation through the host-buffer C-ABI call a Python user makes (numpy in, numpy out; the library
@@ -469,6 +490,10 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
                         "timing": "median of %d blocks of %d steps (each block: barrier + synchronize both sides, CUDA events, "
                                   "max over ranks); timed total %.2f s" % (len(dev_blocks), args.steps, sum(dev_blocks) * 1e-3),
                         "block_ms_min_max": [min(dev_blocks), max(dev_blocks)]},
+            "collective_alone": None if ms_coll is None else {
+                "ms": ms_coll, "bytes": int(d_out.numel()) * 8,
+                "bus_GBps": 2.0 * (world - 1) / world * d_out.numel() * 8 / (ms_coll * 1e-3) / 1e9,
+                "reference": "8-rank NCCL all-reduce bus bandwidth 725 GB/s at 1 GiB (B200_PROFILING.md); SURVEY 5 ring estimate 1.3 ms for 671 MB"},
             "clocks": clocks,
             "e2e": {"value": world / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -487,6 +512,109 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
     del d_bias, d_w, d_out, e_bias, e_w, e_out
     torch.cuda.empty_cache()
     return line
+
+
+def run_scale_extras(args, pg, torch, dist, timer, world, rank, local_rank):
+    """Sub-records of the multi-GPU line: the C5 population time-sharded with its 671 MB all-reduce, and the collapsed
+    Gibbs sweep of C3 partitioned by postsynaptic neuron (north_star's two splits).  Every rank takes part; rank 0
+    returns the records."""
+    import copy
+    out = []
+    a5 = copy.copy(args)
+    a5.steps, a5.warmup = min(args.steps, 4), 2
+    jobs = [("scale_c5", lambda: llgrad_record(a5, WORKLOADS["c5-shard"], "c5-shard", pg, torch, dist, timer, world, rank,
+                                               local_rank, None, "nccl all_reduce (671 MB per step)", 0.0, 0.0)),
+            ("scale_gibbs", lambda: gibbs_sharded_record(args, WORKLOADS["c3-gibbs"], pg, torch, dist, timer, world, rank, local_rank))]
+    for name, job in jobs:
+        t0 = time.perf_counter()
+        ok = torch.ones(1, device=timer.dev)
+        rec = None
+        try:
+            rec = job()
+        except Exception as exc:
+            rec = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            rec = rec if rec is not None else {}
+            if ok.item() < 1 and "error" not in rec:
+                rec = {"error": "a peer rank failed"}
+            rec["name"] = name
+            rec["wall_s"] = time.perf_counter() - t0
+            out.append(rec)
+        torch.cuda.empty_cache()
+    return out if rank == 0 else None
+
+
+def gibbs_sharded_record(args, wl, pg, torch, dist, timer, world, rank, local_rank):
+    """Collapsed Gibbs over A/W partitioned by postsynaptic neuron (parallel_gibbs.py:162-168): every rank holds the
+    spikes of ALL presynaptic neurons (spikes-only dataset: K4 gathers its currents from the spike trains, no X), owns
+    the columns neuron_shard(N, world, rank) and resamples one edge per owned column per lock-step.  No collective
+    inside a sweep; the resampled columns of A (int8) and W (f64) are all-gathered over NCCL once per sweep.  Strong
+    scaling: the N^2 edges of one sweep are divided among the GPUs."""
+    from theano_pyglm_b200.utils.parallel_util import neuron_shard
+    N, T, B = wl["N"], wl["T"], wl["B"]
+    Q = 11
+    dev = timer.dev
+    stream = timer.stream
+    inp = make_gibbs_inputs(wl, 1234)                       # the same recording and state on every rank
+    n_lo, n_hi = neuron_shard(N, world, rank)
+    nc = n_hi - n_lo
+    ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], x_dtype="none", device=local_rank)
+    ds.gibbs_begin(inp["bias"], inp["w"], inp["A"], inp["W"], nlin="explinear", n_lo=n_lo, n_hi=n_hi)
+    rng = np.random.default_rng(7)
+    orders = np.stack([rng.permutation(N) for _ in range(N)])
+    xs, _ws = np.polynomial.hermite.hermgauss(10)
+    cols = np.arange(n_lo, n_hi, dtype=np.int32)
+    pres0 = orders[n_lo:n_hi, 0].astype(np.int32)
+    diag = pres0 == cols
+    cand = np.concatenate([np.sqrt(2) * np.where(diag, 0.5, 1.0)[:, None] * xs[None, :] + np.where(diag, -0.2, 0.0)[:, None],
+                           np.zeros((nc, 1))], axis=1)
+    d_cols, d_pres = torch.from_numpy(cols).to(dev), torch.from_numpy(pres0).to(dev)
+    d_cand = torch.from_numpy(cand).to(dev)
+    d_out = torch.empty((nc, Q), dtype=torch.float64, device=dev)
+
+    def step():
+        ds.gibbs_delta_ll_dev(nc, d_cols.data_ptr(), d_pres.data_ptr(), Q, d_cand.data_ptr(), d_out.data_ptr(), stream.cuda_stream)
+
+    # the per-sweep splice: owners' columns of A and W to every rank
+    wmax = -(-N // world)
+    a_mine = torch.zeros((wmax, N), dtype=torch.int8, device=dev)
+    w_mine = torch.zeros((wmax, N), dtype=torch.float64, device=dev)
+    a_all = torch.empty((world * wmax, N), dtype=torch.int8, device=dev)
+    w_all = torch.empty((world * wmax, N), dtype=torch.float64, device=dev)
+
+    def gather():
+        dist.all_gather_into_tensor(a_all, a_mine)
+        dist.all_gather_into_tensor(w_all, w_mine)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    gather()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_blk, blocks = timer.blocks(step, args.steps, 0.3, max_blocks=50)
+    ms_step = ms_blk / args.steps
+    ms_gather = timer.blocks(gather, 5, 0.0)[0] / 5
+    clocks = sampler.stop() if rank == 0 else None
+    ds.gibbs_end()
+    ds.close()
+    if rank != 0:
+        return None
+    sweep_ms = N * ms_step + ms_gather
+    return {"metric": "Gibbs edge-sweeps/sec", "value": 1e3 / sweep_ms, "unit": "sweeps/s", "n_gpus": world,
+            "steps": args.steps, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": wl["desc"], "N": N, "T_bins_per_gpu": T, "B": B, "R": 200, "nlin": "explinear",
+                       "candidates_per_edge": Q, "l2": "inputs_exceed_l2"},
+            "details": {"sharding": "by postsynaptic neuron: %d columns per GPU, all presynaptic spike trains on every GPU "
+                                    "(spikes-only dataset, from-spikes K4)" % wmax,
+                        "step": "one lock-step = one edge per owned column x 11 candidate weights; a sweep is N steps + one splice",
+                        "collective": "NCCL all_gather of A[:, n] (int8) and W[:, n] (f64) once per sweep",
+                        "splice_ms": ms_gather, "sweep_ms": sweep_ms, "blocks": len(blocks),
+                        "ars": "excluded (W | A=1 from the prior, as in the single-GPU record)"},
+            "clocks": clocks, "gpu_launches": 2 * args.steps}
 
 
 def filter_record(args, pg, torch, timer, local_rank):

@@ -61,6 +61,11 @@ extern "C" {
  * element); the FP64 path, firing_rate, get_fS and the Gibbs entry points are unavailable.  For
  * recordings whose FP32 X would not fit next to the planes (configs C4/C5 shards). */
 #define PYGLM_B200_X_PLANES 2
+/* spikes only: neither X nor its planes are built.  Only the Gibbs entry points are available; they gather the
+ * presynaptic currents from the spike trains (one byte per bin instead of B filtered values), which is what lets one
+ * GPU of a neuron-sharded run hold ALL presynaptic data of a population whose X would not fit (C4: 4 GB of spikes
+ * against 164 GB of X).  Planes-only datasets run Gibbs the same way. */
+#define PYGLM_B200_X_NONE 3
 
 /* arithmetic path for ll / gradient
  *   PATH_FP64  FP64 CUDA-core contractions over X as stored (exact path: 1e-11 on a float64 dataset).

@@ -261,7 +261,7 @@ def test_bad_arguments_raise(eng):
     ds.close()
 
 
-@pytest.mark.parametrize("x_dtype", ["f64", "f32"])
+@pytest.mark.parametrize("x_dtype", ["f64", "f32", "planes", "none"])
 def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
     """K4 vs gibbs.py:910-937 / :1002-1039 restated: candidate log-likelihoods, then identical
     A decisions for the same uniforms, through a whole shuffled column sweep with commits."""
@@ -278,7 +278,8 @@ def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
     # FP32 storage of X perturbs u = X.w at ~1e-8 relative; candidate lls are differences of O(1e4)
     # sums, so the FP32-X bound is absolute.  Decision parity is asserted for both; the sampler
     # itself uses FP64 X (Population picks x_dtype="f64" for MCMC).
-    rtol, atol = (1e-10, 1e-9) if x_dtype == "f64" else (1e-7, 2e-5)
+    # "planes" / "none" keep no X at all: K4 gathers its currents from the spike trains in FP64 (from-spikes mode)
+    rtol, atol = (1e-7, 2e-5) if x_dtype == "f32" else (1e-10, 1e-9)
     for n_post in (1, 4):
         order = rng.permutation(N)
         unif = rng.random(N)
@@ -310,6 +311,43 @@ def test_gibbs_delta_ll_and_decisions(eng, x_dtype):
         assert np.array_equal(batch[m], one[0])
     ds.gibbs_end()
     ds.close()
+
+
+@pytest.mark.parametrize("nlin", [orc.NLIN_SOFTPLUS, orc.NLIN_EXP])
+def test_gibbs_from_spikes_equals_the_filtered_spike_train_form(eng, nlin):
+    """From-spikes mode of K4 (u[t] = sum_k (ibasis . w)[k] S[t-k], X never read) against the X-based mode on the same
+    edges: several 8192-bin chunks (windows reach into the previous chunk), multi-spike bins, B = 10, a time shard with
+    a left halo, batched edges, and commits (rank-1 updates of the resident I_net) in between."""
+    T, N, B = 20011, 7, 10
+    p = make_problem(T, N, B, network=True, dirichlet=True, seed=31, rate=0.03)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 18.0
+        p['W'] = p['W'] * 0.05
+    rng = np.random.default_rng(2)
+    for lo, halo in ((0, 0), (5003, 200), (5003, 57)):
+        S = p['S'][lo - halo:]
+        ds_x = eng.Dataset(S, p['dt'], p['ibasis'], halo=halo, x_dtype="f64")
+        ds_s = eng.Dataset(S, p['dt'], p['ibasis'], halo=halo, x_dtype="none")
+        with pytest.raises(eng.EngineError):
+            ds_s.ll(p['bias'], p['w'], p['A'], p['W'])                 # spikes-only: no likelihood path
+        for ds in (ds_x, ds_s):
+            ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)
+        for rnd in range(3):
+            cols = rng.permutation(N)[:5]
+            pres = rng.integers(0, N, size=5)
+            cand = rng.standard_normal((5, 11)) * (0.05 if nlin == orc.NLIN_EXP else 1.0)
+            a, b = ds_x.gibbs_delta_ll(cols, pres, cand), ds_s.gibbs_delta_ll(cols, pres, cand)
+            assert np.allclose(a, b, rtol=1e-10, atol=1e-9), (lo, halo, rnd, np.max(np.abs(a - b)))
+            a_new = rng.integers(0, 2, size=5).astype(np.int8)
+            w_new = rng.standard_normal(5) * (0.05 if nlin == orc.NLIN_EXP else 1.0)
+            for ds in (ds_x, ds_s):
+                ds.gibbs_commit(cols, pres, a_new, w_new)
+        Ax, Wx = ds_x.gibbs_state()
+        As, Ws = ds_s.gibbs_state()
+        assert np.array_equal(Ax, As) and np.array_equal(Wx, Ws)
+        for ds in (ds_x, ds_s):
+            ds.gibbs_end()
+            ds.close()
 
 
 # ----------------------------------------------------------------------------------------------

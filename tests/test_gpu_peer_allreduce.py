@@ -197,5 +197,5 @@ def test_neuron_sharded_map_matches_the_serial_coordinate_descent(engine_lib):
         assert pr.exitcode == 0
     assert np.array_equal(res[0][0], res[1][0])                     # one state on both ranks
     assert res[0][1] == res[1][1]                                   # the all-reduced log posterior
-    assert abs(res[0][1] - res[0][2]) < 1e-9 * abs(res[0][2])       # ... equals the single-process evaluation
+    assert abs(res[0][1] - res[0][2]) < 1e-7 * abs(res[0][2])       # ... equals the single-process evaluation
     assert np.allclose(res[0][0], res[0][3], rtol=1e-6, atol=1e-8)  # and the serial driver's optimum

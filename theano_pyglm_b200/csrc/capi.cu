@@ -94,6 +94,7 @@ struct pyglm_b200_dataset {
 
     // Gibbs state
     bool gibbs_active = false;
+    bool g_spk = false;                // from-spikes mode: currents gathered from St, X never read
     int g_nlo = 0, g_ncols = 0, g_nlin = 0;
     DevBuf<double> g_bias, g_w, g_W, Inet, partial, g_wcand, g_out, g_wnew;
     DevBuf<int8_t> g_A, g_anew;
@@ -175,12 +176,12 @@ int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, in
     PYGLM_REQUIRE(R >= 1 && B >= 1 && B <= kMaxBasis, "dataset_create: bad basis shape R=%d B=%d (B<=%d)", R, B, kMaxBasis);
     PYGLM_REQUIRE(S != nullptr || (T + halo) == 0, "dataset_create: S is null");
     PYGLM_REQUIRE(ibasis != nullptr, "dataset_create: ibasis is null");
-    PYGLM_REQUIRE(x_dtype == PYGLM_B200_X_F32 || x_dtype == PYGLM_B200_X_F64 || x_dtype == PYGLM_B200_X_PLANES,
-                  "dataset_create: bad x_dtype %d", x_dtype);
+    PYGLM_REQUIRE(x_dtype == PYGLM_B200_X_F32 || x_dtype == PYGLM_B200_X_F64 || x_dtype == PYGLM_B200_X_PLANES ||
+                  x_dtype == PYGLM_B200_X_NONE, "dataset_create: bad x_dtype %d", x_dtype);
     PYGLM_REQUIRE(dt > 0.0, "dataset_create: dt must be positive");
     PYGLM_REQUIRE(F >= 0 && (F == 0 || fstim != nullptr || T == 0), "dataset_create: bad stimulus block F=%d", F);
-    if (F > 0 && x_dtype == PYGLM_B200_X_PLANES) {
-        set_error("dataset_create: stimulus features are not available for planes-only datasets");
+    if (F > 0 && (x_dtype == PYGLM_B200_X_PLANES || x_dtype == PYGLM_B200_X_NONE)) {
+        set_error("dataset_create: stimulus features need a resident filtered spike train (x_dtype F32 / F64)");
         return PYGLM_B200_EUNSUPPORTED;
     }
     PYGLM_CUDA(cudaSetDevice(device));
@@ -199,9 +200,9 @@ int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, in
 
     const size_t nS = (size_t)(T + halo) * N;
     const size_t esz = x_dtype == PYGLM_B200_X_F64 ? 8 : 4;
-    const bool planes_only = x_dtype == PYGLM_B200_X_PLANES;
+    const bool planes_only = x_dtype == PYGLM_B200_X_PLANES || x_dtype == PYGLM_B200_X_NONE;   // no FP32 / FP64 X resident
     int rc;
-    if ((rc = ds->S.ensure(nS ? nS : 1)) || (rc = ds->St.ensure(planes_only || (size_t)T * N == 0 ? 1 : (size_t)T * N)) ||
+    if ((rc = ds->S.ensure(nS ? nS : 1)) || (rc = ds->St.ensure(nS ? nS : 1)) ||
         (rc = ds->X.ensure(planes_only || (size_t)T * ds->ldx * esz == 0 ? 1 : (size_t)T * ds->ldx * esz)) ||
         (rc = ds->ibasis.ensure((size_t)R * B)))
         return fail(rc);
@@ -209,10 +210,14 @@ int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, in
     if (nS) CK(cudaMemcpyAsync(ds->S.p, S, nS, cudaMemcpyHostToDevice, ds->stream));
     CK(cudaMemcpyAsync(ds->ibasis.p, ibasis, (size_t)R * B * sizeof(double), cudaMemcpyHostToDevice, ds->stream));
     CK(cudaMemsetAsync(ds->X.p, 0, ds->X.n, ds->stream));
-    if (planes_only) {
+    if (x_dtype == PYGLM_B200_X_NONE) {
+        // spikes only: nothing to filter (the Gibbs entry points gather their currents from the spikes)
+    } else if (planes_only) {
         if (T > 0 && (rc = tc_build_planes_streaming(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->stream))) return fail(rc);
     } else if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->X.p, ds->ldx, x_dtype, ds->stream))) return fail(rc);
-    if (!planes_only && (rc = launch_transpose_spikes(ds->S.p, T, N, halo, ds->St.p, ds->stream))) return fail(rc);
+    // spikes by column, halo bins included: St[n][halo + T] (K4 reads per-column streams, and in from-spikes mode the
+    // R bins before a chunk)
+    if ((rc = launch_transpose_spikes(ds->S.p, T + halo, N, 0, ds->St.p, ds->stream))) return fail(rc);
     if (F > 0 && T > 0) {
         DevBuf<double> d_fs;
         if ((rc = d_fs.ensure((size_t)T * F))) return fail(rc);
@@ -272,7 +277,7 @@ int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
 {
     DS_GUARD(ds);
     PYGLM_REQUIRE(out != nullptr, "get_fS: out is null");
-    if (ds->x_dtype == PYGLM_B200_X_PLANES) { set_error("get_fS: planes-only dataset keeps no filtered spike train"); return PYGLM_B200_EUNSUPPORTED; }
+    if (ds->x_dtype == PYGLM_B200_X_PLANES || ds->x_dtype == PYGLM_B200_X_NONE) { set_error("get_fS: this dataset keeps no filtered spike train"); return PYGLM_B200_EUNSUPPORTED; }
     const int64_t NB = (int64_t)ds->N * ds->B;
     if (ds->T == 0) return PYGLM_B200_OK;
     PYGLM_CUDA(cudaStreamSynchronize(ds->stream));
@@ -298,7 +303,7 @@ int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
 int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
 {
     DS_GUARD(ds);
-    if (ds->x_dtype == PYGLM_B200_X_PLANES) { set_error("refilter: planes-only dataset"); return PYGLM_B200_EUNSUPPORTED; }
+    if (ds->x_dtype == PYGLM_B200_X_PLANES || ds->x_dtype == PYGLM_B200_X_NONE) { set_error("refilter: no filtered spike train is resident"); return PYGLM_B200_EUNSUPPORTED; }
     ds->xt_ready = false;
     return launch_filter(ds->S.p, ds->T, ds->N, ds->halo, ds->ibasis.p, ds->R, ds->B, ds->X.p, ds->ldx,
                          ds->x_dtype, (cudaStream_t)stream);
@@ -307,6 +312,7 @@ int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
 // ------------------------------------------------------------------------------------
 static int resolve_path(const pyglm_b200_dataset* ds, int path, bool need_aux)
 {
+    if (ds->x_dtype == PYGLM_B200_X_NONE) return -1;
     const bool planes_only = ds->x_dtype == PYGLM_B200_X_PLANES;
     if (path == PYGLM_B200_PATH_FP64) return planes_only ? -1 : PYGLM_B200_PATH_FP64;
     const bool tc_ok = (planes_only || tc_supported(ds->T, ds->N, ds->B, ds->x_dtype)) && !need_aux;
@@ -625,7 +631,9 @@ static GibbsArgs gibbs_args(pyglm_b200_dataset* ds)
 {
     GibbsArgs g{};
     g.X = ds->Xt.p; g.ldx = ds->ldx; g.x_dtype = ds->x_dtype;
-    g.St = ds->St.p; g.T = ds->T; g.N = ds->N; g.B = ds->B; g.F = ds->F;
+    g.ldst = ds->T + ds->halo; g.halo = ds->halo; g.St = ds->St.p + ds->halo;
+    g.ibasis = ds->ibasis.p; g.R = ds->R; g.spk = ds->g_spk ? 1 : 0;
+    g.T = ds->T; g.N = ds->N; g.B = ds->B; g.F = ds->F;
     g.dt = ds->dt; g.nlin = ds->g_nlin; g.n_lo = ds->g_nlo; g.ncols = ds->g_ncols;
     g.bias = ds->g_bias.p; g.w = ds->g_w.p; g.A = ds->g_A.p; g.W = ds->g_W.p;
     g.Inet = ds->Inet.p; g.partial = ds->partial.p; g.nchunks = gibbs_num_chunks(ds->T);
@@ -640,23 +648,40 @@ int pyglm_b200_gibbs_begin(pyglm_b200_dataset* ds,
     PYGLM_REQUIRE(nlin == PYGLM_B200_NLIN_EXP || nlin == PYGLM_B200_NLIN_SOFTPLUS, "bad nlin %d", nlin);
     PYGLM_REQUIRE(0 <= n_lo && n_lo < n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
     PYGLM_REQUIRE(A && W, "gibbs_begin needs explicit A and W");
-    if (ds->x_dtype == PYGLM_B200_X_PLANES) { set_error("gibbs_begin: planes-only dataset"); return PYGLM_B200_EUNSUPPORTED; }
+    // From-spikes mode (forced by PYGLM_GIBBS_FROM_SPIKES=1, the only mode of planes-only / spikes-only datasets): the
+    // presynaptic currents are gathered from the spike trains, no feature-major copy of X is built or read.
+    bool spk = ds->x_dtype == PYGLM_B200_X_PLANES || ds->x_dtype == PYGLM_B200_X_NONE;
+    if (const char* env = getenv("PYGLM_GIBBS_FROM_SPIKES")) spk = spk || atoi(env) != 0;
+    if (spk && (ds->F > 0 || ds->R > kGibbsMaxLagsFromSpikes)) {
+        if (ds->x_dtype == PYGLM_B200_X_PLANES || ds->x_dtype == PYGLM_B200_X_NONE) {
+            set_error("gibbs_begin: from-spikes mode needs F = 0 and R <= %d", kGibbsMaxLagsFromSpikes);
+            return PYGLM_B200_EUNSUPPORTED;
+        }
+        spk = false;
+    }
     cudaStream_t st = ds->stream;
     ds->gibbs_active = false;
+    ds->g_spk = spk;
     TRY(stage_params(ds, bias, w, A, W, ds->g_bias, ds->g_w, ds->g_A, ds->g_W, st));
     const int ncols = n_hi - n_lo;
-    if (!ds->xt_ready) {
-        const size_t esz = ds->x_dtype == PYGLM_B200_X_F32 ? 4 : 8;
-        const size_t NB = (size_t)ds->N * ds->B;
-        TRY(ds->Xt.ensure(NB * (ds->T ? ds->T : 1) * esz));
-        TRY(launch_transpose_X(ds->X.p, ds->T, (int64_t)NB, ds->ldx, ds->x_dtype, ds->Xt.p, st));
-        ds->xt_ready = true;
-    }
     TRY(ds->Inet.ensure((size_t)ncols * (ds->T ? ds->T : 1)));
-    TRY(ds->o_ll.ensure(ncols));
-    // I_net[:, n] = I_imp @ (A[:,n] * W[:,n])  (glm.py:39) via the FP64 forward contraction
-    TRY(ll_grad_dev_impl(ds, ds->g_bias.p, ds->g_w.p, ds->g_A.p, ds->g_W.p, nlin, n_lo, n_hi, PYGLM_B200_PATH_FP64,
-                         ds->o_ll.p, nullptr, nullptr, ds->Inet.p, nullptr, st));
+    if (spk) {
+        ds->g_nlo = n_lo; ds->g_ncols = ncols; ds->g_nlin = nlin;
+        GibbsArgs g = gibbs_args(ds);
+        TRY(launch_gibbs_inet_from_spikes(g, st));
+    } else {
+        if (!ds->xt_ready) {
+            const size_t esz = ds->x_dtype == PYGLM_B200_X_F32 ? 4 : 8;
+            const size_t NB = (size_t)ds->N * ds->B;
+            TRY(ds->Xt.ensure(NB * (ds->T ? ds->T : 1) * esz));
+            TRY(launch_transpose_X(ds->X.p, ds->T, (int64_t)NB, ds->ldx, ds->x_dtype, ds->Xt.p, st));
+            ds->xt_ready = true;
+        }
+        TRY(ds->o_ll.ensure(ncols));
+        // I_net[:, n] = I_imp @ (A[:,n] * W[:,n])  (glm.py:39) via the FP64 forward contraction
+        TRY(ll_grad_dev_impl(ds, ds->g_bias.p, ds->g_w.p, ds->g_A.p, ds->g_W.p, nlin, n_lo, n_hi, PYGLM_B200_PATH_FP64,
+                             ds->o_ll.p, nullptr, nullptr, ds->Inet.p, nullptr, st));
+    }
     PYGLM_CUDA(cudaStreamSynchronize(st));
     ds->g_nlo = n_lo; ds->g_ncols = ncols; ds->g_nlin = nlin;
     ds->gibbs_active = true;

@@ -86,8 +86,11 @@ int simt_choose_splits(int64_t T, int64_t NF, int Np);
 int launch_simt_ll_grad(const SimtArgs& a, cudaStream_t stream);
 
 struct GibbsArgs {
-    const void* X; int64_t ldx; int x_dtype;     // X here is the feature-major copy Xt[j][t]
-    const uint8_t* St; int64_t T; int N; int B; int F;
+    const void* X; int64_t ldx; int x_dtype;     // X here is the feature-major copy Xt[j][t] (unused when spk != 0)
+    const uint8_t* St; int64_t ldst; int halo;   // spikes by column: St[n * ldst + t], t in [-halo, T)
+    const double* ibasis; int R;                 // [R][B] interpolated basis (from-spikes mode)
+    int spk;                                     // != 0: the presynaptic current u[t] is gathered from the spikes, X is never read
+    int64_t T; int N; int B; int F;
     double dt; int nlin;
     int n_lo, ncols;
     const double* bias;      // [N]
@@ -103,6 +106,9 @@ int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const i
                        const double* d_wcand, double* d_out, cudaStream_t stream);
 int launch_gibbs_commit(const GibbsArgs& g, int M, const int32_t* d_cols, const int32_t* d_pres,
                         const int8_t* d_anew, const double* d_wnew, cudaStream_t stream);
+// from-spikes mode: I_net[nl][t] = sum_pre (A W)[pre][n] * sum_k h_pre[k] S[t-k][pre] for the resident columns
+int launch_gibbs_inet_from_spikes(const GibbsArgs& g, cudaStream_t stream);
+constexpr int kGibbsMaxLagsFromSpikes = 2048;
 
 // ---------------------------------------------------------------------------------
 // Device math shared by K2/K4: nonlinearity, its derivative and log, in FP64.

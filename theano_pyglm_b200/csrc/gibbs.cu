@@ -155,13 +155,98 @@ static int ensure_softplus_table()
     return PYGLM_B200_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// From-spikes mode: u[t] = I_imp[t, pre] = sum_b X[t, pre, b] w_b = sum_{k=1..R} h[k-1] S[t-k][pre],  h = ibasis . w
+// (utils/basis.py:201-236 folded into impulse.py:58).  X (T x N x B) is never read: one byte per bin of the
+// presynaptic spike train instead of B values, which is what lets a GPU hold a population whose filtered spike train
+// would not fit (C4: 164 GB of X, 4 GB of spikes).  Spikes are sparse, so the block compacts the spikes of its chunk
+// plus the R-bin left context into a list and scatters c * h[lag] into the chunk's u, spike by spike in time order
+// (a fixed summation order; a barrier separates spikes because neighbouring spikes write the same bins).
+// Shared memory: su [kGibbsChunk] doubles | sh [R] doubles | spos [kGibbsChunk + R] u16 | scnt [kGibbsChunk + R] u8.
+// ---------------------------------------------------------------------------------------------
+struct SpkSmem {
+    double* su; double* sh; unsigned short* spos; unsigned char* scnt;
+};
+static inline size_t spk_smem_bytes(int R)
+{
+    const size_t W = (size_t)kGibbsChunk + R;
+    return (size_t)kGibbsChunk * 8 + (size_t)round_up(R, 2) * 8 + round_up(W * 2, 16) + round_up(W, 16);
+}
+__device__ inline SpkSmem spk_carve(unsigned char* base, int R)
+{
+    SpkSmem m;
+    const size_t W = (size_t)kGibbsChunk + R;
+    m.su = reinterpret_cast<double*>(base);
+    m.sh = m.su + kGibbsChunk;
+    m.spos = reinterpret_cast<unsigned short*>(m.sh + ((R + 1) & ~1));
+    m.scnt = reinterpret_cast<unsigned char*>(m.spos) + ((W * 2 + 15) & ~(size_t)15);
+    return m;
+}
+
+// Adds scale * sum_b ibasis[l][b] w[b] convolved with the spikes of row `st_pre` (indexable from -halo) into
+// su[0 .. nbins) for the bins [tbeg, tbeg + nbins).  All threads of the block must call it; su is NOT cleared.
+__device__ void spk_accumulate_u(const SpkSmem& m, const uint8_t* __restrict__ st_pre, int halo, int64_t tbeg, int nbins,
+                                 const double* __restrict__ ibasis, int R, int B, const double* __restrict__ w, double scale,
+                                 int* s_scan /* [kGibbsThreads / 32 + 1] */)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int l = tid; l < R; l += kGibbsThreads) {
+        double h = 0.0;
+        for (int b = 0; b < B; ++b) h = fma(ibasis[(int64_t)l * B + b], w[b], h);
+        m.sh[l] = h * scale;
+    }
+    // spikes of the window [tbeg - R, tbeg + nbins - 1): each thread scans a contiguous segment (time order is kept)
+    const int W = R + nbins - 1;
+    const int seg = (W + kGibbsThreads - 1) / kGibbsThreads;
+    const int p0 = tid * seg, p1 = min(W, p0 + seg);
+    int cnt = 0;
+    for (int p = p0; p < p1; ++p) {
+        const int64_t t = tbeg - R + p;
+        cnt += (t >= -(int64_t)halo && st_pre[t] != 0) ? 1 : 0;
+    }
+    int incl = cnt;                                       // block-wide exclusive scan of the counts
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < kGibbsThreads / 32; ++i) { const int v = s_scan[i]; s_scan[i] = run; run += v; }
+        s_scan[kGibbsThreads / 32] = run;
+    }
+    __syncthreads();
+    int k = s_scan[warp] + incl - cnt;
+    const int nspk = s_scan[kGibbsThreads / 32];
+    for (int p = p0; p < p1; ++p) {
+        const int64_t t = tbeg - R + p;
+        const unsigned char c = t >= -(int64_t)halo ? st_pre[t] : (unsigned char)0;
+        if (c) { m.spos[k] = (unsigned short)p; m.scnt[k] = c; ++k; }
+    }
+    __syncthreads();
+    // spike at window position p (bin tbeg - R + p) reaches bins tbeg - R + p + 1 + l, l in [0, R): index p + 1 + l - R
+    for (int s = 0; s < nspk; ++s) {
+        const int base = (int)m.spos[s] + 1 - R;
+        const double c = (double)m.scnt[s];
+        for (int l = tid; l < R; l += kGibbsThreads) {
+            const int idx = base + l;
+            if (idx >= 0 && idx < nbins) m.su[idx] = fma(c, m.sh[l], m.su[idx]);
+        }
+        __syncthreads();
+    }
+}
+
 // log(lam) of the Poisson term is needed only in the ~2% of bins that hold a spike.  Those bins are handed to
 // the whole warp: lane q evaluates candidate q, so one FP64 log serves all candidates.
-template <typename XT, int QMAX, int NLIN, int BMAX>
+template <typename XT, int QMAX, int NLIN, int BMAX, bool SPK>
 __global__ void __launch_bounds__(kGibbsThreads, PYGLM_GIBBS_MINBLOCKS)
 gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t* __restrict__ pres,
                    int Q, const double* __restrict__ wcand)
 {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ int sScan[kGibbsThreads / 32 + 1];
     __shared__ double sW[kMaxBasis];
     __shared__ double sRed[QMAX][kGibbsThreads / 32];
     __shared__ double sRedSp[kGibbsThreads / 32][32];
@@ -193,8 +278,15 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     const int64_t tbeg = (int64_t)blockIdx.x * kGibbsChunk;
     const int64_t tend = min(g.T, tbeg + kGibbsChunk);
     const double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
-    const uint8_t* __restrict__ st = g.St + (int64_t)col * g.T;
-    const XT* __restrict__ xcol = X + (int64_t)pre * g.B * g.T;      // feature-major copy: Xt[j][t]
+    const uint8_t* __restrict__ st = g.St + (int64_t)col * g.ldst;
+    const XT* __restrict__ xcol = SPK ? nullptr : X + (int64_t)pre * g.B * g.T;      // feature-major copy: Xt[j][t]
+    SpkSmem spk{};
+    if (SPK) {                                             // u of the whole chunk from the presynaptic spike train
+        spk = spk_carve(dyn_smem, g.R);
+        for (int i = tid; i < kGibbsChunk; i += kGibbsThreads) spk.su[i] = 0.0;
+        __syncthreads();
+        spk_accumulate_u(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.R, g.B, sW, 1.0, sScan);
+    }
 
     // the operands of the next 256 bins are fetched while the current ones are evaluated
     XT xr[BMAX];
@@ -204,8 +296,10 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     do {                                                                                        \
         const int64_t tt_ = (TT);                                                               \
         const bool lv_ = tt_ < tend;                                                            \
-        _Pragma("unroll") for (int b = 0; b < BMAX; ++b)                                        \
-            xr[b] = (lv_ && b < g.B) ? xcol[(int64_t)b * g.T + tt_] : (XT)0;                    \
+        if (!SPK) {                                                                             \
+            _Pragma("unroll") for (int b = 0; b < BMAX; ++b)                                    \
+                xr[b] = (lv_ && b < g.B) ? xcol[(int64_t)b * g.T + tt_] : (XT)0;                \
+        }                                                                                       \
         ir = lv_ ? inet[tt_] : 0.0;                                                             \
         sr = lv_ ? (unsigned)st[tt_] : 0u;                                                      \
     } while (0)
@@ -214,8 +308,12 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     for (int64_t t0 = tbeg; t0 < tend; t0 += kGibbsThreads) {        // warp-uniform trip count
         const bool live = t0 + tid < tend;
         double u = 0.0;
+        if (SPK) {
+            u = live ? spk.su[(int)(t0 - tbeg) + tid] : 0.0;
+        } else {
 #pragma unroll
-        for (int b = 0; b < BMAX; ++b) u = fma((double)xr[b], sW[b], u);
+            for (int b = 0; b < BMAX; ++b) u = fma((double)xr[b], sW[b], u);
+        }
         const double base = bias + (ir - aw_old * u);
         const double s = (double)sr;
         PYGLM_GIBBS_FETCH(t0 + kGibbsThreads + tid);
@@ -286,11 +384,13 @@ __global__ void gibbs_reduce_kernel(const double* __restrict__ partial, int M, i
     out[idx] = s;
 }
 
-template <typename XT>
+template <typename XT, bool SPK>
 __global__ void __launch_bounds__(kGibbsThreads)
 gibbs_commit_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t* __restrict__ pres,
                     const int8_t* __restrict__ anew, const double* __restrict__ wnew)
 {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ int sScan[kGibbsThreads / 32 + 1];
     __shared__ double sW[kMaxBasis];
     const XT* __restrict__ X = static_cast<const XT*>(g.X);
     const int m = blockIdx.y;
@@ -307,12 +407,59 @@ gibbs_commit_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t
     const int64_t tbeg = (int64_t)blockIdx.x * kGibbsChunk;
     const int64_t tend = min(g.T, tbeg + kGibbsChunk);
     double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
+    if (SPK) {
+        SpkSmem spk = spk_carve(dyn_smem, g.R);
+        for (int i = tid; i < kGibbsChunk; i += kGibbsThreads) spk.su[i] = 0.0;
+        __syncthreads();
+        spk_accumulate_u(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.R, g.B, sW, 1.0, sScan);
+        for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) inet[t] += delta * spk.su[(int)(t - tbeg)];
+        return;
+    }
     const XT* __restrict__ xcol = X + (int64_t)pre * g.B * g.T;
     for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) {
         double u = 0.0;
         for (int b = 0; b < g.B; ++b) u += (double)xcol[(int64_t)b * g.T + t] * sW[b];
         inet[t] += delta * u;
     }
+}
+
+// I_net of the resident columns from the spikes alone (== seval(glm.I_net), glm.py:39): block = (chunk, column); the
+// presynaptic neurons with A W != 0 are visited in index order and their currents accumulate in shared memory.
+__global__ void __launch_bounds__(kGibbsThreads)
+gibbs_inet_spk_kernel(GibbsArgs g)
+{
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    __shared__ int sScan[kGibbsThreads / 32 + 1];
+    __shared__ double sW[kMaxBasis];
+    const int nl = blockIdx.y, col = g.n_lo + nl;
+    const int tid = threadIdx.x;
+    const int64_t NB = (int64_t)g.N * g.B + g.F;
+    const int64_t tbeg = (int64_t)blockIdx.x * kGibbsChunk;
+    const int64_t tend = min(g.T, tbeg + kGibbsChunk);
+    SpkSmem spk = spk_carve(dyn_smem, g.R);
+    for (int i = tid; i < kGibbsChunk; i += kGibbsThreads) spk.su[i] = 0.0;
+    for (int pre = 0; pre < g.N; ++pre) {
+        const double aw = (double)g.A[(int64_t)pre * g.N + col] * g.W[(int64_t)pre * g.N + col];
+        if (aw == 0.0) continue;                            // block-uniform
+        __syncthreads();
+        if (tid < kMaxBasis) sW[tid] = tid < g.B ? g.w[(int64_t)col * NB + (int64_t)pre * g.B + tid] : 0.0;
+        __syncthreads();
+        spk_accumulate_u(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.R, g.B, sW, aw, sScan);
+    }
+    __syncthreads();
+    double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
+    for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) inet[t] = spk.su[(int)(t - tbeg)];
+}
+
+int launch_gibbs_inet_from_spikes(const GibbsArgs& g, cudaStream_t stream)
+{
+    if (g.T <= 0 || g.ncols <= 0) return PYGLM_B200_OK;
+    const size_t smem = spk_smem_bytes(g.R);
+    PYGLM_CUDA(cudaFuncSetAttribute(gibbs_inet_spk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)g.nchunks, (unsigned)g.ncols);
+    gibbs_inet_spk_kernel<<<grid, kGibbsThreads, smem, stream>>>(g);
+    PYGLM_CUDA(cudaGetLastError());
+    return PYGLM_B200_OK;
 }
 
 __global__ void gibbs_store_state_kernel(int8_t* A, double* W, int N, int M, const int32_t* cols,
@@ -369,12 +516,30 @@ int launch_gibbs_delta(const GibbsArgs& g, int M, const int32_t* d_cols, const i
     const bool f32 = g.x_dtype == PYGLM_B200_X_F32;
     const bool sp = g.nlin == PYGLM_B200_NLIN_SOFTPLUS;
     if (sp) { int rc = ensure_softplus_table(); if (rc) return rc; }
+    if (g.spk) {                                            // u from the spikes: X is not read, one instantiation per (Q, nlin)
+        const size_t smem = spk_smem_bytes(g.R);
+#define PYGLM_GIBBS_SPK(QM)                                                                                            \
+        do {                                                                                                           \
+            auto kern = sp ? gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_SOFTPLUS, 1, true>                         \
+                           : gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_EXP, 1, true>;                             \
+            PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+            kern<<<grid, kGibbsThreads, smem, stream>>>(g, d_cols, d_pres, Q, d_wcand);                                \
+        } while (0)
+        if (Q <= 4) PYGLM_GIBBS_SPK(4);
+        else if (Q <= 11) PYGLM_GIBBS_SPK(11);
+        else PYGLM_GIBBS_SPK(16);
+#undef PYGLM_GIBBS_SPK
+        PYGLM_CUDA(cudaGetLastError());
+        gibbs_reduce_kernel<<<(unsigned)ceil_div((int64_t)M * Q, 128), 128, 0, stream>>>(g.partial, M, g.nchunks, Q, d_out);
+        PYGLM_CUDA(cudaGetLastError());
+        return PYGLM_B200_OK;
+    }
 #define PYGLM_GIBBS_LAUNCH3(QM, BM)                                                                                   \
     do {                                                                                                               \
-        if (f32 && sp)       gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_SOFTPLUS, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
-        else if (f32)        gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_EXP, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);      \
-        else if (sp)         gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_SOFTPLUS, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
-        else                 gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_EXP, BM><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);     \
+        if (f32 && sp)       gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_SOFTPLUS, BM, false><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
+        else if (f32)        gibbs_delta_kernel<float, QM, PYGLM_B200_NLIN_EXP, BM, false><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);      \
+        else if (sp)         gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_SOFTPLUS, BM, false><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand); \
+        else                 gibbs_delta_kernel<double, QM, PYGLM_B200_NLIN_EXP, BM, false><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, Q, d_wcand);     \
     } while (0)
 #define PYGLM_GIBBS_LAUNCH(QM)                                                                                         \
     do {                                                                                                               \
@@ -398,10 +563,14 @@ int launch_gibbs_commit(const GibbsArgs& g, int M, const int32_t* d_cols, const 
 {
     if (M <= 0) return PYGLM_B200_OK;
     dim3 grid((unsigned)g.nchunks, (unsigned)M);
-    if (g.x_dtype == PYGLM_B200_X_F32)
-        gibbs_commit_kernel<float><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, d_anew, d_wnew);
+    if (g.spk) {
+        const size_t smem = spk_smem_bytes(g.R);
+        PYGLM_CUDA(cudaFuncSetAttribute(gibbs_commit_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gibbs_commit_kernel<double, true><<<grid, kGibbsThreads, smem, stream>>>(g, d_cols, d_pres, d_anew, d_wnew);
+    } else if (g.x_dtype == PYGLM_B200_X_F32)
+        gibbs_commit_kernel<float, false><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, d_anew, d_wnew);
     else
-        gibbs_commit_kernel<double><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, d_anew, d_wnew);
+        gibbs_commit_kernel<double, false><<<grid, kGibbsThreads, 0, stream>>>(g, d_cols, d_pres, d_anew, d_wnew);
     PYGLM_CUDA(cudaGetLastError());
     gibbs_store_state_kernel<<<(unsigned)ceil_div(M, 128), 128, 0, stream>>>(g.A, g.W, g.N, M, d_cols, d_pres,
                                                                            d_anew, d_wnew);

@@ -829,14 +829,14 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             const uint32_t t_f = tmem_base;
             int slot = 0; uint32_t par = 0;
             for (int it = 0; it < ntl; ++it) {
-                mbar_wait(bar_fwd_empty, (it & 1) ^ 1);
+                mbar_wait_role(bar_fwd_empty, (it & 1) ^ 1);
                 for (int plane = 0; plane < 2; ++plane) {
                     const uint32_t sX = smem_u32(smem + slot * G::kSlotBytes);
                     // plane 0: x1 [m1 | m2] -> columns 0..63 (first MMA overwrites); plane 1: x2 m1 -> added to columns 32..63
                     const uint32_t t_d = plane ? t_f + 32 : t_f;
                     const uint32_t idesc = plane ? idesc_f32 : idesc_f64;
                     for (int u = 0; u < 2; ++u) {
-                        mbar_wait(&bar_full[slot * 3 + u], par);
+                        mbar_wait_role(&bar_full[slot * 3 + u], par);
                         if (plane == 0 && u == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
                         tc_fence_after();
                         const uint64_t wx = umma_desc_sw128(sX + u * kBlockBytes);
@@ -846,7 +846,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                             umma_f16(t_d, wx + 2 * ks, wm + 2 * ks, idesc, (plane | u | ks) ? 1u : 0u);
                     }
                     if (TAIL) {
-                        mbar_wait(&bar_full[slot * 3 + 2], par);
+                        mbar_wait_role(&bar_full[slot * 3 + 2], par);
                         tc_fence_after();
                         if (TAIL == 32) {
                             const uint64_t dx = umma_desc(sX + 2 * kBlockBytes, 16, 512), dm = umma_desc(sMb + 2 * G::kMBlock, 16, 512);
@@ -877,11 +877,11 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                 const int sB = (slot + 1 == NS) ? 0 : slot + 1;
                 const uint32_t parB = (slot + 1 == NS) ? par ^ 1 : par;
                 for (int u = 0; u < G::kUnits; ++u) {                                  // landed long ago
-                    mbar_wait(&bar_full[sA * 3 + u], par);
-                    mbar_wait(&bar_full[sB * 3 + u], parB);
+                    mbar_wait_role(&bar_full[sA * 3 + u], par);
+                    mbar_wait_role(&bar_full[sB * 3 + u], parB);
                 }
-                mbar_wait(&bar_r_ready[b], rph);
-                mbar_wait(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
+                mbar_wait_role(&bar_r_ready[b], rph);
+                mbar_wait_role(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
                 if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
                 tc_fence_after();
                 const uint32_t sX1 = smem_u32(smem + sA * G::kSlotBytes), sX2 = smem_u32(smem + sB * G::kSlotBytes);
@@ -936,8 +936,13 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
 #pragma unroll
         for (int c = 0; c < kColsPerWarp; ++c) gacc[c] = 0.0;
         static_assert(kColsPerWarp == 8, "the tail fold assigns two of eight columns to each lane quarter");
-        auto fold_gradient = [&](int j) {
-            float g0[kColsPerWarp], g1[kColsPerWarp], h0[2], h1[2];
+        // The gradient block of tile j is read out of TMEM in two steps.  fold_load: tcgen05.ld into registers, issued
+        // BEFORE this warp signals its residual rows of the next tile -- the next gradient MMAs cannot start until every
+        // warp has done so, and a tcgen05.ld issued while MMAs are running waits behind them (measured: ~2k cycles, which
+        // made the slowest warp slower still, tile after tile).  fold_add: the FP64 accumulation, registers only, after
+        // the signal, under the MMAs.
+        float g0[kColsPerWarp], g1[kColsPerWarp], h0[2], h1[2];
+        auto fold_load = [&](int j) {
             const int gb = j & 1;
             const uint32_t t_g = t_lane + kV2FwdCols + gb * kV2GradBuf;
             mbar_wait(&bar_g_full[gb], (j >> 1) & 1);
@@ -952,6 +957,8 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_g_empty[gb]);
+        };
+        auto fold_add = [&]() {
 #pragma unroll
             for (int c = 0; c < kColsPerWarp; ++c) gacc[c] += (double)fmaf(g1[c], 1.0f / kLoScale, g0[c]);
             if (TAIL == 32) {
@@ -988,9 +995,11 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         load_spikes(0, sb_next);
         unsigned badmask = 0;
 
+#define PYGLM_WSTAMP(K) do { if (a.trace && blockIdx.x == 0 && lane == 0 && it < 24) a.trace[2048 + ((warp - kFirstEpiWarp) * 24 + it) * 8 + (K)] = clock64(); } while (0)
         for (int it = 0; it < ntl; ++it) {
             const int b = it % RB;
             const uint32_t rph = (uint32_t)(it / RB) & 1u;
+            PYGLM_WSTAMP(0);
             const int64_t t = (first + (int64_t)it * step) * kTileT + row;
             const float lv = t < a.T ? 1.0f : 0.0f;
 #pragma unroll
@@ -1000,6 +1009,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             if (tr) a.trace[(2 * 32 + it) * 4 + 0] = clock64();
             mbar_wait(bar_fwd_full, it & 1);
             if (tr) a.trace[(2 * 32 + it) * 4 + 1] = clock64();
+            PYGLM_WSTAMP(1);
             tc_fence_after();
             float d0[kColsPerWarp], d1[kColsPerWarp];
             tmem_ld<kColsPerWarp>(t_lane + 0, d0);
@@ -1008,6 +1018,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_fwd_empty);
+            PYGLM_WSTAMP(2);
 
             float xs[kColsPerWarp];
             float xmin = 3.0e38f;
@@ -1051,7 +1062,10 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             // residual operand [r1 | r2] of this bin: one 128-byte row, 16-byte units 0..3 = r1 (8 columns each), 4..7 = r2,
             // unit index XOR (row & 7) (SWIZZLE_128B); this warp owns unit cg of each half
             if (tr) a.trace[1408 + it * 4 + 1] = clock64();
+            PYGLM_WSTAMP(3);
+            if (it >= 1) fold_load(it - 1);
             mbar_wait(&bar_r_free[b], rph ^ 1);
+            PYGLM_WSTAMP(4);
             if (tr) a.trace[1408 + it * 4 + 2] = clock64();
             {
                 unsigned char* prow = sR + b * G::kRBuf + row * 128;
@@ -1072,6 +1086,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_r_ready[b]);
+            PYGLM_WSTAMP(5);
             if (tr) a.trace[(2 * 32 + it) * 4 + 2] = clock64();
             if (a.trace && blockIdx.x == 0 && lane == 0 && it < 32) a.trace[384 + warp * 32 + it] = clock64();
 
@@ -1081,11 +1096,14 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
 #pragma unroll
                 for (int c = 0; c < kColsPerWarp; ++c) { pll[c] = 0.f; pgb[c] = 0.f; }
             }
-            if (it >= 1) fold_gradient(it - 1);
+            PYGLM_WSTAMP(6);
+            if (it >= 1) fold_add();
+            PYGLM_WSTAMP(7);
             if (tr) a.trace[(2 * 32 + it) * 4 + 3] = clock64();
         }
+#undef PYGLM_WSTAMP
 
-        if (ntl > 0) fold_gradient(ntl - 1);
+        if (ntl > 0) { fold_load(ntl - 1); fold_add(); }
         if (NLIN == PYGLM_B200_NLIN_EXP && a.flags) {
             badmask = __reduce_or_sync(0xffffffffu, badmask);
             if (lane < kColsPerWarp && ((badmask >> lane) & 1u)) a.flags[a.n_lo + c0 + lane] = 1u;
@@ -1396,7 +1414,8 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         { const char* fl = getenv("PYGLM_TC_FLUSH"); k.flush = fl ? std::max(1, atoi(fl)) : kFlushTiles; }
         static long long* d_trace = nullptr;
         const bool want_trace = getenv("PYGLM_TC_TRACE") != nullptr;
-        if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, (384 + 32 * 32 + 32 * 16) * sizeof(long long)));
+        constexpr int kTraceWords = 2048 + 16 * 24 * 8;
+        if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, kTraceWords * sizeof(long long)));
         k.trace = want_trace ? d_trace : nullptr;
         if (v2) {
             const int rc2 = tail2 == 0 ? launch_fused2<0>(a, ws, k, maps, nctas, stream)
@@ -1410,10 +1429,18 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         if (want_trace) {
             static int dumped = 0;
             if (dumped++ == 5) {
-                long long h[384 + 32 * 32 + 32 * 16];
+                static long long h[kTraceWords];
                 PYGLM_CUDA(cudaStreamSynchronize(stream));
                 PYGLM_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
                 const long long t0 = h[0];
+                if (v2) {       // per-warp phase stamps of tiles 10..12: start, fwd_full, ld done, math done, r_free, r_ready, sums, fold
+                    for (int it = 10; it < 13; ++it)
+                        for (int w = 0; w < 16; ++w) {
+                            const long long* e = h + 2048 + (w * 24 + it) * 8;
+                            fprintf(stderr, "tile %d warp %2d: start %7lld | fwd_full +%5lld ld +%4lld math +%5lld gload+r_free +%5lld r_ready +%4lld sums +%4lld fold_add +%5lld\n",
+                                    it, w, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2], e[4] - e[3], e[5] - e[4], e[6] - e[5], e[7] - e[6]);
+                        }
+                }
                 fprintf(stderr, "tile  tma_issue | fwd_iss fwd_done_iss bwd_iss bwd_done_iss | epi_start fwd_full r_ready iter_end\n");
                 for (int i = 0; i < 24; ++i) {
                     fprintf(stderr, "%3d %9lld | %9lld %9lld %9lld %9lld | %9lld %9lld %9lld %9lld\n", i, h[(0 * 32 + i) * 4] - t0,

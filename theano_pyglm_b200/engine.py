@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PYGLM_B200_LIB") or os.path.join(_HERE, "lib", "libpyglm_b200.so")   # env: A/B builds
 
 NLIN_EXP, NLIN_SOFTPLUS = 0, 1
-X_F32, X_F64, X_PLANES = 0, 1, 2
+X_F32, X_F64, X_PLANES, X_NONE = 0, 1, 2, 3
 PATH_AUTO, PATH_FP64, PATH_TC = 0, 1, 2
 _PATHS = {"auto": PATH_AUTO, "fp64": PATH_FP64, "tc": PATH_TC}
 _NLINS = {"exp": NLIN_EXP, "explinear": NLIN_SOFTPLUS, "softplus": NLIN_SOFTPLUS}
@@ -164,7 +164,8 @@ class Dataset:
         self.halo = int(halo)
         self.device = int(device)
         self.x_dtype = (X_F64 if x_dtype in ("f64", X_F64, np.float64) else
-                        X_PLANES if x_dtype in ("planes", X_PLANES) else X_F32)
+                        X_PLANES if x_dtype in ("planes", X_PLANES) else
+                        X_NONE if x_dtype in ("none", "spikes", X_NONE) else X_F32)
         self.h2d_bytes = S.nbytes + ibasis.nbytes
         self.F = 0
         if fstim is not None and np.size(fstim):
