@@ -173,7 +173,7 @@ def test_tensor_core_path_at_benchmark_size(eng):
 @pytest.mark.parametrize("T,N,B", [(3000, 27, 5), (2500, 70, 5)])
 def test_planes_only_dataset(eng, T, N, B, monkeypatch):
     """x_dtype="planes": only the FP16 split planes are resident (built by a chunked two-pass filter);
-    results equal the regular dataset's bit for bit, and the FP64-side entry points refuse."""
+    results equal the regular dataset's bit for bit, and the entry points that need X itself refuse."""
     p = make_problem(T, N, B, network=True)
     _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)
     full = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
@@ -191,8 +191,16 @@ def test_planes_only_dataset(eng, T, N, B, monkeypatch):
             ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="fp64")
         with pytest.raises(eng.EngineError):
             ds.fS()
-        with pytest.raises(eng.EngineError):
-            ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'])
+        # the Gibbs entry points do work on a planes-only dataset: they gather their currents from the spike trains
+        ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'])
+        cand = np.linspace(-1.0, 1.0, 11)[None, :]
+        got = ds.gibbs_delta_ll([1], [2], cand)
+        ds.gibbs_end()
+        f64 = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f64")
+        f64.gibbs_begin(p['bias'], p['w'], p['A'], p['W'])
+        assert np.allclose(got, f64.gibbs_delta_ll([1], [2], cand), rtol=1e-10, atol=1e-9)
+        f64.gibbs_end()
+        f64.close()
         ds.close()
 
 

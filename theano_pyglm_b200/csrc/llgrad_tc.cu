@@ -57,6 +57,10 @@ constexpr int kEpiWarps = 4 * kColGroups;
 #if PYGLM_TC_ROLE_BASE == 0
 constexpr int kFirstEpiWarp = 3, kProducerWarp = 0, kFwdWarp = 1, kBwdWarp = 2;
 constexpr int kThreads = 32 * (kFirstEpiWarp + kEpiWarps);
+#elif PYGLM_TC_ROLE_BASE == 2
+// no idle warp: 19 warps leave 104 registers per thread instead of 96
+constexpr int kFirstEpiWarp = 0, kProducerWarp = kEpiWarps, kFwdWarp = kEpiWarps + 1, kBwdWarp = kEpiWarps + 2;
+constexpr int kThreads = 32 * (kEpiWarps + 3);
 #else
 constexpr int kFirstEpiWarp = 0, kProducerWarp = kEpiWarps + 1, kFwdWarp = kEpiWarps + 2, kBwdWarp = kEpiWarps + 3;
 constexpr int kThreads = 32 * (kEpiWarps + 4);
@@ -682,12 +686,24 @@ tc_fused_kernel(const __grid_constant__ CUtensorMap tmap1, const __grid_constant
 //     folded by ALL warps every tile, one or two columns each, instead of by one lane quarter every fourth tile --
 //     no warp trails the others into the residual barrier any more.
 // =============================================================================================
+#ifndef PYGLM_TC_SCHED
+#define PYGLM_TC_SCHED 0                     // 1: clustered TMEM reads before the residual signal (see the epilogue loop)
+#endif
+#ifndef PYGLM_TC_TRACE_BUILD
+#define PYGLM_TC_TRACE_BUILD 0               // 1: keep the clock64 pipeline stamps (PYGLM_TC_TRACE) in the V2 kernel
+#endif
 constexpr uint32_t kSw32 = 6;                // UMMA LayoutType::SWIZZLE_32B
-constexpr int kV2FwdCols = 64;               // [hi | lo] activation accumulators
+#ifndef PYGLM_TC_GBASE
+#define PYGLM_TC_GBASE 64
+#endif
+constexpr int kV2FwdCols = PYGLM_TC_GBASE;   // [hi | lo] activation accumulators in columns 0..63; gradient buffers start here
 constexpr int kV2GradTile = 64;              // [hi | lo] gradient accumulators of one 128-feature tile
 constexpr int kV2GradBuf = 2 * kV2GradTile;  // tile 0 (features 0..127) + tile 1 (tail)
 constexpr int kV2MaxSlots = 6;
-constexpr int kBlockBytes = kTileT * 128;    // one 64-feature block of one plane: 128 rows x 128 B
+#ifndef PYGLM_TC_TAIL_M64
+#define PYGLM_TC_TAIL_M64 1                  // M = 64 MMAs for the replicated 16-feature tail block: half the operand fetch (measured 0.154 -> 0.147 ms);
+                                             // their accumulator rows sit in lanes 0..15 of every TMEM lane quarter
+#endif
 
 struct TcV2Args {
     TcKernelArgs k;
@@ -695,20 +711,26 @@ struct TcV2Args {
     int rbufs;                     // residual buffers (1 or 2)
 };
 
-template <int TAIL> struct V2Geom {
+// TILE = bins per tile: 128, or 112 -- the forward MMA still spans 128 rows (UMMA M), its last 16 rows then read
+// whatever follows the block in shared memory (finite FP16 data) and are discarded; what 112 buys is a sixth slot
+// (three whole tiles resident) within the 227 KB, so that the load of a tile no longer waits for the gradient MMAs
+// of the tile two before it.
+template <int TAIL, int TILE> struct V2Geom {
+    static constexpr int kBlock = TILE * 128;                        // one 64-feature block of one plane: TILE rows x 128 B
     static constexpr int kTailRowB = 2 * TAIL;                       // bytes per tail row (32 or 64)
-    static constexpr int kTailBytes = kTileT * kTailRowB;            // X tail block of one plane
-    static constexpr int kSlotBytes = 2 * kBlockBytes + kTailBytes;  // one plane of one tile
+    static constexpr int kTailBytes = TILE * kTailRowB;              // X tail block of one plane
+    static constexpr int kSlotBytes = (2 * kBlock + kTailBytes + 1023) / 1024 * 1024;   // one plane of one tile
     static constexpr int kMBlock = 64 * 128;                         // [M1 | M2] rows of one 64-feature block
     static constexpr int kMBytes = 2 * kMBlock + 64 * kTailRowB;
-    static constexpr int kRBuf = kTileT * 128;                       // [r1 | r2]: 128 bins x 128 B
+    static constexpr int kRBuf = TILE * 128;                         // [r1 | r2]: TILE bins x 128 B
     static constexpr int kUnits = TAIL ? 3 : 2;
+    static constexpr int kKSteps = TILE / 16;                        // gradient MMAs step through 16 bins
 };
 
-template <int TAIL>
+template <int TAIL, int TILE>
 __host__ __device__ inline int v2_smem_bytes(int nslots, int rbufs)
 {
-    using G = V2Geom<TAIL>;
+    using G = V2Geom<TAIL, TILE>;
     return nslots * G::kSlotBytes + G::kMBytes + rbufs * G::kRBuf + 1024;
 }
 
@@ -718,13 +740,19 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
 }
 
-template <int NLIN, int TAIL>
+template <int NLIN, int TAIL, int TILE>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_constant__ CUtensorMap tmapW2,
                  const __grid_constant__ CUtensorMap tmapT1, const __grid_constant__ CUtensorMap tmapT2, TcV2Args va)
 {
-    using G = V2Geom<TAIL>;
+    using G = V2Geom<TAIL, TILE>;
+    constexpr int kBlockBytes = G::kBlock;
     const TcKernelArgs& a = va.k;
+#if PYGLM_TC_TRACE_BUILD
+    long long* const V2TRACE = a.trace;
+#else
+    constexpr long long* V2TRACE = nullptr;      // the clock64 stamps are compiled out of the production build
+#endif
     const int NS = va.nslots, RB = va.rbufs;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -758,6 +786,10 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)kTmemAlloc) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TILE != kTileT) {          // rows TILE..127 of a block are read (and discarded) by the forward MMA: keep them finite
+        for (int u = threadIdx.x; u < NS * G::kSlotBytes / 16; u += kThreads)
+            reinterpret_cast<uint4*>(smem)[u] = make_uint4(0u, 0u, 0u, 0u);
     }
     // weight planes -> shared memory, swizzled by hand: per 64-feature block 64 rows [M1 rows | M2 rows] of 128 B
     // (SWIZZLE_128B), then the tail block with rows of kTailRowB bytes (SWIZZLE_64B / SWIZZLE_32B)
@@ -800,10 +832,10 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         if (lane == 0) {
             int slot = 0; uint32_t par = 1;              // parity on which the slot's empty barrier is waited
             for (int it = 0; it < ntl; ++it) {
-                const int row0 = (int)((first + (int64_t)it * step) * kTileT);
+                const int row0 = (int)((first + (int64_t)it * step) * TILE);
                 for (int plane = 0; plane < 2; ++plane) {
                     mbar_wait_relaxed(&bar_empty[slot], par, a.producer_sleep_ns);
-                    if (plane == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
+                    if (plane == 0 && V2TRACE && blockIdx.x == 0 && it < 32) a.trace[(0 * 32 + it) * 4 + 0] = clock64();
                     unsigned char* st = smem + slot * G::kSlotBytes;
                     const CUtensorMap* mw = plane ? &tmapW2 : &tmapW1;
                     for (int u = 0; u < 2; ++u) {
@@ -837,7 +869,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                     const uint32_t idesc = plane ? idesc_f32 : idesc_f64;
                     for (int u = 0; u < 2; ++u) {
                         mbar_wait_role(&bar_full[slot * 3 + u], par);
-                        if (plane == 0 && u == 0 && a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
+                        if (plane == 0 && u == 0 && V2TRACE && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 0] = clock64();
                         tc_fence_after();
                         const uint64_t wx = umma_desc_sw128(sX + u * kBlockBytes);
                         const uint64_t wm = umma_desc_sw128(sMb + u * G::kMBlock);
@@ -861,7 +893,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                     if (++slot == NS) { slot = 0; par ^= 1; }
                 }
                 umma_commit(bar_fwd_full);
-                if (a.trace && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 1] = clock64();
+                if (V2TRACE && blockIdx.x == 0 && it < 32) a.trace[(1 * 32 + it) * 4 + 1] = clock64();
             }
         }
     } else if (warp == kBwdWarp) {
@@ -882,7 +914,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                 }
                 mbar_wait_role(&bar_r_ready[b], rph);
                 mbar_wait_role(&bar_g_empty[gb], ((j >> 1) & 1) ^ 1);
-                if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
+                if (V2TRACE && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 2] = clock64();
                 tc_fence_after();
                 const uint32_t sX1 = smem_u32(smem + sA * G::kSlotBytes), sX2 = smem_u32(smem + sB * G::kSlotBytes);
                 const uint64_t dr = umma_desc_layout(smem_u32(sR + b * G::kRBuf), 16, 1024, kSw128);    // one 64-wide atom
@@ -891,7 +923,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                     const uint64_t d1 = umma_desc_layout(sX1, kBlockBytes, 1024, kSw128);
                     const uint64_t d2 = umma_desc_layout(sX2, kBlockBytes, 1024, kSw128);
 #pragma unroll
-                    for (int ks = 0; ks < kTileT / 16; ++ks) {                        // 16 bins per step: 2048 B of both operands
+                    for (int ks = 0; ks < G::kKSteps; ++ks) {                         // 16 bins per step: 2048 B of both operands
                         const uint64_t off = (uint64_t)(ks * 2048 >> 4);
                         umma_f16(t_g, d1 + off, dr + off, idesc_b64, ks ? 1u : 0u);   // X1^T [r1 | r2] -> hi, lo
                         umma_f16(t_g + 32, d2 + off, dr + off, idesc_b32, 1u);        // X2^T r1 -> lo
@@ -905,18 +937,20 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                                                    : umma_desc_layout(sX1 + 2 * kBlockBytes, 0, 256, kSw32);
                     const uint64_t d2 = TAIL == 32 ? umma_desc(sX2 + 2 * kBlockBytes, 0, 512)
                                                    : umma_desc_layout(sX2 + 2 * kBlockBytes, 0, 256, kSw32);
+                    constexpr uint32_t idesc_t64 = umma_idesc((PYGLM_TC_TAIL_M64 && TAIL == 16) ? 64 : 128, 64, 1, 1);
+                    constexpr uint32_t idesc_t32 = umma_idesc((PYGLM_TC_TAIL_M64 && TAIL == 16) ? 64 : 128, 32, 1, 1);
 #pragma unroll
-                    for (int ks = 0; ks < kTileT / 16; ++ks) {
+                    for (int ks = 0; ks < G::kKSteps; ++ks) {
                         const uint64_t offx = (uint64_t)(ks * kstep >> 4), off = (uint64_t)(ks * 2048 >> 4);
-                        umma_f16(t_g + kV2GradTile, d1 + offx, dr + off, idesc_b64, ks ? 1u : 0u);
-                        umma_f16(t_g + kV2GradTile + 32, d2 + offx, dr + off, idesc_b32, 1u);
+                        umma_f16(t_g + kV2GradTile, d1 + offx, dr + off, idesc_t64, ks ? 1u : 0u);
+                        umma_f16(t_g + kV2GradTile + 32, d2 + offx, dr + off, idesc_t32, 1u);
                     }
                 }
                 umma_commit(&bar_empty[sA]);
                 umma_commit(&bar_empty[sB]);
                 umma_commit(&bar_r_free[b]);
                 umma_commit(&bar_g_full[gb]);
-                if (a.trace && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 3] = clock64();
+                if (V2TRACE && blockIdx.x == 0 && j < 32) a.trace[(1 * 32 + j) * 4 + 3] = clock64();
                 slot += 2;
                 if (slot >= NS) { slot -= NS; par ^= 1; }
             }
@@ -936,11 +970,9 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
 #pragma unroll
         for (int c = 0; c < kColsPerWarp; ++c) gacc[c] = 0.0;
         static_assert(kColsPerWarp == 8, "the tail fold assigns two of eight columns to each lane quarter");
-        // The gradient block of tile j is read out of TMEM in two steps.  fold_load: tcgen05.ld into registers, issued
-        // BEFORE this warp signals its residual rows of the next tile -- the next gradient MMAs cannot start until every
-        // warp has done so, and a tcgen05.ld issued while MMAs are running waits behind them (measured: ~2k cycles, which
-        // made the slowest warp slower still, tile after tile).  fold_add: the FP64 accumulation, registers only, after
-        // the signal, under the MMAs.
+        // The gradient block of tile j is read out of TMEM (fold_load) and added into FP64 registers (fold_add).  A
+        // tcgen05.ld issued while MMAs are in flight waits behind them (measured: ~2k cycles when it lands in a gradient
+        // burst), so where it sits in the loop matters; after the residual signal was the best position measured.
         float g0[kColsPerWarp], g1[kColsPerWarp], h0[2], h1[2];
         auto fold_load = [&](int j) {
             const int gb = j & 1;
@@ -961,7 +993,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         auto fold_add = [&]() {
 #pragma unroll
             for (int c = 0; c < kColsPerWarp; ++c) gacc[c] += (double)fmaf(g1[c], 1.0f / kLoScale, g0[c]);
-            if (TAIL == 32) {
+            if (TAIL == 32 || (PYGLM_TC_TAIL_M64 && TAIL == 16)) {
                 gtail[0] += (double)fmaf(h1[0], 1.0f / kLoScale, h0[0]);
                 gtail[1] += (double)fmaf(h1[1], 1.0f / kLoScale, h0[1]);
             } else if (TAIL == 16) {
@@ -978,8 +1010,8 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         uint32_t sb[kSpWords], sb_next[kSpWords];
         const bool vec_ok = ((a.n_lo + c0) % kColsPerWarp) == 0;
         auto load_spikes = [&](int it, uint32_t (&dst)[kSpWords]) {
-            const int64_t t = (first + (int64_t)it * step) * kTileT + row;
-            const bool ok = it < ntl && t < a.T;
+            const int64_t t = (first + (int64_t)it * step) * TILE + row;
+            const bool ok = it < ntl && t < a.T && row < TILE;
 #pragma unroll
             for (int i = 0; i < kSpWords; ++i) dst[i] = 0;
             if (!ok) return;
@@ -995,29 +1027,58 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         load_spikes(0, sb_next);
         unsigned badmask = 0;
 
-#define PYGLM_WSTAMP(K) do { if (a.trace && blockIdx.x == 0 && lane == 0 && it < 24) a.trace[2048 + ((warp - kFirstEpiWarp) * 24 + it) * 8 + (K)] = clock64(); } while (0)
+#if PYGLM_TC_TRACE_BUILD
+#define PYGLM_WSTAMP(K) do { if (V2TRACE && blockIdx.x == 0 && lane == 0 && it < 24) a.trace[2048 + ((warp - kFirstEpiWarp) * 24 + it) * 8 + (K)] = clock64(); } while (0)
+#else
+#define PYGLM_WSTAMP(K) do { } while (0)
+#endif
+#if PYGLM_TC_SCHED
+        // Clustered TMEM reads: every tcgen05.ld of an iteration -- the gradient block of the previous tile AND the
+        // activation accumulators of the NEXT tile -- is issued at one point, just before this warp signals its residual
+        // rows.  At that point the tensor pipe is idle by construction (the previous gradient MMAs and the next forward
+        // MMAs are complete, the following ones cannot be issued before these loads are done), so no load ever queues
+        // behind a burst of MMAs; after the signal the gradient MMAs of this tile and the forward MMAs of the tile after
+        // next run back to back while the epilogue warps do the next tile's math.
+        float d0n[kColsPerWarp], d1n[kColsPerWarp];
+        if (ntl > 0) {
+            mbar_wait(bar_fwd_full, 0);
+            tc_fence_after();
+            tmem_ld<kColsPerWarp>(t_lane + 0, d0n);
+            tmem_ld<kColsPerWarp>(t_lane + 32, d1n);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_fwd_empty);
+        }
+#endif
         for (int it = 0; it < ntl; ++it) {
             const int b = it % RB;
             const uint32_t rph = (uint32_t)(it / RB) & 1u;
             PYGLM_WSTAMP(0);
-            const int64_t t = (first + (int64_t)it * step) * kTileT + row;
-            const float lv = t < a.T ? 1.0f : 0.0f;
+            const int64_t t = (first + (int64_t)it * step) * TILE + row;
+            const float lv = (t < a.T && row < TILE) ? 1.0f : 0.0f;
 #pragma unroll
             for (int i = 0; i < kSpWords; ++i) sb[i] = sb_next[i];
             load_spikes(it + 1, sb_next);
-            const bool tr = a.trace && blockIdx.x == 0 && warp == kFirstEpiWarp + (a.debug >> 8) && lane == 0 && it < 32;
+            const bool tr = V2TRACE && blockIdx.x == 0 && warp == kFirstEpiWarp + (a.debug >> 8) && lane == 0 && it < 32;
             if (tr) a.trace[(2 * 32 + it) * 4 + 0] = clock64();
+            float d0[kColsPerWarp], d1[kColsPerWarp];
+#if PYGLM_TC_SCHED
+#pragma unroll
+            for (int c = 0; c < kColsPerWarp; ++c) { d0[c] = d0n[c]; d1[c] = d1n[c]; }
+            PYGLM_WSTAMP(1);
+#else
             mbar_wait(bar_fwd_full, it & 1);
             if (tr) a.trace[(2 * 32 + it) * 4 + 1] = clock64();
             PYGLM_WSTAMP(1);
             tc_fence_after();
-            float d0[kColsPerWarp], d1[kColsPerWarp];
             tmem_ld<kColsPerWarp>(t_lane + 0, d0);
             tmem_ld<kColsPerWarp>(t_lane + 32, d1);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_fwd_empty);
+#endif
             PYGLM_WSTAMP(2);
 
             float xs[kColsPerWarp];
@@ -1026,6 +1087,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             for (int c = 0; c < kColsPerWarp; ++c) {
                 const float2 cp = cpar[c0 + c];
                 xs[c] = fmaf(fmaf(d1[c], 1.0f / kLoScale, d0[c]), cp.x, cp.y);
+                if (TILE != kTileT && row >= TILE) xs[c] = 30.0f;      // discarded rows: any finite activation
                 if (c0 + c < a.ncols) xmin = fminf(xmin, xs[c]);
                 if (NLIN == PYGLM_B200_NLIN_EXP && c0 + c < a.ncols && lv != 0.f && !(xs[c] <= kExpSafe)) badmask |= 1u << c;
             }
@@ -1036,12 +1098,17 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                     float r = 0.f;
                     if (c0 + c < a.ncols) {              // warp-uniform: padded columns cost nothing
                         const float x = xs[c];
-                        const float sv = (float)((sb[c >> 2] >> ((c & 3) * 8)) & 0xffu);     // 0 past the end of the recording
-                        float lg, rc;
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(x));
-                        pll[c] += fmaf(sv * 0.69314718f, lg, -dtl * x);                        // -dt*lam + s*log(lam)
-                        r = fmaf(sv, rc, -dtl);                                                 // (s/lam - dt) * 1
+                        const unsigned sbyte = (sb[c >> 2] >> ((c & 3) * 8)) & 0xffu;          // 0 past the end of the recording
+                        pll[c] = fmaf(-dtl, x, pll[c]);                                         // -dt*lam
+                        r = -dtl;                                                               // -dt * f', f' = 1
+                        if (__any_sync(0xffffffffu, sbyte != 0u)) {     // ~half of the 32-bin column slices hold no spike at all
+                            const float sv = (float)sbyte;
+                            float lg, rc;
+                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(x));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(x));
+                            pll[c] = fmaf(sv * 0.69314718f, lg, pll[c]);                        // + s*log(lam)
+                            r = fmaf(sv, rc, r);                                                // + s/lam
+                        }
                         pgb[c] += r;
                     }
                     d1[c] = r;
@@ -1063,11 +1130,40 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             // unit index XOR (row & 7) (SWIZZLE_128B); this warp owns unit cg of each half
             if (tr) a.trace[1408 + it * 4 + 1] = clock64();
             PYGLM_WSTAMP(3);
-            if (it >= 1) fold_load(it - 1);
+#if PYGLM_TC_SCHED
+            {
+                const bool hasg = it >= 1, hasf = it + 1 < ntl;
+                const int gbp = (it - 1) & 1;
+                if (hasg) {
+                    const uint32_t t_g = t_lane + kV2FwdCols + gbp * kV2GradBuf;
+                    mbar_wait(&bar_g_full[gbp], ((it - 1) >> 1) & 1);
+                    tc_fence_after();
+                    tmem_ld<kColsPerWarp>(t_g + 0, g0);
+                    tmem_ld<kColsPerWarp>(t_g + 32, g1);
+                    if (TAIL) {
+                        tmem_ld2(t_g + kV2GradTile + 2 * q, h0);
+                        tmem_ld2(t_g + kV2GradTile + 32 + 2 * q, h1);
+                    }
+                }
+                if (hasf) {
+                    mbar_wait(bar_fwd_full, (it + 1) & 1);
+                    tc_fence_after();
+                    tmem_ld<kColsPerWarp>(t_lane + 0, d0n);
+                    tmem_ld<kColsPerWarp>(t_lane + 32, d1n);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (hasg) mbar_arrive(&bar_g_empty[gbp]);
+                    if (hasf) mbar_arrive(bar_fwd_empty);
+                }
+            }
+#endif
             mbar_wait(&bar_r_free[b], rph ^ 1);
             PYGLM_WSTAMP(4);
             if (tr) a.trace[1408 + it * 4 + 2] = clock64();
-            {
+            if (TILE == kTileT || row < TILE) {
                 unsigned char* prow = sR + b * G::kRBuf + row * 128;
                 uint32_t h1[4], h2[4];
 #pragma unroll
@@ -1088,7 +1184,7 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             if (lane == 0) mbar_arrive(&bar_r_ready[b]);
             PYGLM_WSTAMP(5);
             if (tr) a.trace[(2 * 32 + it) * 4 + 2] = clock64();
-            if (a.trace && blockIdx.x == 0 && lane == 0 && it < 32) a.trace[384 + warp * 32 + it] = clock64();
+            if (V2TRACE && blockIdx.x == 0 && lane == 0 && it < 32) a.trace[384 + warp * 32 + it] = clock64();
 
             if (((it + 1) % F) == 0 || it == ntl - 1) {
                 ll_acc += (double)warp_column_sums<kColsPerWarp>(pll, lane);
@@ -1097,7 +1193,11 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
                 for (int c = 0; c < kColsPerWarp; ++c) { pll[c] = 0.f; pgb[c] = 0.f; }
             }
             PYGLM_WSTAMP(6);
+#if PYGLM_TC_SCHED
             if (it >= 1) fold_add();
+#else
+            if (it >= 1) { fold_load(it - 1); fold_add(); }
+#endif
             PYGLM_WSTAMP(7);
             if (tr) a.trace[(2 * 32 + it) * 4 + 3] = clock64();
         }
@@ -1110,7 +1210,12 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
         }
 #pragma unroll
         for (int c = 0; c < kColsPerWarp; ++c) gp[(int64_t)row * kNcol + c0 + c] = gacc[c];
-        if (TAIL == 32) {
+        if (TAIL == 16 && PYGLM_TC_TAIL_M64) {           // M = 64: every lane quarter holds the 16 rows once, in its lanes 0..15
+            if (lane < 16) {
+                gp[((int64_t)128 + lane) * kNcol + c0 + 2 * q] = gtail[0];
+                gp[((int64_t)128 + lane) * kNcol + c0 + 2 * q + 1] = gtail[1];
+            }
+        } else if (TAIL == 32) {
             gp[((int64_t)128 + lane) * kNcol + c0 + 2 * q] = gtail[0];
             gp[((int64_t)128 + lane) * kNcol + c0 + 2 * q + 1] = gtail[1];
         } else if (TAIL == 16) {
@@ -1277,7 +1382,7 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)T * ws.Np, stream));
     PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
     PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, NB * sizeof(unsigned), stream));
-    ws.tmaps = malloc(6 * sizeof(CUtensorMap));
+    ws.tmaps = malloc(12 * sizeof(CUtensorMap));
     if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
     CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
     int rc;
@@ -1287,6 +1392,12 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     if ((rc = tc_make_map_2d(&maps[3], ws.X2, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;
     if ((rc = tc_make_map_2d(&maps[4], ws.X1, ws.ldp, T, ws.ldp, 16, kTileT, 2))) return rc;         // 16-feature tail, 32B swizzle
     if ((rc = tc_make_map_2d(&maps[5], ws.X2, ws.ldp, T, ws.ldp, 16, kTileT, 2))) return rc;
+    for (int pl = 0; pl < 2; ++pl) {                      // the same three box shapes with 112-bin boxes (fused kernel V2)
+        const __half* base = pl ? ws.X2 : ws.X1;
+        if ((rc = tc_make_map_2d(&maps[6 + pl], base, ws.ldp, T, ws.ldp, kChunkF, 112))) return rc;
+        if ((rc = tc_make_map_2d(&maps[8 + pl], base, ws.ldp, T, ws.ldp, 64, 112, 1))) return rc;
+        if ((rc = tc_make_map_2d(&maps[10 + pl], base, ws.ldp, T, ws.ldp, 16, 112, 2))) return rc;
+    }
     return PYGLM_B200_OK;
 }
 
@@ -1346,10 +1457,12 @@ int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int 
     return PYGLM_B200_OK;
 }
 
-template <int TAIL>
-static int launch_fused2(const TcArgs& a, TcWorkspace& ws, TcKernelArgs k, const CUtensorMap* maps, int nctas, cudaStream_t stream)
+template <int TAIL, int TILE>
+static int launch_fused2(const TcArgs& a, TcWorkspace& ws, TcKernelArgs k, const CUtensorMap* maps, cudaStream_t stream)
 {
-    using G = V2Geom<TAIL>;
+    using G = V2Geom<TAIL, TILE>;
+    k.ntiles = ceil_div(a.T, TILE);
+    const int nctas = (int)std::min<int64_t>(k.ntiles, ws.num_sms);
     const int budget = 232448 - 1024;                     // the kernel aligns its carve-up to 1024 bytes itself
     auto slots_for = [&](int rb) { return std::min(kV2MaxSlots, (budget - 1024 - G::kMBytes - rb * G::kRBuf) / G::kSlotBytes); };
     int rbufs = slots_for(1) > slots_for(2) ? 1 : 2;
@@ -1357,12 +1470,15 @@ static int launch_fused2(const TcArgs& a, TcWorkspace& ws, TcKernelArgs k, const
     int nslots = slots_for(rbufs);
     if (const char* env = getenv("PYGLM_TC_SLOTS")) nslots = std::max(4, std::min(nslots, atoi(env)));
     TcV2Args va{k, nslots, rbufs};
-    const int smem_bytes = v2_smem_bytes<TAIL>(nslots, rbufs) + 1024;
-    auto kern = a.nlin == PYGLM_B200_NLIN_EXP ? tc_fused2_kernel<PYGLM_B200_NLIN_EXP, TAIL> : tc_fused2_kernel<PYGLM_B200_NLIN_SOFTPLUS, TAIL>;
+    const int smem_bytes = v2_smem_bytes<TAIL, TILE>(nslots, rbufs) + 1024;
+    auto kern = a.nlin == PYGLM_B200_NLIN_EXP ? tc_fused2_kernel<PYGLM_B200_NLIN_EXP, TAIL, TILE>
+                                              : tc_fused2_kernel<PYGLM_B200_NLIN_SOFTPLUS, TAIL, TILE>;
     PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    const CUtensorMap& t1 = TAIL == 16 ? maps[4] : maps[0];
-    const CUtensorMap& t2 = TAIL == 16 ? maps[5] : maps[1];
-    kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[2], maps[3], t1, t2, va);
+    // maps: [0,1] 32-feature boxes (64B swizzle), [2,3] 64-feature boxes (128B), [4,5] 16-feature boxes (32B); + 6 for 112-bin boxes
+    const int mo = TILE == kTileT ? 0 : 6;
+    const CUtensorMap& t1 = TAIL == 16 ? maps[mo + 4] : maps[mo + 0];
+    const CUtensorMap& t2 = TAIL == 16 ? maps[mo + 5] : maps[mo + 1];
+    kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[mo + 2], maps[mo + 3], t1, t2, va);
     PYGLM_CUDA(cudaGetLastError());
     return PYGLM_B200_OK;
 }
@@ -1377,11 +1493,13 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     const int nch = (int)ceil_div(NB, kChunkF);
     const int nmt = (int)ceil_div(nch, 4);
     const int Kp = nch * kChunkF;
-    const int64_t ntiles = ceil_div(a.T, kTileT);
-    const int nctas = (int)std::min<int64_t>(ntiles, ws.num_sms);
     bool v2 = nch >= 4;                                   // 97..160 features: the plane-slot ring kernel
     if (const char* env = getenv("PYGLM_TC_V2")) v2 = v2 && atoi(env) != 0;
     const int tail2 = NB <= 128 ? 0 : (NB <= 144 ? 16 : 32);
+    int tile2 = 128;                                      // bins per tile of the V2 kernel (112: a sixth plane slot)
+    if (const char* env = getenv("PYGLM_TC_TILE")) tile2 = atoi(env) == 112 ? 112 : 128;
+    const int64_t ntiles = ceil_div(a.T, (v2 && tile2 == 112) ? 112 : kTileT);
+    const int nctas = (int)std::min<int64_t>(ntiles, ws.num_sms);
     const size_t per_cta = v2 ? (size_t)(128 + tail2) * kNcol + 2 * kNcol : (size_t)nmt * 128 * kNcol + 2 * kNcol;
     if (ws.part_elems < per_cta * nctas) {
         cudaFree(ws.part);
@@ -1418,9 +1536,13 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
         if (want_trace && !d_trace) PYGLM_CUDA(cudaMalloc(&d_trace, kTraceWords * sizeof(long long)));
         k.trace = want_trace ? d_trace : nullptr;
         if (v2) {
-            const int rc2 = tail2 == 0 ? launch_fused2<0>(a, ws, k, maps, nctas, stream)
-                          : tail2 == 16 ? launch_fused2<16>(a, ws, k, maps, nctas, stream)
-                                        : launch_fused2<32>(a, ws, k, maps, nctas, stream);
+            int rc2;
+            if (tile2 == 112)
+                rc2 = tail2 == 0 ? launch_fused2<0, 112>(a, ws, k, maps, stream)
+                    : tail2 == 16 ? launch_fused2<16, 112>(a, ws, k, maps, stream) : launch_fused2<32, 112>(a, ws, k, maps, stream);
+            else
+                rc2 = tail2 == 0 ? launch_fused2<0, 128>(a, ws, k, maps, stream)
+                    : tail2 == 16 ? launch_fused2<16, 128>(a, ws, k, maps, stream) : launch_fused2<32, 128>(a, ws, k, maps, stream);
             if (rc2) return rc2;
         } else {
             kern<<<nctas, kThreads, smem_bytes, stream>>>(maps[0], maps[1], maps[2], maps[3], k);
