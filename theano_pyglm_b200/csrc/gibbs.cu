@@ -160,45 +160,51 @@ static int ensure_softplus_table()
 // (utils/basis.py:201-236 folded into impulse.py:58).  X (T x N x B) is never read: one byte per bin of the
 // presynaptic spike train instead of B values, which is what lets a GPU hold a population whose filtered spike train
 // would not fit (C4: 164 GB of X, 4 GB of spikes).  Spikes are sparse, so the block compacts the spikes of its chunk
-// plus the R-bin left context into a list and scatters c * h[lag] into the chunk's u, spike by spike in time order
-// (a fixed summation order; a barrier separates spikes because neighbouring spikes write the same bins).
-// Shared memory: su [kGibbsChunk] doubles | sh [R] doubles | spos [kGibbsChunk + R] u16 | scnt [kGibbsChunk + R] u8.
+// plus the R-bin left context into a time-ordered list and records, for every bin of the window, how many spikes
+// precede it; a bin then sums c * h[lag] over the ~4 list entries of its own window, in increasing spike time (a fixed
+// order: reproducible sums), with no barrier and no atomics.
+// Shared memory: sh [R] doubles | spos [W] u16 | scum [W + 1] u16 | scnt [W] u8,  W = kGibbsChunk + R.
 // ---------------------------------------------------------------------------------------------
 struct SpkSmem {
-    double* su; double* sh; unsigned short* spos; unsigned char* scnt;
+    double* sh; unsigned short* spos; unsigned short* scum; unsigned char* scnt;
+    int R;
 };
 static inline size_t spk_smem_bytes(int R)
 {
     const size_t W = (size_t)kGibbsChunk + R;
-    return (size_t)kGibbsChunk * 8 + (size_t)round_up(R, 2) * 8 + round_up(W * 2, 16) + round_up(W, 16);
+    return (size_t)round_up(R, 2) * 8 + round_up(W * 2, 16) + round_up((W + 1) * 2, 16) + round_up(W, 16);
 }
 __device__ inline SpkSmem spk_carve(unsigned char* base, int R)
 {
     SpkSmem m;
     const size_t W = (size_t)kGibbsChunk + R;
-    m.su = reinterpret_cast<double*>(base);
-    m.sh = m.su + kGibbsChunk;
+    m.sh = reinterpret_cast<double*>(base);
     m.spos = reinterpret_cast<unsigned short*>(m.sh + ((R + 1) & ~1));
-    m.scnt = reinterpret_cast<unsigned char*>(m.spos) + ((W * 2 + 15) & ~(size_t)15);
+    m.scum = m.spos + ((W * 2 + 15) & ~(size_t)15) / 2;
+    m.scnt = reinterpret_cast<unsigned char*>(m.scum) + (((W + 1) * 2 + 15) & ~(size_t)15);
+    m.R = R;
     return m;
 }
 
-// Adds scale * sum_b ibasis[l][b] w[b] convolved with the spikes of row `st_pre` (indexable from -halo) into
-// su[0 .. nbins) for the bins [tbeg, tbeg + nbins).  All threads of the block must call it; su is NOT cleared.
-__device__ void spk_accumulate_u(const SpkSmem& m, const uint8_t* __restrict__ st_pre, int halo, int64_t tbeg, int nbins,
-                                 const double* __restrict__ ibasis, int R, int B, const double* __restrict__ w, double scale,
-                                 int* s_scan /* [kGibbsThreads / 32 + 1] */)
+// Prepare the gather for the bins [tbeg, tbeg + nbins) of presynaptic row `st_pre` (indexable from -halo):
+// h = scale * ibasis . w, the spike list of the window [tbeg - R, tbeg + nbins - 1) and the per-position spike counts.
+// All threads of the block must call it; it ends with a barrier.
+__device__ void spk_build(const SpkSmem& m, const uint8_t* __restrict__ st_pre, int halo, int64_t tbeg, int nbins,
+                          const double* __restrict__ ibasis, int B, const double* __restrict__ w, double scale,
+                          int* s_scan /* [kGibbsThreads / 32 + 1] */)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int R = m.R;
+    __syncthreads();                                      // the previous edge's gathers are done with these arrays
     for (int l = tid; l < R; l += kGibbsThreads) {
         double h = 0.0;
         for (int b = 0; b < B; ++b) h = fma(ibasis[(int64_t)l * B + b], w[b], h);
         m.sh[l] = h * scale;
     }
-    // spikes of the window [tbeg - R, tbeg + nbins - 1): each thread scans a contiguous segment (time order is kept)
+    // each thread scans a contiguous segment of the window, so the list keeps time order
     const int W = R + nbins - 1;
     const int seg = (W + kGibbsThreads - 1) / kGibbsThreads;
-    const int p0 = tid * seg, p1 = min(W, p0 + seg);
+    const int p0 = min(W, tid * seg), p1 = min(W, p0 + seg);
     int cnt = 0;
     for (int p = p0; p < p1; ++p) {
         const int64_t t = tbeg - R + p;
@@ -219,23 +225,23 @@ __device__ void spk_accumulate_u(const SpkSmem& m, const uint8_t* __restrict__ s
     }
     __syncthreads();
     int k = s_scan[warp] + incl - cnt;
-    const int nspk = s_scan[kGibbsThreads / 32];
     for (int p = p0; p < p1; ++p) {
         const int64_t t = tbeg - R + p;
         const unsigned char c = t >= -(int64_t)halo ? st_pre[t] : (unsigned char)0;
+        m.scum[p] = (unsigned short)k;                    // spikes at window positions < p
         if (c) { m.spos[k] = (unsigned short)p; m.scnt[k] = c; ++k; }
     }
+    if (tid == kGibbsThreads - 1) m.scum[W] = (unsigned short)s_scan[kGibbsThreads / 32];
     __syncthreads();
-    // spike at window position p (bin tbeg - R + p) reaches bins tbeg - R + p + 1 + l, l in [0, R): index p + 1 + l - R
-    for (int s = 0; s < nspk; ++s) {
-        const int base = (int)m.spos[s] + 1 - R;
-        const double c = (double)m.scnt[s];
-        for (int l = tid; l < R; l += kGibbsThreads) {
-            const int idx = base + l;
-            if (idx >= 0 && idx < nbins) m.su[idx] = fma(c, m.sh[l], m.su[idx]);
-        }
-        __syncthreads();
-    }
+}
+
+// u of bin tbeg + i: the spikes at window positions [i, i + R) are lags R .. 1 away (position p is bin tbeg - R + p)
+__device__ __forceinline__ double spk_u(const SpkSmem& m, int i)
+{
+    const int k0 = m.scum[i], k1 = m.scum[i + m.R];
+    double u = 0.0;
+    for (int k = k0; k < k1; ++k) u = fma((double)m.scnt[k], m.sh[i + m.R - 1 - (int)m.spos[k]], u);
+    return u;
 }
 
 // log(lam) of the Poisson term is needed only in the ~2% of bins that hold a spike.  Those bins are handed to
@@ -281,11 +287,9 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
     const uint8_t* __restrict__ st = g.St + (int64_t)col * g.ldst;
     const XT* __restrict__ xcol = SPK ? nullptr : X + (int64_t)pre * g.B * g.T;      // feature-major copy: Xt[j][t]
     SpkSmem spk{};
-    if (SPK) {                                             // u of the whole chunk from the presynaptic spike train
+    if (SPK) {                                             // spike list of the presynaptic train for this chunk
         spk = spk_carve(dyn_smem, g.R);
-        for (int i = tid; i < kGibbsChunk; i += kGibbsThreads) spk.su[i] = 0.0;
-        __syncthreads();
-        spk_accumulate_u(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.R, g.B, sW, 1.0, sScan);
+        spk_build(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.B, sW, 1.0, sScan);
     }
 
     // the operands of the next 256 bins are fetched while the current ones are evaluated
@@ -309,7 +313,7 @@ gibbs_delta_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t*
         const bool live = t0 + tid < tend;
         double u = 0.0;
         if (SPK) {
-            u = live ? spk.su[(int)(t0 - tbeg) + tid] : 0.0;
+            u = live ? spk_u(spk, (int)(t0 - tbeg) + tid) : 0.0;
         } else {
 #pragma unroll
             for (int b = 0; b < BMAX; ++b) u = fma((double)xr[b], sW[b], u);
@@ -409,10 +413,8 @@ gibbs_commit_kernel(GibbsArgs g, const int32_t* __restrict__ cols, const int32_t
     double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
     if (SPK) {
         SpkSmem spk = spk_carve(dyn_smem, g.R);
-        for (int i = tid; i < kGibbsChunk; i += kGibbsThreads) spk.su[i] = 0.0;
-        __syncthreads();
-        spk_accumulate_u(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.R, g.B, sW, 1.0, sScan);
-        for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) inet[t] += delta * spk.su[(int)(t - tbeg)];
+        spk_build(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.B, sW, 1.0, sScan);
+        for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) inet[t] += delta * spk_u(spk, (int)(t - tbeg));
         return;
     }
     const XT* __restrict__ xcol = X + (int64_t)pre * g.B * g.T;
@@ -437,18 +439,30 @@ gibbs_inet_spk_kernel(GibbsArgs g)
     const int64_t tbeg = (int64_t)blockIdx.x * kGibbsChunk;
     const int64_t tend = min(g.T, tbeg + kGibbsChunk);
     SpkSmem spk = spk_carve(dyn_smem, g.R);
-    for (int i = tid; i < kGibbsChunk; i += kGibbsThreads) spk.su[i] = 0.0;
+    constexpr int kPer = kGibbsChunk / kGibbsThreads;      // bins per thread: tid, tid + 256, ...
+    double acc[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) acc[j] = 0.0;
+    const int nbins = (int)(tend - tbeg);
     for (int pre = 0; pre < g.N; ++pre) {
         const double aw = (double)g.A[(int64_t)pre * g.N + col] * g.W[(int64_t)pre * g.N + col];
         if (aw == 0.0) continue;                            // block-uniform
         __syncthreads();
         if (tid < kMaxBasis) sW[tid] = tid < g.B ? g.w[(int64_t)col * NB + (int64_t)pre * g.B + tid] : 0.0;
         __syncthreads();
-        spk_accumulate_u(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, (int)(tend - tbeg), g.ibasis, g.R, g.B, sW, aw, sScan);
+        spk_build(spk, g.St + (int64_t)pre * g.ldst, g.halo, tbeg, nbins, g.ibasis, g.B, sW, aw, sScan);
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) {
+            const int i = tid + j * kGibbsThreads;
+            if (i < nbins) acc[j] += spk_u(spk, i);
+        }
     }
-    __syncthreads();
     double* __restrict__ inet = g.Inet + (int64_t)nl * g.T;
-    for (int64_t t = tbeg + tid; t < tend; t += kGibbsThreads) inet[t] = spk.su[(int)(t - tbeg)];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kGibbsThreads;
+        if (i < nbins) inet[tbeg + i] = acc[j];
+    }
 }
 
 int launch_gibbs_inet_from_spikes(const GibbsArgs& g, cudaStream_t stream)
