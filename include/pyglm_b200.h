@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PYGLM_B200_ABI_VERSION 3
+#define PYGLM_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define PYGLM_B200_API __attribute__((visibility("default")))
@@ -142,8 +142,12 @@ PYGLM_B200_API int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, doubl
 PYGLM_B200_API void* pyglm_b200_dataset_device_X(const pyglm_b200_dataset* ds);
 PYGLM_B200_API void* pyglm_b200_dataset_device_S(const pyglm_b200_dataset* ds);
 
-/* re-run K1 on the resident spikes (bench / profiling of the filter alone) */
+/* re-run K1 on the resident spikes (bench / profiling of the filter alone): one pass rewrites everything K1 produced for
+ * this dataset -- the filtered spike train X and, for FP32 / planes-only datasets without stimulus features, the FP16
+ * split planes of the tensor-core path (utils/basis.py:201-236 fused with the operand split). */
 PYGLM_B200_API int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream);
+/* bytes one such pass reads (spikes) and writes (X and / or planes): the algorithmic traffic of K1 */
+PYGLM_B200_API int pyglm_b200_dataset_filter_bytes(const pyglm_b200_dataset* ds, int64_t* bytes_read, int64_t* bytes_written);
 
 /* ------------------------------------------------------------------------------------
  * Log-likelihood and gradient for postsynaptic neurons n in [n_lo, n_hi)  (kernels K2f/K2b).

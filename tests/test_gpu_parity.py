@@ -43,6 +43,42 @@ def test_filter_matches_oracle(eng, T, N, B, x_dtype):
     ds.close()
 
 
+def test_filter_long_window_and_heavy_counts(eng):
+    """R >= 256 takes the runtime-pitch variant of K1; counts up to 255 in one bin; N a multiple of four above one
+    column block (word-aligned row segments) and not (byte loads)."""
+    from tests.helpers import make_ibasis
+    for N, B in ((36, 5), (35, 3)):
+        p = make_problem(1500, N, B)
+        ib = make_ibasis(B, dt_max=0.3)
+        assert ib.shape[0] >= 256
+        S = p['S'].copy()
+        S[[5, 700, 701, 1499], [0, N - 1, N - 1, 3]] = [255, 17, 2, 200]
+        for x_dtype in ("f64", "f32"):
+            ds = eng.Dataset(S, p['dt'], ib, x_dtype=x_dtype)
+            ref = orc.convolve_with_basis_direct(S.astype(np.float64), ib)
+            assert np.array_equal(ds.fS(), ref if x_dtype == "f64" else ref.astype(np.float32).astype(np.float64))
+            ds.close()
+
+
+def test_planes_written_by_the_filter_equal_planes_split_from_X(eng, monkeypatch):
+    """Single-pass ingest: K1 writes the FP16 split planes itself (analytic per-feature scales).  The same planes built
+    afterwards from the resident FP32 X (the path datasets with stimulus features take) give bit-identical results."""
+    for T, N, B in ((3000, 27, 5), (2000, 70, 5), (1500, 9, 10)):
+        p = make_problem(T, N, B, network=True)
+        eager = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+        a = eager.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="tc")
+        eager.refilter()                                   # a second pass rewrites X and planes in place
+        a2 = eager.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="tc")
+        eager.close()
+        monkeypatch.setenv("PYGLM_LAZY_PLANES", "1")
+        lazy = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+        monkeypatch.delenv("PYGLM_LAZY_PLANES")
+        b = lazy.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="tc")
+        lazy.close()
+        for x, y, z in zip(a, b, a2):
+            assert np.array_equal(x, y) and np.array_equal(x, z)
+
+
 def test_filter_halo_matches_unsharded(eng):
     """Time-sharded ingest: shard k with an R-bin left halo reproduces rows of the unsharded X."""
     p = make_problem(4000, 6, 5)
@@ -172,16 +208,14 @@ def test_tensor_core_path_at_benchmark_size(eng):
 
 @pytest.mark.parametrize("T,N,B", [(3000, 27, 5), (2500, 70, 5)])
 def test_planes_only_dataset(eng, T, N, B, monkeypatch):
-    """x_dtype="planes": only the FP16 split planes are resident (built by a chunked two-pass filter);
+    """x_dtype="planes": only the FP16 split planes are resident (K1 writes them directly, no FP32 X anywhere);
     results equal the regular dataset's bit for bit, and the entry points that need X itself refuse."""
     p = make_problem(T, N, B, network=True)
     _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)
     full = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
     ref = full.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="tc")
     full.close()
-    for chunk in (None, "1000"):                          # one chunk, then several (chunk boundaries need filter context)
-        if chunk:
-            monkeypatch.setenv("PYGLM_PLANES_CHUNK", chunk)
+    for _ in range(1):
         ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="planes")
         out = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], path="auto")
         for o, r in zip(out, ref):

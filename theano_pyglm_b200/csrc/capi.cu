@@ -213,8 +213,23 @@ int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, in
     if (x_dtype == PYGLM_B200_X_NONE) {
         // spikes only: nothing to filter (the Gibbs entry points gather their currents from the spikes)
     } else if (planes_only) {
-        if (T > 0 && (rc = tc_build_planes_streaming(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->stream))) return fail(rc);
-    } else if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->X.p, ds->ldx, x_dtype, ds->stream))) return fail(rc);
+        if (T > 0 && (rc = tc_build_planes_direct(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, nullptr, 0, ds->stream))) return fail(rc);
+    } else {
+        // single-pass ingest: an FP32 dataset without stimulus features gets its tensor-core planes from the same K1 pass
+        bool done = false;
+        const char* lazy = getenv("PYGLM_LAZY_PLANES");       // tests: build the planes from the resident X at the first tensor-core call
+        if (x_dtype == PYGLM_B200_X_F32 && F == 0 && T > 0 && tc_supported(T, N, B, x_dtype) && !(lazy && atoi(lazy))) {
+            rc = tc_build_planes_direct(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, (float*)ds->X.p, ds->ldx, ds->stream);
+            if (rc == PYGLM_B200_OK) done = true;
+            else if (rc == PYGLM_B200_ENOMEM) { ds->tc.release(); cudaGetLastError(); }   // no room for the planes now: X alone
+            else return fail(rc);
+        }
+        if (!done) {
+            FilterOut fo;
+            fo.X = ds->X.p; fo.ldx = ds->ldx; fo.x_dtype = x_dtype;
+            if ((rc = launch_filter(ds->S.p, T, N, halo, ds->ibasis.p, R, B, fo, ds->stream))) return fail(rc);
+        }
+    }
     // spikes by column, halo bins included: St[n][halo + T] (K4 reads per-column streams, and in from-spikes mode the
     // R bins before a chunk)
     if ((rc = launch_transpose_spikes(ds->S.p, T + halo, N, 0, ds->St.p, ds->stream))) return fail(rc);
@@ -300,13 +315,34 @@ int pyglm_b200_dataset_get_fS(const pyglm_b200_dataset* ds, double* out)
     return PYGLM_B200_OK;
 }
 
+// what one K1 pass over this dataset writes: the resident X and / or the split planes (spike-history features only)
+static FilterOut filter_outputs(pyglm_b200_dataset* ds)
+{
+    FilterOut fo;
+    if (ds->x_dtype == PYGLM_B200_X_F32 || ds->x_dtype == PYGLM_B200_X_F64) { fo.X = ds->X.p; fo.ldx = ds->ldx; fo.x_dtype = ds->x_dtype; }
+    if (ds->x_dtype != PYGLM_B200_X_F64 && ds->F == 0 && ds->tc.planes_ready) {
+        fo.X1 = ds->tc.X1; fo.X2 = ds->tc.X2; fo.ldp = ds->tc.ldp; fo.sx = ds->tc.sx;
+    }
+    return fo;
+}
+
 int pyglm_b200_dataset_refilter(pyglm_b200_dataset* ds, void* stream)
 {
     DS_GUARD(ds);
-    if (ds->x_dtype == PYGLM_B200_X_PLANES || ds->x_dtype == PYGLM_B200_X_NONE) { set_error("refilter: no filtered spike train is resident"); return PYGLM_B200_EUNSUPPORTED; }
+    if (ds->x_dtype == PYGLM_B200_X_NONE) { set_error("refilter: this dataset keeps no filtered spike train"); return PYGLM_B200_EUNSUPPORTED; }
     ds->xt_ready = false;
-    return launch_filter(ds->S.p, ds->T, ds->N, ds->halo, ds->ibasis.p, ds->R, ds->B, ds->X.p, ds->ldx,
-                         ds->x_dtype, (cudaStream_t)stream);
+    return launch_filter(ds->S.p, ds->T, ds->N, ds->halo, ds->ibasis.p, ds->R, ds->B, filter_outputs(ds), (cudaStream_t)stream);
+}
+
+int pyglm_b200_dataset_filter_bytes(const pyglm_b200_dataset* ds, int64_t* bytes_read, int64_t* bytes_written)
+{
+    PYGLM_REQUIRE(ds != nullptr, "null dataset handle");
+    const FilterOut fo = filter_outputs(const_cast<pyglm_b200_dataset*>(ds));
+    if (bytes_read) *bytes_read = (ds->T + ds->halo) * ds->N;
+    if (bytes_written)
+        *bytes_written = (fo.X ? ds->T * (int64_t)ds->N * ds->B * (fo.x_dtype == PYGLM_B200_X_F64 ? 8 : 4) : 0) +
+                         (fo.X1 ? ds->T * fo.ldp * 4 : 0);
+    return PYGLM_B200_OK;
 }
 
 // ------------------------------------------------------------------------------------
@@ -348,7 +384,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     if (use == PYGLM_B200_PATH_TC) {
         TcArgs t{};
         t.X = ds->x_dtype == PYGLM_B200_X_PLANES ? nullptr : (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
-        t.B = ds->B; t.F = ds->F; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
+        t.B = ds->B; t.F = ds->F; t.ibasis = ds->ibasis.p; t.R = ds->R; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
         t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
         t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
         t.flags = nullptr;

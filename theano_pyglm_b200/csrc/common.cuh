@@ -1,5 +1,6 @@
 // Shared declarations for the pyglm_b200 engine (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -45,9 +46,15 @@ constexpr int kMaxCand = 16;    // Q <= 16 candidate weights per edge (reference
 // Launchers (defined in the .cu files).  All enqueue on `stream` and return a status.
 // ---------------------------------------------------------------------------------
 
-// K1: X[t][pre*B+b] = sum_{k=1..R} ibasis[k-1][b] * S[halo+t-k][pre]
+// K1: X[t][pre*B+b] = sum_{k=1..R} ibasis[k-1][b] * S[halo+t-k][pre], written in one pass as the full-precision
+// filtered spike train (X: FP32 or FP64, may be null) and / or as the FP16 split planes of the tensor-core path
+// (X1, X2 with per-feature power-of-two scales sx; may be null): X * sx = X1 + X2 * 2^-11.
+struct FilterOut {
+    void* X = nullptr; int64_t ldx = 0; int x_dtype = PYGLM_B200_X_F32;
+    __half* X1 = nullptr; __half* X2 = nullptr; int64_t ldp = 0; const float* sx = nullptr;
+};
 int launch_filter(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
-                  void* dX, int64_t ldx, int x_dtype, cudaStream_t stream);
+                  const FilterOut& out, cudaStream_t stream);
 
 // dense FP64 causal filter of a real-valued stimulus (device pointers): out[t][d*B+b]
 int launch_filter_dense(const double* d_stim, int64_t T, int D, const double* d_ibasis, int R, int B, double* d_out,

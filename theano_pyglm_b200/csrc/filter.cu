@@ -4,207 +4,334 @@
 // 'full'[:T] :232-234), called from LinearBasisImpulses.preprocess_data (impulse.py:114-130).
 //
 // The reference runs B dense FFT convolutions.  Spike trains are sparse small integers
-// (~2% of bins non-zero), so this kernel gathers instead: each block owns a tile of TT output
-// bins x PC presynaptic columns, compacts the spikes of the tile (plus its R-bin left halo)
-// into per-column lists in shared memory, and every output bin sums ibasis rows over the
-// spikes inside its own window.  Accumulation is FP64 in increasing spike-time order (the
-// order oracle/convolve_with_basis_direct uses), the result is rounded once to the storage
-// type and leaves through a padded shared-memory tile so global stores are fully coalesced.
+// (~2% of bins non-zero), so this kernel gathers instead: a block owns a tile of `tt` output
+// bins x `pc` presynaptic columns.
+//  * Tile load.  The spike bytes of the tile (plus its R-bin left context) are read with 16-byte
+//    vector loads (a tile that spans all N columns is one contiguous byte range) and only the
+//    non-zero bytes do anything: they set a bit in a per-column bitmap over the tile's rows
+//    (counts > 1 also set a bit in a second bitmap and leave their count in a byte array).
+//  * Gather.  A warp task is 32 consecutive output bins of one column: the lanes fetch the bitmap
+//    words of the window [first bin - R, last bin), and the warp walks the set bits in increasing
+//    time (warp-uniform ffs loop).  Lane l adds basis[lag_l][b] for its own lag; the basis sits in
+//    shared memory basis-function-major, so the 32 lanes read 32 consecutive doubles (conflict-free,
+//    the 8 bytes per FP64 add that bound this kernel: DESIGN.md section 4).
+//    Accumulation is FP64 in increasing spike-time order (the order oracle/convolve_with_basis_direct
+//    uses), rounded once to the storage type.
+//  * Copy-out.  Results leave through a padded shared-memory tile so global stores are full rows:
+//    the full-precision X and / or -- in the same pass -- the FP16 split planes of the tensor-core
+//    path (X * sx = X1 + X2 * 2^-11 with the analytic per-feature scales of tc_spike_scales).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace pyglm {
 
 constexpr int kFiltThreads = 512;
 constexpr int kFiltWarps = kFiltThreads / 32;
-constexpr int kFiltSub = 64;        // output bins staged through shared memory at a time
+constexpr int kZ = 64;              // leading zeros of each basis function in shared memory
 
-struct FiltSmemLayout {
-    size_t off_basis, off_out, off_ent, off_idx, off_s, total;
+struct FiltLayout {
+    int tt, pc, sub, rows, mw, ostride;
+    size_t off_basis, off_sx, off_mask, off_cnt, off_out, off_next, total;
 };
 
-template <typename XT>
-static FiltSmemLayout filt_layout(int R, int B, int tt, int pc) {
-    FiltSmemLayout L;
-    const int rows = tt + R;
+static FiltLayout filt_layout(int R, int B, int bmax, int rpitch, int tt, int pc, size_t xsz)
+{
+    FiltLayout L{};
+    L.tt = tt; L.pc = pc;
+    L.rows = tt + R;
+    L.mw = (L.rows + 31) / 32 + 1;
+    L.ostride = (pc * B + 2) | 1;                                    // odd: conflict-free staging writes; room for one pad element
+    L.sub = 128;
+    while (L.sub > 32 && ((size_t)L.sub * L.ostride * xsz > 48 * 1024 || L.sub > tt)) L.sub >>= 1;
     size_t o = 0;
-    L.off_basis = o; o += (size_t)R * B * sizeof(double);
-    L.off_out = o;   o += (size_t)kFiltSub * (pc * B + 1) * sizeof(XT);
-    o = (o + 7) & ~(size_t)7;
-    L.off_ent = o;   o += (size_t)rows * pc * sizeof(uint16_t);
-    L.off_idx = o;   o += (size_t)(rows + 1) * pc * sizeof(uint16_t);
-    L.off_s = o;     o += (size_t)rows * (pc + 4);
+    L.off_basis = o; o += (size_t)rpitch * bmax * sizeof(double);
+    L.off_out = o;   o += (size_t)L.sub * L.ostride * xsz;
+    o = (o + 15) & ~(size_t)15;
+    L.off_mask = o;  o += (size_t)2 * pc * L.mw * sizeof(uint32_t);  // spike bitmap, then the counts>1 bitmap
+    L.off_sx = o;    o += (size_t)(pc * B + 2) * sizeof(float);
+    L.off_next = o;  o += 8;
+    L.off_cnt = o;   o += (size_t)pc * L.rows;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
 
-// BEXACT: B is exactly BMAX (no per-basis predicates in the inner loop)
-template <typename XT, int BMAX, bool BEXACT>
+// WX: write the full-precision X; WP: write the split planes.  BEXACT: B == BMAX (no per-basis predicates).
+// RP: pitch of one basis function in shared memory (0: R + kZ + 32): kZ zeros, the R values, >= 32 zeros.  A lane whose
+// lag falls outside 1..R reads one of the zeros instead of branching (x + 0.0 == x for every x the sums can hold).
+template <typename XT, int BMAX, bool BEXACT, bool WX, bool WP, int RP>
 __global__ void __launch_bounds__(kFiltThreads)
 filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
               const double* __restrict__ ibasis, int R, int B,
-              XT* __restrict__ X, int64_t ldx, int tt, int pc, FiltSmemLayout L)
+              XT* __restrict__ X, int64_t ldx,
+              __half* __restrict__ X1, __half* __restrict__ X2, int64_t ldp, const float* __restrict__ sx,
+              FiltLayout L)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    double*   sB   = reinterpret_cast<double*>(smem + L.off_basis);   // [R][B]
-    XT*       sOut = reinterpret_cast<XT*>(smem + L.off_out);         // [kFiltSub][pc*B+1]
-    uint16_t* sEnt = reinterpret_cast<uint16_t*>(smem + L.off_ent);   // [rows][pc]  tile row of the e-th spike of a column
-    uint16_t* sIdx = reinterpret_cast<uint16_t*>(smem + L.off_idx);   // [rows+1][pc] #spikes in tile rows [0,i)
-    uint8_t*  sS   = smem + L.off_s;                                  // [rows][pc+4]
+    double*   sB     = reinterpret_cast<double*>(smem + L.off_basis);    // [BMAX][P]   basis-function-major, zero beyond R
+    XT*       sOut   = reinterpret_cast<XT*>(smem + L.off_out);          // [sub][ostride]
+    uint32_t* sMask  = reinterpret_cast<uint32_t*>(smem + L.off_mask);   // [pc][mw]    bit i: tile row i of the column holds a spike
+    uint32_t* sMulti = sMask + L.pc * L.mw;                              // [pc][mw]    ... more than one
+    float*    sSx    = reinterpret_cast<float*>(smem + L.off_sx);        // [pc*B]      plane scales of the tile's features
+    uint8_t*  sCnt   = smem + L.off_cnt;                                 // [pc][rows]  count, written where sMulti is set
+    int*      sNext  = reinterpret_cast<int*>(smem + L.off_next);        // task counter of the gather
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int rows = tt + R;
+    const int tt = L.tt, pc = L.pc, rows = L.rows, mw = L.mw, ostride = L.ostride;
     const int64_t t0 = (int64_t)blockIdx.x * tt;      // first output bin of the tile
     const int c0 = blockIdx.y * pc;                   // first presynaptic column of the tile
-    const int sstride = pc + 4;
-    const int ostride = pc * B + 1;
-
-    // ---- stage the spike tile (tile row i <-> S row halo + t0 - R + i) and the basis.
-    // One warp per tile row, lanes across columns, eight rows in flight per warp.
-    const int64_t g0 = (int64_t)halo + t0 - R;
-    const int64_t gmax = (int64_t)halo + T;
-    for (int c = lane; c < pc; c += 32) {
-        const bool col_ok = c0 + c < N;
-        const uint8_t* src = S + (g0 + warp) * N + c0 + c;            // row `warp` of the tile, this lane's column
-        uint8_t* dsts = sS + warp * sstride + c;
-        for (int i = warp; i < rows; i += 4 * kFiltWarps) {
-            uint8_t v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t g = g0 + i + u * kFiltWarps;
-                v[u] = (col_ok && i + u * kFiltWarps < rows && g >= 0 && g < gmax) ? src[(int64_t)u * kFiltWarps * N] : (uint8_t)0;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u * kFiltWarps < rows) dsts[u * kFiltWarps * sstride] = v[u];
-            src += (int64_t)4 * kFiltWarps * N;
-            dsts += 4 * kFiltWarps * sstride;
-        }
-    }
-    for (int e = tid; e < R * B; e += kFiltThreads) sB[e] = ibasis[e];
-    __syncthreads();
-
-    // ---- compact each column's spikes: one warp per column, ballot prefix sums
-    for (int c = warp; c < pc; c += kFiltWarps) {
-        int count = 0;
-        for (int i0 = 0; i0 < rows; i0 += 32) {
-            const int i = i0 + lane;
-            const uint32_t v = (i < rows) ? sS[i * sstride + c] : 0u;
-            const uint32_t m = __ballot_sync(0xffffffffu, v != 0u);
-            const int pos = count + __popc(m & ((1u << lane) - 1u));
-            if (i < rows) sIdx[i * pc + c] = (uint16_t)pos;
-            if (v) sEnt[pos * pc + c] = (uint16_t)i;
-            count += __popc(m);
-        }
-        if (lane == 0) sIdx[rows * pc + c] = (uint16_t)count;
-    }
-    __syncthreads();
-
     const int ncol = min(pc, N - c0);
     const int width = ncol * B;
-    for (int sub = 0; sub < tt; sub += kFiltSub) {
-        if (t0 + sub >= T) break;
-        // ---- gather: a warp task = 32 consecutive output bins of one column
-        for (int task = warp; task < (kFiltSub / 32) * ncol; task += kFiltWarps) {
-            const int tg = task / ncol, c = task - tg * ncol;
-            const int ts = tg * 32 + lane;          // output bin within the sub-tile
-            const int tl = sub + ts;                // ... within the tile
-            const int i = tl + R;                   // its tile row; window = tile rows [tl, tl+R-1]
-            const int e0 = sIdx[(sub + tg * 32) * pc + c];
-            const int e1 = sIdx[(sub + tg * 32 + 31 + R) * pc + c];
-            double acc[BMAX];
+
+    for (int e = tid; e < 2 * pc * mw; e += kFiltThreads) sMask[e] = 0u;
+    const int P = RP ? RP : R + kZ + 32;
+    for (int e = tid; e < P * BMAX; e += kFiltThreads) {
+        const int b = e / P, k = e - b * P - kZ;
+        sB[e] = (b < B && k >= 0 && k < R) ? ibasis[(size_t)k * B + b] : 0.0;
+    }
+    if (tid == 0) *sNext = 0;
+    if (WP) for (int e = tid; e < pc * B + 2; e += kFiltThreads) sSx[e] = e < width ? sx[(size_t)c0 * B + e] : 0.f;
+    __syncthreads();
+
+    // ---- tile load: tile row i <-> S row g0 + i; rows outside [0, halo+T) hold no spikes
+    const int64_t g0 = (int64_t)halo + t0 - R;
+    const int r_lo = (int)max((int64_t)0, -g0);
+    const int r_hi = (int)min((int64_t)rows, (int64_t)halo + T - g0);
+    auto insert = [&](int row, int col, uint32_t v) {
+        atomicOr(&sMask[col * mw + (row >> 5)], 0x80000000u >> (row & 31));      // bit 31 = first row of the word
+        if (v > 1u) {
+            atomicOr(&sMulti[col * mw + (row >> 5)], 0x80000000u >> (row & 31));
+            sCnt[col * rows + row] = (uint8_t)v;
+        }
+    };
+    if (r_hi > r_lo) {
+        if (ncol == N) {
+            // every column: the tile is one contiguous byte range
+            const uint8_t* base = S + (g0 + r_lo) * N;
+            const int nbytes = (r_hi - r_lo) * N;
+            const int head = min(nbytes, (int)((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15));
+            const int nvec = (nbytes - head) >> 4;
+            auto insert_flat = [&](int f, uint32_t v) { const int r = f / N; insert(r_lo + r, f - r * N, v); };
+            for (int f = tid; f < head; f += kFiltThreads) { const uint32_t v = base[f]; if (v) insert_flat(f, v); }
+            const uint4* vp = reinterpret_cast<const uint4*>(base + head);
+            for (int v = tid; v < nvec; v += kFiltThreads) {
+                const uint4 q = __ldg(vp + v);
+                if ((q.x | q.y | q.z | q.w) == 0u) continue;
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
-#pragma unroll 1
-            for (int e = e0; e < e1; ++e) {
-                const int srow = sEnt[e * pc + c];            // warp-uniform broadcast
-                const int k = i - srow;                       // lag
-                const uint32_t cnt = sS[srow * sstride + c];  // warp-uniform: spike count of that bin
-                if (k >= 1 && k <= R) {
-                    const double* row = sB + (size_t)(k - 1) * B;
-                    if (cnt == 1u) {                          // the usual case: no multiply
+                for (int i = 0; i < 4; ++i) {
+                    if (w[i] == 0u) continue;
 #pragma unroll
-                        for (int b = 0; b < BMAX; ++b)
-                            if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], row[b]);
-                    } else {
-                        const double dc = (double)cnt;
-#pragma unroll
-                        for (int b = 0; b < BMAX; ++b)
-                            if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(dc, row[b]));
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t b = (w[i] >> (8 * j)) & 0xffu;
+                        if (b) insert_flat(head + 16 * v + 4 * i + j, b);
                     }
                 }
             }
+            for (int f = head + 16 * nvec + tid; f < nbytes; f += kFiltThreads) { const uint32_t v = base[f]; if (v) insert_flat(f, v); }
+        } else if (((N | c0 | ncol) & 3) == 0 && (reinterpret_cast<uintptr_t>(S) & 3) == 0) {
+            // a block of columns, word-aligned row segments
+            const int wpr = ncol >> 2;
+            for (int it = tid; it < (r_hi - r_lo) * wpr; it += kFiltThreads) {
+                const int r = it / wpr, wi = it - r * wpr;
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(S + (g0 + r_lo + r) * N + c0) + wi);
+                if (w == 0u) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t b = (w >> (8 * j)) & 0xffu;
+                    if (b) insert(r_lo + r, 4 * wi + j, b);
+                }
+            }
+        } else {
+            for (int it = tid; it < (r_hi - r_lo) * ncol; it += kFiltThreads) {
+                const int r = it / ncol, c = it - r * ncol;
+                const uint32_t b = S[(g0 + r_lo + r) * N + c0 + c];
+                if (b) insert(r_lo + r, c, b);
+            }
+        }
+    }
+    __syncthreads();
+
+    // copy-out roles, fixed for the whole tile: a thread owns one pair of adjacent features (planes, and X when both are
+    // written) or one feature (X alone) and walks down the rows of the sub-tile, `rp` rows per pass of the block
+    const int wpl = WP ? ((c0 + ncol == N) ? (int)(ldp - (int64_t)c0 * B) : width) : 0;   // plane columns incl. the zero pad [N*B, ldp)
+    const int nitem = WP ? (wpl + 1) / 2 : width;
+    const int rp = kFiltThreads / nitem;
+    const int prow = tid / nitem, pit = tid - prow * nitem;
+    const bool pact = prow < rp;
+    const int pe = WP ? 2 * pit : pit;
+    const bool pv0 = pe < width, pv1 = WP && pe + 1 < width;
+    const float ps0 = (WP && pv0) ? sSx[pe] : 0.f, ps1 = (WP && pv1) ? sSx[pe + 1] : 0.f;   // exact power-of-two scales
+
+    const int sub_n = L.sub, ngrp = sub_n >> 5;
+    for (int sub = 0; sub < tt; sub += sub_n) {
+        if (t0 + sub >= T) break;
+        // ---- gather: a warp task = 32 consecutive output bins of one column, handed out by a counter
+        for (;;) {
+            int task = 0;
+            if (lane == 0) task = atomicAdd(sNext, 1);
+            task = __shfl_sync(0xffffffffu, task, 0);
+            if (task >= ngrp * ncol) break;
+            int grp = 0, c = task;
+            while (c >= ncol) { c -= ncol; ++grp; }
+            const int tb = sub + (grp << 5);            // first output bin of the task within the tile (multiple of 32)
+            // lag - 1 of a spike in tile row s is (tb + lane + R - 1) - s, in [-62, R + 30] for the rows of the window's
+            // words; the basis sits between kZ leading and >= 32 trailing zeros, so no lane needs a range check
+            const double* lbase = sB + (tb + lane + R - 1 + kZ);
+            double acc[BMAX];
+#pragma unroll
+            for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
+            const int w0 = tb >> 5, w1 = min((tb + R + 30) >> 5, mw - 1);
+            const uint32_t* mrow = sMask + c * mw;
+            const uint32_t* xrow = sMulti + c * mw;
+            for (int wb = w0; wb <= w1; wb += 32) {
+                const int wi = wb + lane;
+                const uint32_t mm = wi <= w1 ? mrow[wi] : 0u;
+                const uint32_t mx = wi <= w1 ? xrow[wi] : 0u;
+                uint32_t nz = __ballot_sync(0xffffffffu, mm != 0u);
+                while (nz) {
+                    const int j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t m = __shfl_sync(0xffffffffu, mm, j);       // bit 31 = first row of the word
+                    const uint32_t x = __shfl_sync(0xffffffffu, mx, j);
+                    const int rb = (wb + j) << 5;
+                    const double* wbase = lbase - rb;
+                    if (x == 0u) {                             // the usual case: single spikes, no multiply
+                        do {
+                            const int pos = __clz(m);          // warp-uniform: the spike's row within the word
+                            m &= ~(0x80000000u >> pos);
+                            const double* p = wbase - pos;
+#pragma unroll
+                            for (int b = 0; b < BMAX; ++b)
+                                if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], p[b * P]);
+                        } while (m);
+                    } else {                                   // rare: a bin of this word holds several spikes
+                        do {
+                            const int pos = __clz(m);
+                            const uint32_t bit = 0x80000000u >> pos;
+                            m &= ~bit;
+                            const double* p = wbase - pos;
+                            const double dc = (x & bit) ? (double)sCnt[c * rows + rb + pos] : 1.0;
+#pragma unroll
+                            for (int b = 0; b < BMAX; ++b)
+                                if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(dc, p[b * P]));
+                        } while (m);
+                    }
+                }
+            }
+            XT* o = sOut + ((grp << 5) + lane) * ostride + c * B;
 #pragma unroll
             for (int b = 0; b < BMAX; ++b)
-                if (BEXACT || b < B) sOut[ts * ostride + c * B + b] = (XT)acc[b];
+                if (BEXACT || b < B) o[b] = (XT)acc[b];
         }
         __syncthreads();
+        if (tid == 0) *sNext = 0;
         // ---- coalesced copy-out of the valid part of the sub-tile
-        const int nrow = (int)min((int64_t)kFiltSub, T - (t0 + sub));
-        XT* dst = X + (t0 + sub) * ldx + (int64_t)c0 * B;
-        {
-            const XT* src = sOut + warp * ostride + lane;
-            XT* drow = dst + (int64_t)warp * ldx + lane;
-            for (int ts = warp; ts < nrow; ts += kFiltWarps) {
-#pragma unroll
-                for (int j = 0; j < (32 * BMAX + 31) / 32; ++j)              // pc <= 32 columns: at most BMAX chunks of 32
-                    if (lane + 32 * j < width) drow[32 * j] = src[32 * j];
-                src += kFiltWarps * ostride;
-                drow += (int64_t)kFiltWarps * ldx;
+        const int nrow = (int)min((int64_t)sub_n, T - (t0 + sub));
+        if (pact) {
+            const XT* src = sOut + prow * ostride + pe;
+            const int64_t t = t0 + sub + prow;
+            if (WP) {
+                __half2* d1 = reinterpret_cast<__half2*>(X1 + t * ldp + (int64_t)c0 * B) + pit;
+                __half2* d2 = reinterpret_cast<__half2*>(X2 + t * ldp + (int64_t)c0 * B) + pit;
+                XT* dx = WX ? X + t * ldx + (int64_t)c0 * B + pe : nullptr;
+                for (int r = prow; r < nrow; r += rp) {
+                    const float x0 = pv0 ? (float)src[0] : 0.f, x1 = pv1 ? (float)src[1] : 0.f;
+                    if (WX) {
+                        if (pv1) *reinterpret_cast<float2*>(dx) = make_float2(x0, x1);
+                        else if (pv0) *reinterpret_cast<float*>(dx) = x0;
+                        dx += (int64_t)rp * ldx;
+                    }
+                    const float v0 = x0 * ps0, v1 = x1 * ps1;
+                    const __half2 h1 = __floats2half2_rn(v0, v1);
+                    const float2 f1 = __half22float2(h1);
+                    *d1 = h1;
+                    *d2 = __floats2half2_rn((v0 - f1.x) * 2048.0f, (v1 - f1.y) * 2048.0f);
+                    d1 += (int64_t)rp * (ldp >> 1);
+                    d2 += (int64_t)rp * (ldp >> 1);
+                    src += rp * ostride;
+                }
+            } else {
+                XT* dx = X + t * ldx + (int64_t)c0 * B + pe;
+                for (int r = prow; r < nrow; r += rp) {
+                    *dx = *src;
+                    dx += (int64_t)rp * ldx;
+                    src += rp * ostride;
+                }
             }
         }
         __syncthreads();
     }
 }
 
-template <typename XT, int BMAX, bool BEXACT>
-static int launch_filter_t(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
-                           XT* dX, int64_t ldx, cudaStream_t stream)
+template <typename XT, int BMAX, bool BEXACT, bool WX, bool WP, int RP>
+static int launch_filter_r(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                           const FilterOut& out, cudaStream_t stream)
 {
-    // pick the largest tile whose shared memory fits (<= 200 KB: one resident block per SM at worst)
-    const int cand[][2] = {{192, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {64, 4}};
-    int tt = 0, pc = 0;
-    FiltSmemLayout L{};
-    for (auto& c : cand) {
-        L = filt_layout<XT>(R, B, c[0], c[1]);
-        if (L.total <= 113 * 1024) { tt = c[0]; pc = c[1]; break; }     // two resident blocks per SM
+    // the largest tile with two resident blocks per SM, else the largest that fits at all
+    const int cand[][2] = {{512, 32}, {256, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {32, 4}};
+    FiltLayout L{};
+    bool found = false;
+    for (size_t limit : {(size_t)113 * 1024, (size_t)227 * 1024}) {
+        for (auto& c : cand) {
+            L = filt_layout(R, B, BMAX, RP ? RP : R + kZ + 32, c[0], std::min(c[1], N), sizeof(XT));
+            if (L.total <= limit) { found = true; break; }
+        }
+        if (found) break;
     }
-    if (tt == 0) {
+    if (!found) {
         set_error("filter: R=%d B=%d needs more shared memory than one SM has", R, B);
         return PYGLM_B200_EUNSUPPORTED;
     }
-    if (tt + R > 65535) {
-        set_error("filter: R=%d too long", R);
-        return PYGLM_B200_EUNSUPPORTED;
-    }
-    auto kern = filter_kernel<XT, BMAX, BEXACT>;
+    auto kern = filter_kernel<XT, BMAX, BEXACT, WX, WP, RP>;
     PYGLM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-    dim3 grid((unsigned)ceil_div(T, tt), (unsigned)ceil_div(N, pc));
-    kern<<<grid, kFiltThreads, L.total, stream>>>(dS, T, N, halo, d_ibasis, R, B, dX, ldx, tt, pc, L);
+    dim3 grid((unsigned)ceil_div(T, L.tt), (unsigned)ceil_div(N, L.pc));
+    kern<<<grid, kFiltThreads, L.total, stream>>>(dS, T, N, halo, d_ibasis, R, B, static_cast<XT*>(out.X), out.ldx,
+                                                   out.X1, out.X2, out.ldp, out.sx, L);
     PYGLM_CUDA(cudaGetLastError());
     return PYGLM_B200_OK;
 }
 
+template <typename XT, int BMAX, bool BEXACT, bool WX, bool WP>
+static int launch_filter_v(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                           const FilterOut& out, cudaStream_t stream)
+{
+    if (R + kZ + 32 <= 320) return launch_filter_r<XT, BMAX, BEXACT, WX, WP, 320>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    return launch_filter_r<XT, BMAX, BEXACT, WX, WP, 0>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+}
+
+template <typename XT, bool WX, bool WP>
+static int launch_filter_b(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                           const FilterOut& out, cudaStream_t stream)
+{
+    if (B == 5)  return launch_filter_v<XT, 5, true, WX, WP>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    if (B == 10) return launch_filter_v<XT, 10, true, WX, WP>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    if (B <= 4)  return launch_filter_v<XT, 4, false, WX, WP>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    if (B <= 8)  return launch_filter_v<XT, 8, false, WX, WP>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    return launch_filter_v<XT, 16, false, WX, WP>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+}
+
 int launch_filter(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
-                  void* dX, int64_t ldx, int x_dtype, cudaStream_t stream)
+                  const FilterOut& out, cudaStream_t stream)
 {
     if (B < 1 || B > kMaxBasis) {
         set_error("filter: B=%d outside [1,%d]", B, kMaxBasis);
         return PYGLM_B200_EUNSUPPORTED;
     }
     if (T <= 0) return PYGLM_B200_OK;
-    if (x_dtype == PYGLM_B200_X_F32) {
-        float* x = static_cast<float*>(dX);
-        if (B == 5)  return launch_filter_t<float, 5, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        if (B == 10) return launch_filter_t<float, 10, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        if (B <= 8)  return launch_filter_t<float, 8, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        return launch_filter_t<float, 16, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-    } else {
-        double* x = static_cast<double*>(dX);
-        if (B == 5)  return launch_filter_t<double, 5, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        if (B == 10) return launch_filter_t<double, 10, true>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        if (B <= 8)  return launch_filter_t<double, 8, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
-        return launch_filter_t<double, 16, false>(dS, T, N, halo, d_ibasis, R, B, x, ldx, stream);
+    const bool wx = out.X != nullptr, wp = out.X1 != nullptr;
+    if (!wx && !wp) return PYGLM_B200_OK;
+    if (wp && (out.X2 == nullptr || out.sx == nullptr || (out.ldp & 1) || out.ldp < (int64_t)N * B)) {
+        set_error("filter: bad plane outputs");
+        return PYGLM_B200_EINVAL;
     }
+    if (wx && out.x_dtype == PYGLM_B200_X_F64) {
+        if (wp) { set_error("filter: split planes are built from the FP32 filtered spike train"); return PYGLM_B200_EUNSUPPORTED; }
+        return launch_filter_b<double, true, false>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    }
+    if (wx && wp) return launch_filter_b<float, true, true>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    if (wx)       return launch_filter_b<float, true, false>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    return launch_filter_b<float, false, true>(dS, T, N, halo, d_ibasis, R, B, out, stream);
 }
 
 // ---------------------------------------------------------------------------------

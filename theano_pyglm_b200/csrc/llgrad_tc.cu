@@ -91,18 +91,64 @@ bool tc_uses_fused_kernel(int64_t nfeat) { return nfeat <= kMaxChunks * kChunkF;
 // ---------------------------------------------------------------------------------------------
 // One-time: per-feature scales and the FP16 split planes of X
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_colmax_kernel(const float* __restrict__ X, int64_t T, int NB, int64_t ldx, unsigned* colmax)
+// Spike-history features: analytic bound |X[t][pre*B+b]| <= (largest count in column pre) * sum_k |ibasis[k][b]|, so the
+// scales need no pass over X (and are the same whether the planes come straight from K1 or from a resident X).
+__global__ void __launch_bounds__(256)
+tc_spike_colmax_kernel(const uint8_t* __restrict__ S, int64_t nbytes, int N, unsigned* __restrict__ cmax)
 {
-    const int j = blockIdx.y * blockDim.x + threadIdx.x;
+    extern __shared__ unsigned s_cmax[];                                  // [N]
+    for (int n = threadIdx.x; n < N; n += blockDim.x) s_cmax[n] = 0u;
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t mis = (int64_t)((16 - (reinterpret_cast<uintptr_t>(S) & 15)) & 15);
+    const int64_t head = nbytes < mis ? nbytes : mis;
+    const int64_t nvec = (nbytes - head) >> 4;
+    auto note = [&](int64_t f, unsigned v) {
+        const int n = (int)(f % N);
+        if (v > s_cmax[n]) atomicMax(&s_cmax[n], v);
+    };
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid < head && S[gtid]) note(gtid, S[gtid]);
+    const uint4* vp = reinterpret_cast<const uint4*>(S + head);
+    for (int64_t v = gtid; v < nvec; v += stride) {
+        const uint4 q = __ldg(vp + v);
+        if ((q.x | q.y | q.z | q.w) == 0u) continue;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) {
+                const unsigned b = (w[i] >> (8 * j)) & 0xffu;
+                if (b) note(head + 16 * v + 4 * i + j, b);
+            }
+    }
+    for (int64_t f = head + 16 * nvec + gtid; f < nbytes; f += stride) if (S[f]) note(f, S[f]);
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) if (s_cmax[n]) atomicMax(&cmax[n], s_cmax[n]);
+}
+
+__global__ void tc_spike_scales_kernel(const unsigned* __restrict__ cmax, const double* __restrict__ ibasis, int R, int B, int N,
+                                       float* __restrict__ sx)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N * B) return;
+    const int pre = j / B, b = j - pre * B;
+    double s = 0.0;
+    for (int k = 0; k < R; ++k) s += fabs(ibasis[(size_t)k * B + b]);
+    sx[j] = pow2_scale((float)(s * (double)cmax[pre]) * 1.0001f);
+}
+
+// Stimulus features (real valued): the scale comes from the data.
+__global__ void tc_colmax_kernel(const float* __restrict__ X, int64_t T, int j0, int NB, int64_t ldx, unsigned* colmax)
+{
+    const int j = j0 + blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= NB) return;
     float m = 0.f;
     for (int64_t t = blockIdx.x; t < T; t += gridDim.x) m = fmaxf(m, fabsf(X[t * ldx + j]));
     atomicMax(&colmax[j], __float_as_uint(m));       // non-negative floats order like unsigned ints
 }
 
-__global__ void tc_scales_kernel(const unsigned* colmax, int NB, float* sx)
+__global__ void tc_scales_kernel(const unsigned* colmax, int j0, int NB, float* sx)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = j0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (j < NB) sx[j] = pow2_scale(__uint_as_float(colmax[j]));
 }
 
@@ -1372,7 +1418,7 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMalloc(&ws.X1, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.X2, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.sx, NB * sizeof(float)));
-    PYGLM_CUDA(cudaMalloc(&ws.colmax, NB * sizeof(unsigned)));
+    PYGLM_CUDA(cudaMalloc(&ws.colmax, (size_t)(NB + N) * sizeof(unsigned)));   // per feature, then per presynaptic column
     PYGLM_CUDA(cudaMalloc(&ws.Mp, (size_t)2 * kNcol * kMaxChunks * kChunkF * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.colpar, 2 * kNcol * sizeof(float)));
     ws.Np = (int)round_up(N, 32) + 32;            // slack: a column group may start anywhere below N
@@ -1381,7 +1427,6 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMalloc(&ws.Sp, (size_t)T * ws.Np));
     PYGLM_CUDA(cudaMemsetAsync(ws.Sp, 0, (size_t)T * ws.Np, stream));
     PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
-    PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, NB * sizeof(unsigned), stream));
     ws.tmaps = malloc(12 * sizeof(CUtensorMap));
     if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
     CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
@@ -1401,6 +1446,32 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     return PYGLM_B200_OK;
 }
 
+// per-feature scales: analytic for the N*B spike-history features, from the data for F stimulus features (X resident)
+static int tc_compute_scales(TcWorkspace& ws, const uint8_t* S, int64_t srows, int N, const double* d_ibasis, int R, int B,
+                             const float* X, int64_t T, int F, int64_t ldx, cudaStream_t stream)
+{
+    const int NS = N * B, NB = NS + F;
+    PYGLM_CUDA(cudaMemsetAsync(ws.colmax, 0, (size_t)(NB + N) * sizeof(unsigned), stream));
+    unsigned* cmax = ws.colmax + NB;                                       // [N] largest count per presynaptic column
+    const int64_t nbytes = srows * N;
+    if (nbytes > 0) {
+        const unsigned blocks = (unsigned)std::min<int64_t>(148 * 8, ceil_div(nbytes, 256 * 16));
+        tc_spike_colmax_kernel<<<blocks, 256, (size_t)N * sizeof(unsigned), stream>>>(S, nbytes, N, cmax);
+        PYGLM_CUDA(cudaGetLastError());
+    }
+    tc_spike_scales_kernel<<<(unsigned)ceil_div(NS, 128), 128, 0, stream>>>(cmax, d_ibasis, R, B, N, ws.sx);
+    PYGLM_CUDA(cudaGetLastError());
+    if (F > 0) {
+        dim3 gmax((unsigned)std::min<int64_t>(T, 148 * 16), (unsigned)ceil_div(F, 128));
+        tc_colmax_kernel<<<gmax, 128, 0, stream>>>(X, T, NS, NB, ldx, ws.colmax);
+        PYGLM_CUDA(cudaGetLastError());
+        tc_scales_kernel<<<(unsigned)ceil_div(F, 128), 128, 0, stream>>>(ws.colmax, NS, NB, ws.sx);
+        PYGLM_CUDA(cudaGetLastError());
+    }
+    return PYGLM_B200_OK;
+}
+
+// Planes from a resident FP32 X (datasets with stimulus features, or planes dropped earlier): scales, then one split pass.
 int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
 {
     if (ws.planes_ready) return PYGLM_B200_OK;
@@ -1408,51 +1479,27 @@ int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
     const int NB = a.N * a.B + a.F;
     int rc = alloc_planes(ws, a.S, a.T, a.N, a.halo, NB, stream);
     if (rc) return rc;
-    dim3 gmax((unsigned)std::min<int64_t>(a.T, 148 * 16), (unsigned)ceil_div(NB, 128));
-    tc_colmax_kernel<<<gmax, 128, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.colmax);
-    PYGLM_CUDA(cudaGetLastError());
-    tc_scales_kernel<<<(unsigned)ceil_div(NB, 128), 128, 0, stream>>>(ws.colmax, NB, ws.sx);
-    PYGLM_CUDA(cudaGetLastError());
+    if ((rc = tc_compute_scales(ws, a.S, a.T + a.halo, a.N, a.ibasis, a.R, a.B, a.X, a.T, a.F, a.ldx, stream))) return rc;
     tc_split_X_kernel<<<(unsigned)ceil_div((int64_t)a.T * ws.ldp, 256), 256, 0, stream>>>(a.X, a.T, NB, a.ldx, ws.sx, ws.X1, ws.X2, ws.ldp);
     PYGLM_CUDA(cudaGetLastError());
     ws.planes_ready = true;
     return PYGLM_B200_OK;
 }
 
-// Planes-only ingest (PYGLM_B200_X_PLANES): the FP32 filtered spike train is never resident.  The filter runs
-// twice over time chunks through one scratch buffer: pass 1 finds the per-feature scales, pass 2 splits.
-int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
-                              int R, int B, cudaStream_t stream)
+// Single-pass ingest: K1 writes the split planes (and, when `X` is given, the FP32 filtered spike train) straight from its
+// gather; no FP32 round trip, no pass over X for the scales.  Used for planes-only datasets and for FP32 datasets without
+// stimulus features.
+int tc_build_planes_direct(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
+                           int R, int B, float* X, int64_t ldx, cudaStream_t stream)
 {
     const int NB = N * B;
-    const int64_t ldx = round_up(NB, 4);
-    int rc = alloc_planes(ws, S, T, N, halo, NB, stream);
-    if (rc) return rc;
-    int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(T, ((int64_t)256 << 20) / (ldx * 4)));   // ~256 MB scratch
-    if (const char* env = getenv("PYGLM_PLANES_CHUNK")) chunk = std::max<int64_t>(1, atoll(env));          // tests: force several chunks
-    float* scratch = nullptr;
-    PYGLM_CUDA(cudaMalloc(&scratch, (size_t)chunk * ldx * sizeof(float)));
-    PYGLM_CUDA(cudaMemsetAsync(scratch, 0, (size_t)chunk * ldx * sizeof(float), stream));
-    for (int pass = 0; pass < 2 && rc == PYGLM_B200_OK; ++pass) {
-        for (int64_t r0 = 0; r0 < T && rc == PYGLM_B200_OK; r0 += chunk) {
-            const int64_t nt = std::min(chunk, T - r0);
-            const int64_t h = std::min<int64_t>(R, halo + r0);                 // left context available for this chunk
-            rc = launch_filter(S + (halo + r0 - h) * N, nt, N, (int)h, d_ibasis, R, B, scratch, ldx, PYGLM_B200_X_F32, stream);
-            if (rc) break;
-            if (pass == 0) {
-                dim3 gmax((unsigned)std::min<int64_t>(nt, 148 * 16), (unsigned)ceil_div(NB, 128));
-                tc_colmax_kernel<<<gmax, 128, 0, stream>>>(scratch, nt, NB, ldx, ws.colmax);
-            } else {
-                tc_split_X_kernel<<<(unsigned)ceil_div(nt * ws.ldp, 256), 256, 0, stream>>>(
-                    scratch, nt, NB, ldx, ws.sx, ws.X1 + r0 * ws.ldp, ws.X2 + r0 * ws.ldp, ws.ldp);
-            }
-            if (cudaGetLastError() != cudaSuccess) { set_error("planes-only ingest: kernel launch failed"); rc = PYGLM_B200_ECUDA; }
-        }
-        if (pass == 0 && rc == PYGLM_B200_OK) tc_scales_kernel<<<(unsigned)ceil_div(NB, 128), 128, 0, stream>>>(ws.colmax, NB, ws.sx);
-    }
-    cudaStreamSynchronize(stream);
-    cudaFree(scratch);
-    if (rc) return rc;
+    int rc = PYGLM_B200_OK;
+    if (!ws.X1 && (rc = alloc_planes(ws, S, T, N, halo, NB, stream))) return rc;
+    if ((rc = tc_compute_scales(ws, S, T + halo, N, d_ibasis, R, B, nullptr, T, 0, 0, stream))) return rc;
+    FilterOut out;
+    out.X = X; out.ldx = ldx; out.x_dtype = PYGLM_B200_X_F32;
+    out.X1 = ws.X1; out.X2 = ws.X2; out.ldp = ws.ldp; out.sx = ws.sx;
+    if ((rc = launch_filter(S, T, N, halo, d_ibasis, R, B, out, stream))) return rc;
     ws.planes_ready = true;
     return PYGLM_B200_OK;
 }

@@ -13,7 +13,7 @@ struct TcWorkspace {
     __half* X2 = nullptr;
     int64_t ldp = 0;              // row pitch of the planes in elements (multiple of 8)
     float* sx = nullptr;          // [NB] per-feature power-of-two scale
-    unsigned* colmax = nullptr;   // [NB] scratch for the scale search
+    unsigned* colmax = nullptr;   // [NB + N] scratch for the scale search (per feature, per presynaptic column)
     uint8_t* Sp = nullptr;        // [T][Np] zero-padded copy of the spikes (Np % 32 == 0)
     int Np = 0;
     unsigned* colflag = nullptr;  // [N] range flags raised by the FP32 epilogues (exp nonlinearity, see kExpSafe)
@@ -32,6 +32,7 @@ struct TcWorkspace {
 struct TcArgs {
     const float* X; int64_t ldx;
     const uint8_t* S; int64_t T; int N; int halo; int B; int F;
+    const double* ibasis; int R;  // [R][B] interpolated basis (scales of the split planes)
     double dt; int nlin;
     int n_lo, ncols;
     const double* bias; const double* w; const int8_t* A; const double* W;
@@ -43,8 +44,8 @@ bool tc_supported(int64_t T, int N, int B, int x_dtype);
 bool tc_uses_fused_kernel(int64_t nfeat);
 // shared with the GEMM path
 int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
-int tc_build_planes_streaming(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
-                              int R, int B, cudaStream_t stream);
+int tc_build_planes_direct(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
+                           int R, int B, float* X, int64_t ldx, cudaStream_t stream);
 int tc_make_map_2d(void* map, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1,
                    int swizzle = 0);        // 0: SWIZZLE_64B, 1: SWIZZLE_128B, 2: SWIZZLE_32B
 int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);

@@ -24,7 +24,7 @@ EXPORTS = [
     "pyglm_b200_dataset_create", "pyglm_b200_dataset_create_stim", "pyglm_b200_dataset_destroy",
     "pyglm_b200_dataset_num_stim", "pyglm_b200_filter_dense", "pyglm_b200_dataset_info",
     "pyglm_b200_dataset_get_fS", "pyglm_b200_dataset_device_X", "pyglm_b200_dataset_device_S",
-    "pyglm_b200_dataset_refilter",
+    "pyglm_b200_dataset_refilter", "pyglm_b200_dataset_filter_bytes",
     "pyglm_b200_ll_grad", "pyglm_b200_ll_grad_dev", "pyglm_b200_resolve_path", "pyglm_b200_range_flags",
     "pyglm_b200_firing_rate",
     "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_delta_ll_dev", "pyglm_b200_gibbs_commit",
@@ -67,6 +67,7 @@ def load_library():
     lib.pyglm_b200_dataset_device_S.argtypes = [p]
     lib.pyglm_b200_dataset_device_S.restype = p
     lib.pyglm_b200_dataset_refilter.argtypes = [p, p]
+    lib.pyglm_b200_dataset_filter_bytes.argtypes = [p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.pyglm_b200_ll_grad.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p]
     lib.pyglm_b200_ll_grad_dev.argtypes = [p, p, p, p, p, i32, i32, i32, i32, p, p, p, p]
     lib.pyglm_b200_resolve_path.argtypes = [p, i32]
@@ -204,6 +205,12 @@ class Dataset:
 
     def refilter(self, stream=0):
         _check(load_library().pyglm_b200_dataset_refilter(self._h, C.c_void_p(stream)))
+
+    def filter_bytes(self):
+        """(bytes read, bytes written) by one K1 pass over this dataset."""
+        r, w = C.c_int64(0), C.c_int64(0)
+        _check(load_library().pyglm_b200_dataset_filter_bytes(self._h, C.byref(r), C.byref(w)))
+        return r.value, w.value
 
     def device_X(self):
         return load_library().pyglm_b200_dataset_device_X(self._h)
