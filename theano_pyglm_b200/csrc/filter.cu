@@ -28,7 +28,7 @@ namespace pyglm {
 
 constexpr int kFiltThreads = 512;
 constexpr int kFiltWarps = kFiltThreads / 32;
-constexpr int kZ = 64;              // leading zeros of each basis function in shared memory
+constexpr int kZ = 96;              // leading zeros of each basis function in shared memory (>= 64 trailing ones)
 
 struct FiltLayout {
     int tt, pc, sub, rows, mw, ostride;
@@ -43,7 +43,7 @@ static FiltLayout filt_layout(int R, int B, int bmax, int rpitch, int tt, int pc
     L.mw = (L.rows + 31) / 32 + 1;
     L.ostride = (pc * B + 2) | 1;                                    // odd: conflict-free staging writes; room for one pad element
     L.sub = 128;
-    while (L.sub > 32 && ((size_t)L.sub * L.ostride * xsz > 48 * 1024 || L.sub > tt)) L.sub >>= 1;
+    while (L.sub > 64 && ((size_t)L.sub * L.ostride * xsz > 48 * 1024 || L.sub > tt)) L.sub >>= 1;
     size_t o = 0;
     L.off_basis = o; o += (size_t)rpitch * bmax * sizeof(double);
     L.off_out = o;   o += (size_t)L.sub * L.ostride * xsz;
@@ -57,7 +57,7 @@ static FiltLayout filt_layout(int R, int B, int bmax, int rpitch, int tt, int pc
 }
 
 // WX: write the full-precision X; WP: write the split planes.  BEXACT: B == BMAX (no per-basis predicates).
-// RP: pitch of one basis function in shared memory (0: R + kZ + 32): kZ zeros, the R values, >= 32 zeros.  A lane whose
+// RP: pitch of one basis function in shared memory (0: R + kZ + 64): kZ zeros, the R values, >= 64 zeros.  A lane whose
 // lag falls outside 1..R reads one of the zeros instead of branching (x + 0.0 == x for every x the sums can hold).
 template <typename XT, int BMAX, bool BEXACT, bool WX, bool WP, int RP>
 __global__ void __launch_bounds__(kFiltThreads)
@@ -84,7 +84,7 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
     const int width = ncol * B;
 
     for (int e = tid; e < 2 * pc * mw; e += kFiltThreads) sMask[e] = 0u;
-    const int P = RP ? RP : R + kZ + 32;
+    const int P = RP ? RP : R + kZ + 64;
     for (int e = tid; e < P * BMAX; e += kFiltThreads) {
         const int b = e / P, k = e - b * P - kZ;
         sB[e] = (b < B && k >= 0 && k < R) ? ibasis[(size_t)k * B + b] : 0.0;
@@ -163,66 +163,74 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
     const bool pv0 = pe < width, pv1 = WP && pe + 1 < width;
     const float ps0 = (WP && pv0) ? sSx[pe] : 0.f, ps1 = (WP && pv1) ? sSx[pe + 1] : 0.f;   // exact power-of-two scales
 
-    const int sub_n = L.sub, ngrp = sub_n >> 5;
+    const int sub_n = L.sub, ngrp = sub_n >> 6;
+    const uint32_t next_addr = (uint32_t)__cvta_generic_to_shared(sNext);
     for (int sub = 0; sub < tt; sub += sub_n) {
         if (t0 + sub >= T) break;
-        // ---- gather: a warp task = 32 consecutive output bins of one column, handed out by a counter
+        // ---- gather: a warp task = 64 consecutive output bins of one column (lane l: bins l and l + 32), handed out
+        // by a counter
         for (;;) {
             int task = 0;
-            if (lane == 0) task = atomicAdd(sNext, 1);
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(task) : "r"(next_addr) : "memory");
             task = __shfl_sync(0xffffffffu, task, 0);
             if (task >= ngrp * ncol) break;
             int grp = 0, c = task;
             while (c >= ncol) { c -= ncol; ++grp; }
-            const int tb = sub + (grp << 5);            // first output bin of the task within the tile (multiple of 32)
-            // lag - 1 of a spike in tile row s is (tb + lane + R - 1) - s, in [-62, R + 30] for the rows of the window's
-            // words; the basis sits between kZ leading and >= 32 trailing zeros, so no lane needs a range check
-            const double* lbase = sB + (tb + lane + R - 1 + kZ);
-            double acc[BMAX];
+            const int tb = sub + (grp << 6);            // first output bin of the task within the tile (multiple of 64)
+            // lag - 1 of a spike in tile row s is (tb + lane + R - 1) - s for my first bin, 32 more for my second; over the
+            // rows of the window's words that is [-94, R + 62]: the basis sits between kZ leading and >= 64 trailing
+            // zeros, so no lane needs a range check (x + 0.0 == x)
+            const double* lbase = sB + (tb + lane + R - 1 + kZ - 31);
+            double acc[BMAX], acc2[BMAX];
 #pragma unroll
-            for (int b = 0; b < BMAX; ++b) acc[b] = 0.0;
-            const int w0 = tb >> 5, w1 = min((tb + R + 30) >> 5, mw - 1);
+            for (int b = 0; b < BMAX; ++b) acc[b] = acc2[b] = 0.0;
+            const int w0 = tb >> 5, w1 = min((tb + R + 62) >> 5, mw - 1);
             const uint32_t* mrow = sMask + c * mw;
             const uint32_t* xrow = sMulti + c * mw;
             for (int wb = w0; wb <= w1; wb += 32) {
-                const int wi = wb + lane;
+                const int wi = wb + 31 - lane;                          // lane 31 holds the first word: highest ballot bit first
                 const uint32_t mm = wi <= w1 ? mrow[wi] : 0u;
                 const uint32_t mx = wi <= w1 ? xrow[wi] : 0u;
                 uint32_t nz = __ballot_sync(0xffffffffu, mm != 0u);
+                const bool anyx = __ballot_sync(0xffffffffu, mx != 0u) != 0u;
                 while (nz) {
-                    const int j = __ffs(nz) - 1;
-                    nz &= nz - 1;
+                    const int j = 31 - __clz(nz);
+                    nz ^= 1u << j;
                     uint32_t m = __shfl_sync(0xffffffffu, mm, j);       // bit 31 = first row of the word
-                    const uint32_t x = __shfl_sync(0xffffffffu, mx, j);
-                    const int rb = (wb + j) << 5;
-                    const double* wbase = lbase - rb;
-                    if (x == 0u) {                             // the usual case: single spikes, no multiply
+                    const double* wbase = lbase - ((wb + 31 - j) << 5);
+                    if (!anyx) {                               // the usual case: single spikes, no multiply
                         do {
-                            const int pos = __clz(m);          // warp-uniform: the spike's row within the word
-                            m &= ~(0x80000000u >> pos);
-                            const double* p = wbase - pos;
+                            const int hb = 31 - __clz(m);      // warp-uniform: the spike sits in row 31 - hb of the word
+                            m ^= 1u << hb;
+                            const double* p = wbase + hb;
 #pragma unroll
                             for (int b = 0; b < BMAX; ++b)
-                                if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], p[b * P]);
+                                if (BEXACT || b < B) {
+                                    acc[b] = __dadd_rn(acc[b], p[b * P]);
+                                    acc2[b] = __dadd_rn(acc2[b], p[b * P + 32]);
+                                }
                         } while (m);
-                    } else {                                   // rare: a bin of this word holds several spikes
+                    } else {                                   // rare: some bin of these words holds several spikes
+                        const uint32_t x = __shfl_sync(0xffffffffu, mx, j);
                         do {
-                            const int pos = __clz(m);
-                            const uint32_t bit = 0x80000000u >> pos;
-                            m &= ~bit;
-                            const double* p = wbase - pos;
-                            const double dc = (x & bit) ? (double)sCnt[c * rows + rb + pos] : 1.0;
+                            const int hb = 31 - __clz(m);
+                            m ^= 1u << hb;
+                            const double* p = wbase + hb;
+                            const double dc = (x >> hb) & 1u ? (double)sCnt[c * rows + ((wb + 31 - j) << 5) + 31 - hb] : 1.0;
 #pragma unroll
                             for (int b = 0; b < BMAX; ++b)
-                                if (BEXACT || b < B) acc[b] = __dadd_rn(acc[b], __dmul_rn(dc, p[b * P]));
+                                if (BEXACT || b < B) {
+                                    acc[b] = __dadd_rn(acc[b], __dmul_rn(dc, p[b * P]));
+                                    acc2[b] = __dadd_rn(acc2[b], __dmul_rn(dc, p[b * P + 32]));
+                                }
                         } while (m);
                     }
                 }
             }
-            XT* o = sOut + ((grp << 5) + lane) * ostride + c * B;
+            XT* o = sOut + ((grp << 6) + lane) * ostride + c * B;
 #pragma unroll
             for (int b = 0; b < BMAX; ++b)
-                if (BEXACT || b < B) o[b] = (XT)acc[b];
+                if (BEXACT || b < B) { o[b] = (XT)acc[b]; o[32 * ostride + b] = (XT)acc2[b]; }
         }
         __syncthreads();
         if (tid == 0) *sNext = 0;
@@ -269,12 +277,12 @@ static int launch_filter_r(const uint8_t* dS, int64_t T, int N, int halo, const 
                            const FilterOut& out, cudaStream_t stream)
 {
     // the largest tile with two resident blocks per SM, else the largest that fits at all
-    const int cand[][2] = {{512, 32}, {256, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {32, 4}};
+    const int cand[][2] = {{512, 32}, {256, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {64, 4}, {64, 2}, {64, 1}};
     FiltLayout L{};
     bool found = false;
     for (size_t limit : {(size_t)113 * 1024, (size_t)227 * 1024}) {
         for (auto& c : cand) {
-            L = filt_layout(R, B, BMAX, RP ? RP : R + kZ + 32, c[0], std::min(c[1], N), sizeof(XT));
+            L = filt_layout(R, B, BMAX, RP ? RP : R + kZ + 64, c[0], std::min(c[1], N), sizeof(XT));
             if (L.total <= limit) { found = true; break; }
         }
         if (found) break;
@@ -296,7 +304,7 @@ template <typename XT, int BMAX, bool BEXACT, bool WX, bool WP>
 static int launch_filter_v(const uint8_t* dS, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
                            const FilterOut& out, cudaStream_t stream)
 {
-    if (R + kZ + 32 <= 320) return launch_filter_r<XT, BMAX, BEXACT, WX, WP, 320>(dS, T, N, halo, d_ibasis, R, B, out, stream);
+    if (R + kZ + 64 <= 360) return launch_filter_r<XT, BMAX, BEXACT, WX, WP, 360>(dS, T, N, halo, d_ibasis, R, B, out, stream);
     return launch_filter_r<XT, BMAX, BEXACT, WX, WP, 0>(dS, T, N, halo, d_ibasis, R, B, out, stream);
 }
 
