@@ -48,6 +48,11 @@ WORKLOADS = {
     "c5-shard": dict(N=4096, T=131_072, B=5, x_dtype="planes",
                      desc="N=4096 B=5, T=2^17 bins per GPU: time shard of the C5 population (ll+grad, 671 MB all-reduce per step)"),
 }
+# from-spikes K2: spikes-only datasets, operand planes produced by K1 inside every evaluation (never resident)
+WORKLOADS["c2-from-spikes"] = dict(WORKLOADS["c2"], x_dtype="none", desc="C2 evaluated from the spike trains (no X resident): standard_glm N=27 T=1e6 bins B=5")
+WORKLOADS["c4-neuron-shard"] = dict(N=1024, T=250_000, B=10, x_dtype="none",
+                                    desc="N=1024 B=10, T=2.5e5 bins, all presynaptic spike trains on the GPU, its share of the postsynaptic "
+                                         "neurons evaluated from the spikes (C4's split by postsynaptic neuron; C4 proper is T=4e6)")
 METRIC = "GLM ll+grad evals/sec"
 UNIT = "evals/s"
 
@@ -514,6 +519,81 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
     return line
 
 
+def fromspikes_record(args, wl, pg, torch, dist, timer, world, rank, local_rank, shard_of=1):
+    """ll + gradient from the spike trains (x_dtype="none"): every evaluation runs K1 into chunk-sized operand planes and
+    the tensor-core kernels on them; nothing but the spikes is resident.  The rank evaluates the postsynaptic neurons
+    neuron_shard(N, shard_of or world, rank) -- with several GPUs that is north_star's split of C4 by postsynaptic neuron:
+    the same recording on every GPU, no collective inside an evaluation (strong scaling over neurons)."""
+    from theano_pyglm_b200.utils.parallel_util import neuron_shard
+    N, T, B = wl["N"], wl["T"], wl["B"]
+    NB = N * B
+    dev, stream = timer.dev, timer.stream
+    parts = world if world > 1 else shard_of
+    n_lo, n_hi = neuron_shard(N, parts, rank if world > 1 else 0)
+    nc = n_hi - n_lo
+    inp = make_inputs(wl, seed=1234)                          # the same recording on every rank
+    ds = pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank, x_dtype="none")
+    d_bias = torch.from_numpy(inp["bias"]).to(dev)
+    d_w = torch.from_numpy(inp["w"]).to(dev)
+    d_out = torch.zeros(nc * (2 + NB), dtype=torch.float64, device=dev)
+    step = lambda: ds.ll_grad_dev(d_bias.data_ptr(), d_w.data_ptr(), 0, 0, "explinear", n_lo, n_hi, "auto", d_out[:nc].data_ptr(),
+                                  d_out[nc:2 * nc].data_ptr(), d_out[2 * nc:].data_ptr(), stream.cuda_stream)
+    for _ in range(2):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    steps = max(2, min(args.steps, 5))
+    ms, blocks = timer.blocks(step, steps, 0.3)
+    ms /= steps
+    clocks = sampler.stop() if rank == 0 else None
+    # the host-buffer call for the same neurons (parameters up, ll / gradients down): e2e
+    ms_e2e = None
+    if world == 1:
+        call = lambda: ds.ll_grad(inp["bias"], inp["w"], n_lo=n_lo, n_hi=n_hi)
+        for _ in range(2):
+            call()
+        ms_e2e = wall_blocks(call, 2, torch.cuda.synchronize, 0.2)[0] / 2
+    if not bool(torch.isfinite(d_out[:nc]).all()):
+        raise SystemExit("non-finite log-likelihood in the from-spikes run")
+    rd, wr = ds.filter_bytes()
+    ds.close()
+    if rank != 0:
+        return None
+    gemm = NB > 160
+    tpeak, tsrc = load_tensor_peak()
+    hpeak, hsrc = load_peaks()
+    alg_flops = 4.0 * T * nc * N * B
+    rec = {"metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": world, "steps": steps, "ms_per_step": ms,
+           "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+           "dtype": "f16x2-split/f32-acc/f64-sum", "data": "synthetic", "config": workload_config(wl), "clocks": clocks,
+           "details": {"path": "from-spikes: K1 -> chunk planes -> " + ("tcgen05 GEMM kernels" if gemm else "tcgen05 fused kernel"),
+                       "neurons_per_gpu": nc, "resident_bytes_per_gpu": int(inp["S"].nbytes),
+                       "x_bytes_never_materialised": T * NB * 4,
+                       "sharding": ("by postsynaptic neuron: %d of %d columns per GPU, the whole recording on every GPU, no collective "
+                                    "inside an evaluation" % (nc, N)) if parts > 1 else "single GPU, all neurons",
+                       "producer_bytes_per_eval": rd + wr, "blocks": len(blocks)},
+           "gpu_launches": steps * 8}
+    if ms_e2e is not None:
+        rec["e2e"] = {"value": 1e3 / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": (N + N * NB) * 8, "d2h_bytes_per_step": nc * (2 + NB) * 8,
+                      "call": "pyglm_b200_ll_grad (numpy in / out) on the spikes-only dataset"}
+    if gemm:
+        rec["roofline"] = {"bound": "tensor", "achieved": alg_flops / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                           "frac": alg_flops / (ms * 1e-3) / 1e12 / tpeak, "traffic": None,
+                           "kernel": "filter_kernel+tc_gemm_fwd_kernel+tc_gemm_bwd_kernel", "peak_source": tsrc, "kernel_ms": ms,
+                           "algorithmic_flops": alg_flops, "executed_over_algorithmic": 3.0,
+                           "note": "whole evaluation including the operand producer (K1), which writes and the GEMMs re-read "
+                                   "%.1f GB of planes per evaluation through the chunk buffers" % (wr / 1e9)}
+    else:
+        alg = rd + 16 * N * NB                                 # the spikes once: the only algorithmic HBM traffic left
+        rec["roofline"] = {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hpeak, "unit": "GB/s",
+                           "frac": alg / (ms * 1e-3) / 1e9 / hpeak, "traffic": None, "kernel": "filter_kernel+tc_fused_kernel",
+                           "peak_source": hsrc, "kernel_ms": ms, "algorithmic_bytes": alg,
+                           "note": "bound by the producer's gather (shared-memory operand fetch of the FP64 sums), not by HBM: "
+                                   "DESIGN.md section 4, K1"}
+    return rec
+
+
 def run_scale_extras(args, pg, torch, dist, timer, world, rank, local_rank):
     """Sub-records of the multi-GPU line: the C5 population time-sharded with its 671 MB all-reduce, and the collapsed
     Gibbs sweep of C3 partitioned by postsynaptic neuron (north_star's two splits).  Every rank takes part; rank 0
@@ -524,7 +604,8 @@ def run_scale_extras(args, pg, torch, dist, timer, world, rank, local_rank):
     a5.steps, a5.warmup = min(args.steps, 4), 2
     jobs = [("scale_c5", lambda: llgrad_record(a5, WORKLOADS["c5-shard"], "c5-shard", pg, torch, dist, timer, world, rank,
                                                local_rank, None, "nccl all_reduce (671 MB per step)", 0.0, 0.0)),
-            ("scale_gibbs", lambda: gibbs_sharded_record(args, WORKLOADS["c3-gibbs"], pg, torch, dist, timer, world, rank, local_rank))]
+            ("scale_gibbs", lambda: gibbs_sharded_record(args, WORKLOADS["c3-gibbs"], pg, torch, dist, timer, world, rank, local_rank)),
+            ("scale_c4_neuron", lambda: fromspikes_record(args, WORKLOADS["c4-neuron-shard"], pg, torch, dist, timer, world, rank, local_rank))]
     for name, job in jobs:
         t0 = time.perf_counter()
         ok = torch.ones(1, device=timer.dev)
@@ -672,7 +753,10 @@ def run_extras(args, pg, torch, dist, timer, local_rank):
                                          "none (single GPU)", 0.3, 0.0 if args.no_cpu else 6.0)),
             ("c3-gibbs", lambda: gibbs_record(args, WORKLOADS["c3-gibbs"], "c3-gibbs", 0.3)),
             ("c4-shard", lambda: llgrad_record(args, WORKLOADS["c4-shard"], "c4-shard", pg, torch, dist, timer, 1, 0, local_rank,
-                                               None, "none (single GPU)", 0.3, 0.0 if args.no_cpu else 6.0))]
+                                               None, "none (single GPU)", 0.3, 0.0 if args.no_cpu else 6.0)),
+            ("c2-from-spikes", lambda: fromspikes_record(args, WORKLOADS["c2-from-spikes"], pg, torch, dist, timer, 1, 0, local_rank)),
+            ("c4-neuron-shard", lambda: fromspikes_record(args, WORKLOADS["c4-neuron-shard"], pg, torch, dist, timer, 1, 0, local_rank,
+                                                          shard_of=8))]
     for name, job in jobs:
         t0 = time.perf_counter()
         try:

@@ -238,6 +238,53 @@ def test_planes_only_dataset(eng, T, N, B, monkeypatch):
         ds.close()
 
 
+@pytest.mark.parametrize("nlin", [orc.NLIN_SOFTPLUS, orc.NLIN_EXP])
+@pytest.mark.parametrize("T,N,B,chunk", [(3000, 27, 5, None), (3000, 27, 5, "1024"), (2500, 70, 5, "640"),
+                                         (1500, 9, 10, "512"), (700, 40, 10, "256")])
+def test_ll_grad_from_spikes_equals_resident_planes(eng, T, N, B, chunk, nlin, monkeypatch):
+    """From-spikes K2 (x_dtype="none"): every evaluation expands the spikes into chunk-sized operand planes (K1 with the
+    dataset's analytic scales) and runs the tensor-core kernels chunk by chunk.  One chunk: bit-identical to the resident
+    planes.  Several chunks: only the order of the final FP64 additions differs (1e-12), and the oracle bounds hold.
+    Covers the fused kernel (135 / 90 features) and the GEMM path (350 / 400 features), sub-ranges of neurons (the
+    neuron-sharded use), and a time shard with a left halo."""
+    p = make_problem(T, N, B, network=True, seed=77)
+    if nlin == orc.NLIN_EXP:
+        p['bias'] = p['bias'] - 17.0
+    _, ll, gb, gw = oracle_all(p, nlin)
+    res = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="planes")
+    ref = res.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="tc")
+    lo, hi = N // 3, N - 2
+    ref_sub = res.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, path="tc", n_lo=lo, n_hi=hi)
+    res.close()
+    if chunk:
+        monkeypatch.setenv("PYGLM_STREAM_CHUNK", chunk)
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="none")
+    for rep in range(3):                                   # the third call replays the captured CUDA graph
+        out = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)
+        for o, r in zip(out, ref):
+            if chunk is None:
+                assert np.array_equal(o, r)
+            else:
+                assert np.max(np.abs(o - r)) <= 1e-12 * max(1.0, np.max(np.abs(r)))
+    assert np.max(np.abs(out[0] - ll) / np.maximum(np.abs(ll), 1e-3)) < LL_RTOL * max(1.0, (2000.0 / T) ** 0.5)
+    assert rel_err(out[1], gb) < GRAD_RTOL and rel_err(out[2], gw) < GRAD_RTOL
+    sub = ds.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin, n_lo=lo, n_hi=hi)
+    for o, r in zip(sub, ref_sub):
+        assert np.max(np.abs(o - r)) <= 1e-12 * max(1.0, np.max(np.abs(r)))
+    assert np.allclose(ds.ll(p['bias'], p['w'], p['A'], p['W'], nlin=nlin), out[0], rtol=1e-13)
+    ds.close()
+    # a time shard with its left context: rows [cut, T) of the recording
+    cut, R = T // 2 + 3, p['ibasis'].shape[0]
+    halo = min(R, cut)
+    a = eng.Dataset(p['S'][cut - halo:], p['dt'], p['ibasis'], halo=halo, x_dtype="planes")
+    b = eng.Dataset(p['S'][cut - halo:], p['dt'], p['ibasis'], halo=halo, x_dtype="none")
+    ra = a.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)
+    rb = b.ll_grad(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)
+    for o, r in zip(rb, ra):
+        assert np.max(np.abs(o - r)) <= 1e-12 * max(1.0, np.max(np.abs(r)))
+    a.close(); b.close()
+
+
 def test_ll_grad_null_network_is_complete_graph(eng):
     p = make_problem(2000, 6, 5)
     _, ll, gb, gw = oracle_all(p, orc.NLIN_SOFTPLUS)
@@ -371,7 +418,7 @@ def test_gibbs_from_spikes_equals_the_filtered_spike_train_form(eng, nlin):
         ds_x = eng.Dataset(S, p['dt'], p['ibasis'], halo=halo, x_dtype="f64")
         ds_s = eng.Dataset(S, p['dt'], p['ibasis'], halo=halo, x_dtype="none")
         with pytest.raises(eng.EngineError):
-            ds_s.ll(p['bias'], p['w'], p['A'], p['W'])                 # spikes-only: no likelihood path
+            ds_s.ll(p['bias'], p['w'], p['A'], p['W'], path="fp64")    # spikes-only: no filtered spike train to read
         for ds in (ds_x, ds_s):
             ds.gibbs_begin(p['bias'], p['w'], p['A'], p['W'], nlin=nlin)
         for rnd in range(3):

@@ -147,7 +147,7 @@ def test_neuron_sharded_gibbs_splices_to_one_state(engine_lib):
         assert np.all(np.diag(l0['net']['graph']['A']) == 1)         # self edges stay (p_A = 1 - 1e-8 on the diagonal)
 
 
-def _map_worker(rank, world, port, q):
+def _map_worker(rank, world, port, q, x_dtype=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -158,7 +158,7 @@ def _map_worker(rank, world, port, q):
         from theano_pyglm_b200.utils.parallel_util import neuron_shard
         N = 5
         model = make_model('standard_glm', N=N, dt=0.001)
-        popn = Population(model)
+        popn = Population(model, x_dtype=x_dtype)
         rng = np.random.default_rng(11)                              # same data on every rank
         S = (rng.random((8000, N)) < 0.03).astype(float)
         popn.add_data({'S': S, 'N': N, 'dt': 0.001, 'T': 8.0, 'stim': None, 'dt_stim': 0.1})
@@ -179,14 +179,16 @@ def _map_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_neuron_sharded_map_matches_the_serial_coordinate_descent(engine_lib):
+@pytest.mark.parametrize("x_dtype", [None, "none"])
+def test_neuron_sharded_map_matches_the_serial_coordinate_descent(engine_lib, x_dtype):
     """parallel_coord_descent (parallel_coord_descent.py:57-157): two ranks fit their own neurons' GLMs on the engine,
     all-gather the fitted rows and all-reduce the log posterior; the result is the serial coord_descent's, because the
-    per-neuron problems are independent given the (constant) network."""
+    per-neuron problems are independent given the (constant) network.  x_dtype="none": every rank holds the spike trains
+    only and evaluates its neurons from the spikes (from-spikes K2) -- the reference's layout, each engine with the full data."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_map_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_map_worker, args=(r, world, port, q, x_dtype)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = {}

@@ -211,7 +211,9 @@ int pyglm_b200_dataset_create_stim(const uint8_t* S, int64_t T, int32_t halo, in
     CK(cudaMemcpyAsync(ds->ibasis.p, ibasis, (size_t)R * B * sizeof(double), cudaMemcpyHostToDevice, ds->stream));
     CK(cudaMemsetAsync(ds->X.p, 0, ds->X.n, ds->stream));
     if (x_dtype == PYGLM_B200_X_NONE) {
-        // spikes only: nothing to filter (the Gibbs entry points gather their currents from the spikes)
+        // spikes only: nothing resident to filter.  The Gibbs entry points gather their currents from the spikes; ll / gradient
+        // evaluations expand the spikes into the operand planes chunk by chunk (from-spikes K2, llgrad_tc.cu)
+        if (T > 0 && (rc = tc_prepare_streamed(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, ds->stream))) return fail(rc);
     } else if (planes_only) {
         if (T > 0 && (rc = tc_build_planes_direct(ds->tc, ds->S.p, T, N, halo, ds->ibasis.p, R, B, nullptr, 0, ds->stream))) return fail(rc);
     } else {
@@ -348,7 +350,7 @@ int pyglm_b200_dataset_filter_bytes(const pyglm_b200_dataset* ds, int64_t* bytes
 // ------------------------------------------------------------------------------------
 static int resolve_path(const pyglm_b200_dataset* ds, int path, bool need_aux)
 {
-    if (ds->x_dtype == PYGLM_B200_X_NONE) return -1;
+    if (ds->x_dtype == PYGLM_B200_X_NONE) return (path != PYGLM_B200_PATH_FP64 && !need_aux && ds->tc.streamed) ? PYGLM_B200_PATH_TC : -1;
     const bool planes_only = ds->x_dtype == PYGLM_B200_X_PLANES;
     if (path == PYGLM_B200_PATH_FP64) return planes_only ? -1 : PYGLM_B200_PATH_FP64;
     const bool tc_ok = (planes_only || tc_supported(ds->T, ds->N, ds->B, ds->x_dtype)) && !need_aux;
@@ -383,7 +385,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
     }
     if (use == PYGLM_B200_PATH_TC) {
         TcArgs t{};
-        t.X = ds->x_dtype == PYGLM_B200_X_PLANES ? nullptr : (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
+        t.X = (ds->x_dtype == PYGLM_B200_X_PLANES || ds->x_dtype == PYGLM_B200_X_NONE) ? nullptr : (const float*)ds->X.p; t.ldx = ds->ldx; t.S = ds->S.p; t.T = ds->T; t.N = ds->N; t.halo = ds->halo;
         t.B = ds->B; t.F = ds->F; t.ibasis = ds->ibasis.p; t.R = ds->R; t.dt = ds->dt; t.nlin = nlin; t.n_lo = n_lo; t.ncols = ncols;
         t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
         t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
@@ -393,7 +395,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
             PYGLM_CUDA(cudaMemsetAsync(ds->tc.colflag + n_lo, 0, (size_t)ncols * sizeof(unsigned), stream));
             t.flags = ds->tc.colflag;
         }
-        return launch_tc_ll_grad(t, ds->tc, stream);
+        return ds->tc.streamed ? launch_tc_ll_grad_streamed(t, ds->tc, stream) : launch_tc_ll_grad(t, ds->tc, stream);
     }
 
     const int Np = (int)round_up(ncols, 32);
@@ -538,7 +540,8 @@ int pyglm_b200_ll_grad(pyglm_b200_dataset* ds,
     // PATH_AUTO with the exp nonlinearity on the tensor-core path: the epilogue flags every column whose activation
     // leaves the range in which FP32 e^x holds the tolerance; those columns are re-evaluated on the FP64 path below
     const bool heal = path == PYGLM_B200_PATH_AUTO && nlin == PYGLM_B200_NLIN_EXP && ds->T > 0 &&
-                      ds->x_dtype != PYGLM_B200_X_PLANES && resolve_path(ds, path, false) == PYGLM_B200_PATH_TC;
+                      ds->x_dtype != PYGLM_B200_X_PLANES && ds->x_dtype != PYGLM_B200_X_NONE &&
+                      resolve_path(ds, path, false) == PYGLM_B200_PATH_TC;
     if (heal && !h.flags) {
         PYGLM_CUDA(cudaMallocHost(&h.flags, N * sizeof(unsigned)));
         memset(h.flags, 0, N * sizeof(unsigned));

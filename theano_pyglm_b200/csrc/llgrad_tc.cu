@@ -70,6 +70,7 @@ constexpr int kFlushTiles = 8;              // TMEM gradient accumulators are fo
 void TcWorkspace::release()
 {
     cudaFree(Sp); Sp = nullptr;
+    cudaFree(acc); acc = nullptr; acc_elems = 0; streamed = false; chunk_rows = 0; map_rows = 0;
     cudaFree(colflag); colflag = nullptr;
     cudaFree(X1); cudaFree(X2); cudaFree(sx); cudaFree(colmax); cudaFree(Mp); cudaFree(colpar); cudaFree(part);
     X1 = X2 = nullptr; sx = nullptr; colmax = nullptr; Mp = nullptr; colpar = nullptr; part = nullptr;
@@ -1406,14 +1407,37 @@ int tc_make_map_2d(void* map_out, const void* base, int64_t dim0, int64_t dim1, 
     return PYGLM_B200_OK;
 }
 
-// allocate everything the tensor-core path keeps per dataset (planes, scales, padded spikes, maps)
-static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, int NB, cudaStream_t stream)
+// (re)encode the twelve tensor maps over the X planes for `rows` valid rows (rows beyond read as zero)
+static int tc_encode_maps(TcWorkspace& ws, int64_t rows)
 {
+    CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
+    int rc;
+    if ((rc = tc_make_map_2d(&maps[0], ws.X1, ws.ldp, rows, ws.ldp, kChunkF, kTileT))) return rc;
+    if ((rc = tc_make_map_2d(&maps[1], ws.X2, ws.ldp, rows, ws.ldp, kChunkF, kTileT))) return rc;
+    if ((rc = tc_make_map_2d(&maps[2], ws.X1, ws.ldp, rows, ws.ldp, 64, kTileT, true))) return rc;      // wide chunks, 128B swizzle
+    if ((rc = tc_make_map_2d(&maps[3], ws.X2, ws.ldp, rows, ws.ldp, 64, kTileT, true))) return rc;
+    if ((rc = tc_make_map_2d(&maps[4], ws.X1, ws.ldp, rows, ws.ldp, 16, kTileT, 2))) return rc;         // 16-feature tail, 32B swizzle
+    if ((rc = tc_make_map_2d(&maps[5], ws.X2, ws.ldp, rows, ws.ldp, 16, kTileT, 2))) return rc;
+    for (int pl = 0; pl < 2; ++pl) {                      // the same three box shapes with 112-bin boxes (fused kernel V2)
+        const __half* base = pl ? ws.X2 : ws.X1;
+        if ((rc = tc_make_map_2d(&maps[6 + pl], base, ws.ldp, rows, ws.ldp, kChunkF, 112))) return rc;
+        if ((rc = tc_make_map_2d(&maps[8 + pl], base, ws.ldp, rows, ws.ldp, 64, 112, 1))) return rc;
+        if ((rc = tc_make_map_2d(&maps[10 + pl], base, ws.ldp, rows, ws.ldp, 16, 112, 2))) return rc;
+    }
+    ws.map_rows = rows;
+    return PYGLM_B200_OK;
+}
+
+// allocate everything the tensor-core path keeps per dataset (planes of `plane_rows` rows, scales, padded spikes, maps)
+static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, int NB, cudaStream_t stream,
+                        int64_t plane_rows = -1)
+{
+    if (plane_rows < 0) plane_rows = T;
     ws.ldp = round_up(NB, 8);
     int dev = 0;
     PYGLM_CUDA(cudaGetDevice(&dev));
     PYGLM_CUDA(cudaDeviceGetAttribute(&ws.num_sms, cudaDevAttrMultiProcessorCount, dev));
-    const size_t plane = (size_t)T * ws.ldp;
+    const size_t plane = (size_t)plane_rows * ws.ldp;
     note_allocation();
     PYGLM_CUDA(cudaMalloc(&ws.X1, plane * sizeof(__half)));
     PYGLM_CUDA(cudaMalloc(&ws.X2, plane * sizeof(__half)));
@@ -1429,21 +1453,7 @@ static int alloc_planes(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int
     PYGLM_CUDA(cudaMemcpy2DAsync(ws.Sp, ws.Np, S + (size_t)halo * N, N, N, T, cudaMemcpyDeviceToDevice, stream));
     ws.tmaps = malloc(12 * sizeof(CUtensorMap));
     if (!ws.tmaps) { set_error("host allocation failed"); return PYGLM_B200_ENOMEM; }
-    CUtensorMap* maps = static_cast<CUtensorMap*>(ws.tmaps);
-    int rc;
-    if ((rc = tc_make_map_2d(&maps[0], ws.X1, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
-    if ((rc = tc_make_map_2d(&maps[1], ws.X2, ws.ldp, T, ws.ldp, kChunkF, kTileT))) return rc;
-    if ((rc = tc_make_map_2d(&maps[2], ws.X1, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;      // wide chunks, 128B swizzle
-    if ((rc = tc_make_map_2d(&maps[3], ws.X2, ws.ldp, T, ws.ldp, 64, kTileT, true))) return rc;
-    if ((rc = tc_make_map_2d(&maps[4], ws.X1, ws.ldp, T, ws.ldp, 16, kTileT, 2))) return rc;         // 16-feature tail, 32B swizzle
-    if ((rc = tc_make_map_2d(&maps[5], ws.X2, ws.ldp, T, ws.ldp, 16, kTileT, 2))) return rc;
-    for (int pl = 0; pl < 2; ++pl) {                      // the same three box shapes with 112-bin boxes (fused kernel V2)
-        const __half* base = pl ? ws.X2 : ws.X1;
-        if ((rc = tc_make_map_2d(&maps[6 + pl], base, ws.ldp, T, ws.ldp, kChunkF, 112))) return rc;
-        if ((rc = tc_make_map_2d(&maps[8 + pl], base, ws.ldp, T, ws.ldp, 64, 112, 1))) return rc;
-        if ((rc = tc_make_map_2d(&maps[10 + pl], base, ws.ldp, T, ws.ldp, 16, 112, 2))) return rc;
-    }
-    return PYGLM_B200_OK;
+    return tc_encode_maps(ws, plane_rows);
 }
 
 // per-feature scales: analytic for the N*B spike-history features, from the data for F stimulus features (X resident)
@@ -1502,6 +1512,80 @@ int tc_build_planes_direct(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, 
     if ((rc = launch_filter(S, T, N, halo, d_ibasis, R, B, out, stream))) return rc;
     ws.planes_ready = true;
     return PYGLM_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// From-spikes evaluation (spikes-only datasets, PYGLM_B200_X_NONE): the operand planes are never resident.  Every
+// evaluation walks the recording in time chunks: K1 expands the chunk's spikes straight into the two chunk-sized plane
+// buffers (same analytic scales, so the planes are bit-identical to a resident dataset's), the regular tensor-core kernels
+// run on the chunk, and the chunk's ll / gradients are added into the outputs in chunk order (deterministic).  A rank
+// holding ALL presynaptic spike trains (N*T bytes) can thus evaluate any subset of postsynaptic neurons -- the reference's
+// own split (parallel_coord_descent.py:57-157, parallel_gibbs.py:162-168) at sizes whose X would not fit (C4: 164 GB).
+// ---------------------------------------------------------------------------------------------
+int tc_prepare_streamed(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                        cudaStream_t stream)
+{
+    const int NB = N * B;
+    const int64_t ldp = round_up(NB, 8);
+    int64_t chunk = std::max<int64_t>(4096, ((int64_t)2048 << 20) / (ldp * 4));                // ~2 GB of planes per chunk
+    if (const char* env = getenv("PYGLM_STREAM_CHUNK")) chunk = std::max<int64_t>(1, atoll(env));   // tests: several chunks
+    chunk = std::min(round_up(chunk, 128), round_up(T, 128));
+    int rc = alloc_planes(ws, S, T, N, halo, NB, stream, chunk);
+    if (rc) return rc;
+    if ((rc = tc_compute_scales(ws, S, T + halo, N, d_ibasis, R, B, nullptr, T, 0, 0, stream))) return rc;
+    ws.streamed = true;
+    ws.chunk_rows = chunk;
+    ws.planes_ready = true;                       // nothing to build lazily: the planes are produced per evaluation
+    return PYGLM_B200_OK;
+}
+
+__global__ void tc_accumulate_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
+int launch_tc_ll_grad_streamed(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
+{
+    if (a.T <= 0 || a.ncols <= 0) return PYGLM_B200_OK;
+    if (!ws.streamed || a.F != 0) { set_error("from-spikes evaluation needs a spikes-only dataset without stimulus features"); return PYGLM_B200_ESTATE; }
+    const int64_t NB = (int64_t)a.N * a.B;
+    const size_t nacc = (size_t)a.ncols * (NB + 2);
+    if (ws.acc_elems < nacc) {
+        cudaFree(ws.acc);
+        ws.acc = nullptr; ws.acc_elems = 0;
+        note_allocation();
+        PYGLM_CUDA(cudaMalloc(&ws.acc, nacc * sizeof(double)));
+        ws.acc_elems = nacc;
+    }
+    double* t_ll = ws.acc;
+    double* t_gb = ws.acc + a.ncols;
+    double* t_gw = ws.acc + 2 * (size_t)a.ncols;
+    PYGLM_CUDA(cudaMemsetAsync(a.out_ll, 0, a.ncols * sizeof(double), stream));
+    if (a.out_gb) PYGLM_CUDA(cudaMemsetAsync(a.out_gb, 0, a.ncols * sizeof(double), stream));
+    if (a.out_gw) PYGLM_CUDA(cudaMemsetAsync(a.out_gw, 0, (size_t)a.ncols * NB * sizeof(double), stream));
+    uint8_t* const Sp0 = ws.Sp;
+    int rc = PYGLM_B200_OK;
+    for (int64_t r0 = 0; r0 < a.T && rc == PYGLM_B200_OK; r0 += ws.chunk_rows) {
+        const int64_t nt = std::min(ws.chunk_rows, a.T - r0);
+        const int64_t h = std::min<int64_t>(a.R, a.halo + r0);                   // left context available for this chunk
+        FilterOut fo;
+        fo.X1 = ws.X1; fo.X2 = ws.X2; fo.ldp = ws.ldp; fo.sx = ws.sx;
+        if ((rc = launch_filter(a.S + (a.halo + r0 - h) * a.N, nt, a.N, (int)h, a.ibasis, a.R, a.B, fo, stream))) break;
+        if (ws.map_rows != nt && (rc = tc_encode_maps(ws, nt))) break;
+        TcArgs c = a;
+        c.X = nullptr; c.T = nt; c.S = a.S + r0 * a.N;
+        c.out_ll = t_ll; c.out_gb = a.out_gb ? t_gb : nullptr; c.out_gw = a.out_gw ? t_gw : nullptr;
+        ws.Sp = Sp0 + r0 * ws.Np;
+        rc = launch_tc_ll_grad(c, ws, stream);
+        ws.Sp = Sp0;
+        if (rc) break;
+        tc_accumulate_kernel<<<(unsigned)ceil_div(a.ncols, 256), 256, 0, stream>>>(a.out_ll, t_ll, a.ncols);
+        if (a.out_gb) tc_accumulate_kernel<<<(unsigned)ceil_div(a.ncols, 256), 256, 0, stream>>>(a.out_gb, t_gb, a.ncols);
+        if (a.out_gw) tc_accumulate_kernel<<<(unsigned)ceil_div((int64_t)a.ncols * NB, 256), 256, 0, stream>>>(a.out_gw, t_gw, (int64_t)a.ncols * NB);
+        PYGLM_CUDA(cudaGetLastError());
+    }
+    return rc;
 }
 
 template <int TAIL, int TILE>

@@ -18,6 +18,12 @@ struct TcWorkspace {
     int Np = 0;
     unsigned* colflag = nullptr;  // [N] range flags raised by the FP32 epilogues (exp nonlinearity, see kExpSafe)
     bool planes_ready = false;
+    // from-spikes evaluation (spikes-only datasets): X1 / X2 hold one time chunk, refilled by K1 in every evaluation
+    bool streamed = false;
+    int64_t chunk_rows = 0;       // rows of the chunk buffers
+    int64_t map_rows = 0;         // rows the tensor maps over X1 / X2 were encoded for
+    double* acc = nullptr;        // per-chunk ll / g_bias / g_w before they are added into the outputs
+    size_t acc_elems = 0;
     // per-call operands
     __half* Mp = nullptr;         // [2][32][Kp] split planes of the scaled weight matrix
     float* colpar = nullptr;      // [2][32]: 1/sm[n], bias[n]
@@ -46,6 +52,9 @@ bool tc_uses_fused_kernel(int64_t nfeat);
 int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 int tc_build_planes_direct(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,
                            int R, int B, float* X, int64_t ldx, cudaStream_t stream);
+int tc_prepare_streamed(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis, int R, int B,
+                        cudaStream_t stream);
+int launch_tc_ll_grad_streamed(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 int tc_make_map_2d(void* map, const void* base, int64_t dim0, int64_t dim1, int64_t pitch_elems, int box0, int box1,
                    int swizzle = 0);        // 0: SWIZZLE_64B, 1: SWIZZLE_128B, 2: SWIZZLE_32B
 int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
