@@ -58,13 +58,17 @@ extern "C" {
 #define PYGLM_B200_X_F32  0
 #define PYGLM_B200_X_F64  1
 /* planes only: keep just the FP16 split planes of X that the tensor-core path streams (4 bytes per
- * element); the FP64 path, firing_rate, get_fS and the Gibbs entry points are unavailable.  For
- * recordings whose FP32 X would not fit next to the planes (configs C4/C5 shards). */
+ * element, written directly by the filter kernel); the FP64 path, firing_rate and get_fS are unavailable
+ * (the Gibbs entry points gather their currents from the spikes).  For recordings whose FP32 X would not
+ * fit next to the planes (configs C4/C5 shards). */
 #define PYGLM_B200_X_PLANES 2
-/* spikes only: neither X nor its planes are built.  Only the Gibbs entry points are available; they gather the
- * presynaptic currents from the spike trains (one byte per bin instead of B filtered values), which is what lets one
- * GPU of a neuron-sharded run hold ALL presynaptic data of a population whose X would not fit (C4: 4 GB of spikes
- * against 164 GB of X).  Planes-only datasets run Gibbs the same way. */
+/* spikes only: neither X nor its planes are resident.  ll / gradient calls expand the spikes into the operand planes
+ * chunk by chunk inside every evaluation (utils/basis.py:201-236 fused in front of glm.py:33-52; results bit-identical
+ * to a planes-only dataset's up to the order of the last FP64 additions), and the Gibbs entry points gather the
+ * presynaptic currents from the spike trains (one byte per bin instead of B filtered values).  This is what lets one GPU
+ * of a neuron-sharded run -- the reference's own split, every engine with the whole data
+ * (parallel_coord_descent.py:57-157, parallel_gibbs.py:162-168) -- hold ALL presynaptic data of a population whose X
+ * would not fit (C4: 4 GB of spikes against 164 GB of X).  PATH_FP64, firing_rate and get_fS are unavailable. */
 #define PYGLM_B200_X_NONE 3
 
 /* arithmetic path for ll / gradient
