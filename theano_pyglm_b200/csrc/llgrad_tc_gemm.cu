@@ -25,6 +25,10 @@
 #include "llgrad_tc.cuh"
 #include "tc_common.cuh"
 
+#ifndef PYGLM_GEMM_EXPERIMENTS
+#define PYGLM_GEMM_EXPERIMENTS 0
+#endif
+
 namespace pyglm {
 
 constexpr int kGT = 128;                     // bins per tile (UMMA M of the forward, K block of the gradient)
@@ -610,8 +614,10 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
     // 64 KB stages.  0: the same with 32-feature chunks in 64-byte rows (SWIZZLE_64B), seven 32 KB stages -- its MMAs
     // fetch their operands half as efficiently (C3 forward: 2.20 ms against 1.91 ms).  1 / 2: the cluster experiments.
     int mode = 3;
+#if PYGLM_GEMM_EXPERIMENTS                                       // quarantined: build with -DPYGLM_GEMM_EXPERIMENTS=1 to select them
     if (const char* env = getenv("PYGLM_GEMM_MODE")) mode = atoi(env);
     if (mode < 0 || mode > 3) mode = 3;
+#endif
     const int chunkf = mode == 3 ? 64 : 32;                      // features per K chunk
     const int nkc = (int)ceil_div(NB, chunkf);
     const int Kp = nkc * chunkf;
@@ -669,7 +675,9 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
                                                 : tc_gemm_fwd_kernel<PYGLM_B200_NLIN_SOFTPLUS, 3>;
         PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
         kf<<<nctas, kGThreads, smem_f, stream>>>(mX1w, mX2w, mM1, mM2, f);
-    } else if (mode) {
+    }
+#if PYGLM_GEMM_EXPERIMENTS
+    else if (mode) {
         CUtensorMap mM1h, mM2h;                                   // 64-column boxes of the weight planes (mode 2)
         if ((rc = tc_make_map_2d(&mM1h, g.Mp, Kp, Npr, Kp, 32, kGN / 2))) return rc;
         if ((rc = tc_make_map_2d(&mM2h, g.Mp + (size_t)Npr * Kp, Kp, Npr, Kp, 32, kGN / 2))) return rc;
@@ -691,6 +699,7 @@ int launch_tc_gemm_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream
         PYGLM_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
         kf<<<nctas, kGThreads, smem_f, stream>>>(xmaps[0], xmaps[1], mM1, mM2, f);
     }
+#endif
     PYGLM_CUDA(cudaGetLastError());
     tc_gemm_final_ll_kernel<<<(unsigned)a.ncols, 256, 0, stream>>>(g.part, nctas, Npr, a.ncols, a.out_ll, a.out_gb);
     PYGLM_CUDA(cudaGetLastError());
