@@ -275,6 +275,15 @@ def wall_blocks(fn, steps, sync, min_total_s=0.5, max_blocks=400):
     return median_block(times), times
 
 
+def _traffic(kernel, workload_key):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel`, from the committed ncu capture (profiles/)."""
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if not os.path.exists(tpath):
+        return None
+    with open(tpath) as f:
+        return json.load(f).get(kernel, {}).get(workload_key)
+
+
 def llgrad_roofline(ds, wl, ms_kernel, path, workload_key):
     """roofline object of the ll+grad launch sequence: algorithmic bytes (HBM-bound fused kernel) or flops (GEMM path)."""
     N, T, B = wl["N"], wl["T"], wl["B"]
@@ -730,7 +739,7 @@ def filter_record(args, pg, torch, timer, local_rank):
                    "call": "pyglm_b200_dataset_create: upload of the uint8 spikes, K1, spike transpose; synchronous"},
            "gpu_launches": args.steps,
            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "filter_kernel",
+                        "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": _traffic("filter_kernel", "c2"), "kernel": "filter_kernel",
                         "peak_source": peak_src, "kernel_ms": ms, "algorithmic_bytes": alg}}
     if not args.no_cpu:
         from oracle import pyglm_oracle as orc
