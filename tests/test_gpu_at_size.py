@@ -76,3 +76,38 @@ def test_tensor_core_path_against_the_oracle_at_size(eng, name):
     assert mx_b < GRAD_RTOL and mx_w < GRAD_RTOL
     per_neuron = np.max(np.abs(ggot - gref), axis=1) / np.max(np.abs(gref), axis=1)
     assert np.max(per_neuron) < 1e-4 and el_b < 2e-4 and el_w < 2e-3, (name, float(np.max(per_neuron)), el_b, el_w)
+
+
+def test_filter_at_the_benchmark_size_is_bit_exact(eng):
+    """K1 on every bin of C2 (what bench.py's `k1-filter-c2` record times): the FP32 filtered spike train equals the
+    correctly rounded float64 causal sum of the oracle, element for element (1.35e8 values)."""
+    p = _inputs("c2_full")
+    ref = orc.convolve_with_basis_direct(p['S'], p['ibasis']).astype(np.float32)
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="f32")
+    got = ds.fS().astype(np.float32)
+    ds.close()
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name", ["c2_full", "c4_shape"])
+def test_from_spikes_evaluation_at_size(eng, name, monkeypatch):
+    """From-spikes K2 (spikes-only dataset, operand planes produced inside every evaluation) against resident planes at
+    C2 full size (one chunk: bit-identical) and at C4's population size for one GPU's share of the postsynaptic neurons
+    (several chunks: identical up to the order of the last FP64 additions)."""
+    T, N, B = CASES[name]
+    p = _inputs(name)
+    n_lo, n_hi = (0, N) if name == "c2_full" else (N // 8, N // 4)
+    args = (p['bias'], p['w'].reshape(N, -1), p['A'], p['W'])
+    res = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="planes")
+    ref = res.ll_grad(*args, nlin="explinear", n_lo=n_lo, n_hi=n_hi)
+    res.close()
+    if name != "c2_full":
+        monkeypatch.setenv("PYGLM_STREAM_CHUNK", "12800")
+    ds = eng.Dataset(p['S'], p['dt'], p['ibasis'], x_dtype="none")
+    out = ds.ll_grad(*args, nlin="explinear", n_lo=n_lo, n_hi=n_hi)
+    ds.close()
+    for o, r in zip(out, ref):
+        if name == "c2_full":
+            assert np.array_equal(o, r)
+        else:
+            assert np.max(np.abs(o - r)) <= 1e-12 * max(1.0, np.max(np.abs(r)))
