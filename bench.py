@@ -48,6 +48,10 @@ WORKLOADS = {
     "c5-shard": dict(N=4096, T=131_072, B=5, x_dtype="planes",
                      desc="N=4096 B=5, T=2^17 bins per GPU: time shard of the C5 population (ll+grad, 671 MB all-reduce per step)"),
 }
+# the same population with B = 10 basis functions ("C5 ... B=5 default; also report B=10"): 2^16 bins per GPU
+# (10.7 GB of planes), all-reduce of 1.34 GB per step
+WORKLOADS["c5-shard-b10"] = dict(N=4096, T=65_536, B=10, x_dtype="planes",
+                                 desc="N=4096 B=10, T=2^16 bins per GPU: time shard of the C5 population with B=10 (ll+grad, 1.34 GB all-reduce per step)")
 # from-spikes K2: spikes-only datasets, operand planes produced by K1 inside every evaluation (never resident)
 WORKLOADS["c2-from-spikes"] = dict(WORKLOADS["c2"], x_dtype="none", desc="C2 evaluated from the spike trains (no X resident): standard_glm N=27 T=1e6 bins B=5")
 WORKLOADS["c4-neuron-shard"] = dict(N=1024, T=250_000, B=10, x_dtype="none",
@@ -613,6 +617,8 @@ def run_scale_extras(args, pg, torch, dist, timer, world, rank, local_rank):
     a5.steps, a5.warmup = min(args.steps, 4), 2
     jobs = [("scale_c5", lambda: llgrad_record(a5, WORKLOADS["c5-shard"], "c5-shard", pg, torch, dist, timer, world, rank,
                                                local_rank, None, "nccl all_reduce (671 MB per step)", 0.0, 0.0)),
+            ("scale_c5_b10", lambda: llgrad_record(a5, WORKLOADS["c5-shard-b10"], "c5-shard-b10", pg, torch, dist, timer, world, rank,
+                                                   local_rank, None, "nccl all_reduce (1.34 GB per step)", 0.0, 0.0)),
             ("scale_gibbs", lambda: gibbs_sharded_record(args, WORKLOADS["c3-gibbs"], pg, torch, dist, timer, world, rank, local_rank)),
             ("scale_c4_neuron", lambda: fromspikes_record(args, WORKLOADS["c4-neuron-shard"], pg, torch, dist, timer, world, rank, local_rank))]
     for name, job in jobs:
