@@ -92,7 +92,7 @@ def test_peer_allreduce_and_time_sharded_ll_grad(world, engine_lib):
         assert rel_err(out[2 * N:], gw0.reshape(-1)) < 1e-5
 
 
-def _gibbs_worker(rank, world, port, q):
+def _gibbs_worker(rank, world, port, q, x_dtype=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -102,7 +102,7 @@ def _gibbs_worker(rank, world, port, q):
         N = 5
         model = make_model('sparse_weighted_model', N=N, dt=0.001)
         stabilize_sparsity(model)
-        popn = Population(model)
+        popn = Population(model, x_dtype=x_dtype)
         rng = np.random.default_rng(3)                               # same data on every rank
         S = (rng.random((6000, N)) < 0.03).astype(float)
         popn.add_data({'S': S, 'N': N, 'dt': 0.001, 'T': 6.0, 'stim': None, 'dt_stim': 0.1})
@@ -116,13 +116,16 @@ def _gibbs_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_neuron_sharded_gibbs_splices_to_one_state(engine_lib):
+@pytest.mark.parametrize("x_dtype", [None, "none"])
+def test_neuron_sharded_gibbs_splices_to_one_state(engine_lib, x_dtype):
     """parallel_gibbs_sample (parallel_gibbs.py:40-197): two ranks each resample their own columns on the
-    engine; after the all-gather splice both hold the same state, and every column was touched."""
+    engine; after the all-gather splice both hold the same state, and every column was touched.  x_dtype="none": the
+    ranks hold the spike trains only -- the HMC updates evaluate ll / gradients from the spikes (from-spikes K2) and the
+    collapsed A/W updates gather their currents from them (from-spikes K4)."""
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_gibbs_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_gibbs_worker, args=(r, world, port, q, x_dtype)) for r in range(world)]
     for pr in procs:
         pr.start()
     res = {}
