@@ -949,9 +949,9 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             constexpr uint32_t idesc_b64 = umma_idesc(128, 64, 1, 1);     // A: X MN-major, B: [r1|r2] MN-major
             constexpr uint32_t idesc_b32 = umma_idesc(128, 32, 1, 1);
             int slot = 0; uint32_t par = 0;
-            for (int j = 0; j < ntl; ++j) {
-                const int b = j % RB, gb = j & 1;
-                const uint32_t rph = (uint32_t)(j / RB) & 1u;
+            int b = 0; uint32_t rph = 0;                                               // b = j % RB, rph = (j / RB) & 1, kept as running counters
+            for (int j = 0; j < ntl; ++j, rph ^= (b + 1 == RB) ? 1u : 0u, b = (b + 1 == RB) ? 0 : b + 1) {
+                const int gb = j & 1;
                 const int sA = slot;
                 const int sB = (slot + 1 == NS) ? 0 : slot + 1;
                 const uint32_t parB = (slot + 1 == NS) ? par ^ 1 : par;
@@ -1098,9 +1098,10 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             if (lane == 0) mbar_arrive(bar_fwd_empty);
         }
 #endif
-        for (int it = 0; it < ntl; ++it) {
-            const int b = it % RB;
-            const uint32_t rph = (uint32_t)(it / RB) & 1u;
+        // b = it % RB, rph = (it / RB) & 1 and the flush period as running counters: an integer division by a kernel argument
+        // costs ~30 instructions, and this loop is instruction-issue-bound
+        int b = 0, fcnt = 0; uint32_t rph = 0;
+        for (int it = 0; it < ntl; ++it, rph ^= (b + 1 == RB) ? 1u : 0u, b = (b + 1 == RB) ? 0 : b + 1) {
             PYGLM_WSTAMP(0);
             const int64_t t = (first + (int64_t)it * step) * TILE + row;
             const float lv = (t < a.T && row < TILE) ? 1.0f : 0.0f;
@@ -1233,7 +1234,8 @@ tc_fused2_kernel(const __grid_constant__ CUtensorMap tmapW1, const __grid_consta
             if (tr) a.trace[(2 * 32 + it) * 4 + 2] = clock64();
             if (V2TRACE && blockIdx.x == 0 && lane == 0 && it < 32) a.trace[384 + warp * 32 + it] = clock64();
 
-            if (((it + 1) % F) == 0 || it == ntl - 1) {
+            if (++fcnt == F || it == ntl - 1) {
+                fcnt = 0;
                 ll_acc += (double)warp_column_sums<kColsPerWarp>(pll, lane);
                 gb_acc += (double)warp_column_sums<kColsPerWarp>(pgb, lane);
 #pragma unroll
