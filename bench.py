@@ -54,6 +54,9 @@ WORKLOADS["c5-shard-b10"] = dict(N=4096, T=65_536, B=10, x_dtype="planes",
                                  desc="N=4096 B=10, T=2^16 bins per GPU: time shard of the C5 population with B=10 (ll+grad, 1.34 GB all-reduce per step)")
 # from-spikes K2: spikes-only datasets, operand planes produced by K1 inside every evaluation (never resident)
 WORKLOADS["c2-from-spikes"] = dict(WORKLOADS["c2"], x_dtype="none", desc="C2 evaluated from the spike trains (no X resident): standard_glm N=27 T=1e6 bins B=5")
+WORKLOADS["c4-shard-from-spikes"] = dict(WORKLOADS["c4-shard"], x_dtype="none",
+                                         desc="the C4 time shard (N=1024 B=10, T=5e5 bins) evaluated from the spike trains: 0.5 GB of spikes "
+                                              "and 2 GB of chunk buffers resident instead of 20.5 GB of planes")
 WORKLOADS["c4-neuron-shard"] = dict(N=1024, T=250_000, B=10, x_dtype="none",
                                     desc="N=1024 B=10, T=2.5e5 bins, all presynaptic spike trains on the GPU, its share of the postsynaptic "
                                          "neurons evaluated from the spikes (C4's split by postsynaptic neuron; C4 proper is T=4e6)")
@@ -501,7 +504,8 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": info.get("dtype", "f64"), "data": "synthetic",
             "config": workload_config(wl),
-            "details": {"path": info.get("name", path), "x_bytes_per_gpu": T * ds.ldx * 4,
+            "details": {"path": info.get("name", path) + (" (from the spikes: K1 per time chunk inside every evaluation)" if wl.get("x_dtype") == "none" else ""),
+                        "x_bytes_per_gpu": T * ds.ldx * 4, "x_resident": wl.get("x_dtype") != "none",
                         "sharding": "time-sharded: one T-bin sequence per GPU, allreduce(sum) of ll/grad partials"
                         if world > 1 else "single GPU",
                         "collective": collective, "ingest_s_incl_filter_and_planes": ingest_s,
@@ -769,6 +773,8 @@ def run_extras(args, pg, torch, dist, timer, local_rank):
             ("c3-gibbs", lambda: gibbs_record(args, WORKLOADS["c3-gibbs"], "c3-gibbs", 0.3)),
             ("c4-shard", lambda: llgrad_record(args, WORKLOADS["c4-shard"], "c4-shard", pg, torch, dist, timer, 1, 0, local_rank,
                                                None, "none (single GPU)", 0.3, 0.0 if args.no_cpu else 6.0)),
+            ("c4-shard-from-spikes", lambda: llgrad_record(args, WORKLOADS["c4-shard-from-spikes"], "c4-shard-from-spikes", pg, torch, dist,
+                                                           timer, 1, 0, local_rank, None, "none (single GPU)", 0.3, 0.0)),
             ("c2-from-spikes", lambda: fromspikes_record(args, WORKLOADS["c2-from-spikes"], pg, torch, dist, timer, 1, 0, local_rank)),
             ("c4-neuron-shard", lambda: fromspikes_record(args, WORKLOADS["c4-neuron-shard"], pg, torch, dist, timer, 1, 0, local_rank,
                                                           shard_of=8))]
