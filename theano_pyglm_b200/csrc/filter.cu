@@ -20,6 +20,8 @@
 //  * Copy-out.  Results leave through a padded shared-memory tile so global stores are full rows:
 //    the full-precision X and / or -- in the same pass -- the FP16 split planes of the tensor-core
 //    path (X * sx = X1 + X2 * 2^-11 with the analytic per-feature scales of tc_spike_scales).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -280,8 +282,11 @@ static int launch_filter_r(const uint8_t* dS, int64_t T, int N, int halo, const 
     const int cand[][2] = {{512, 32}, {256, 32}, {128, 32}, {64, 32}, {64, 16}, {64, 8}, {64, 4}, {64, 2}, {64, 1}};
     FiltLayout L{};
     bool found = false;
+    int tt_max = 1 << 30;
+    if (const char* env = getenv("PYGLM_FILT_TT")) tt_max = std::max(64, atoi(env));       // experiments: cap the tile length
     for (size_t limit : {(size_t)113 * 1024, (size_t)227 * 1024}) {
         for (auto& c : cand) {
+            if (c[0] > tt_max) continue;
             L = filt_layout(R, B, BMAX, RP ? RP : R + kZ + 64, c[0], std::min(c[1], N), sizeof(XT));
             if (L.total <= limit) { found = true; break; }
         }
