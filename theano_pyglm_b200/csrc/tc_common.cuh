@@ -43,6 +43,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the hardware parks the thread until the phase completes or the time is up, so a
+// waiting warp issues nothing in between (a bare poll loop competes with its scheduler's other warps for issue slots)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
 // non-blocking probe (try_wait may suspend the thread for a while; a poller must not)
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
 {
@@ -55,12 +67,15 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
+// (The watchdog counts polls instead of reading the clock: the 64-bit clock arithmetic of every poll was 11 % of all
+// instructions the fused kernel's epilogue warps issued -- slots their schedulers' other warps needed.)
+constexpr unsigned kMbarMaxPolls = 1u << 25;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+    unsigned polls = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if (++polls > kMbarMaxPolls) __trap();
     }
 }
 // Wait of a single-thread role warp (MMA issuer): the warp scheduler favours the highest warp ids, and the role warps
@@ -72,10 +87,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait_role(uint64_t* bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    unsigned polls = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
         if (PYGLM_TC_ROLE_NAP) __nanosleep(PYGLM_TC_ROLE_NAP);
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++polls > kMbarMaxPolls) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1)
@@ -175,10 +190,10 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns)
 {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
+    unsigned polls = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
         if (ns) __nanosleep(ns);
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++polls > kMbarMaxPolls) __trap();
     }
 }
 
