@@ -69,7 +69,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 // (The watchdog counts polls instead of reading the clock: the 64-bit clock arithmetic of every poll was 11 % of all
 // instructions the fused kernel's epilogue warps issued -- slots their schedulers' other warps needed.)
-constexpr unsigned kMbarMaxPolls = 1u << 25;
+constexpr unsigned kMbarMaxPolls = 1u << 20;   // x up to 20 us per parked poll: a protocol bug traps within ~20 s
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     if (mbar_try_wait(bar, parity)) return;
