@@ -368,7 +368,7 @@ def run_ours(args, wl):
             if ok.item() < 1:
                 comm = None
             else:
-                collective = "one-shot all-reduce over NVLink peer memory (allreduce_kernel)"
+                collective = "sum over ranks folded into the evaluation's final reduction: one-shot exchange over NVLink peer memory (tc_final2_allreduce_kernel)"
 
     stream = torch.cuda.current_stream()
     timer = Timer(torch, dist, world, dev, stream)
@@ -414,10 +414,12 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
                        d_ll.data_ptr(), d_gb.data_ptr(), d_gw.data_ptr(), stream.cuda_stream)
 
     def step_dev():
+        if comm is not None:                # evaluation + sum of the time shards' partial ll / gradients in one call: the
+            # fused kernel's final reduction is the collective (csrc/llgrad_tc.cu, tc_final2_allreduce_kernel)
+            ds.ll_grad_allreduce_dev(comm, d_bias.data_ptr(), d_w.data_ptr(), 0, 0, nlin, path, d_out.data_ptr(), stream.cuda_stream)
+            return
         step_kernel()
-        if comm is not None:                # sum of the time shards' partial ll / gradients
-            comm.allreduce_sum_dev(d_out.data_ptr(), d_out.data_ptr(), d_out.numel(), stream.cuda_stream)
-        elif world > 1:
+        if world > 1:
             dist.all_reduce(d_out)
 
     step_kernel()                            # first call builds the split planes (part of ingest)
@@ -442,13 +444,14 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
             return step_e2e_host()
         e_bias.copy_(h_bias, non_blocking=True)
         e_w.copy_(h_w, non_blocking=True)
-        ds.ll_grad_dev(e_bias.data_ptr(), e_w.data_ptr(), 0, 0, nlin, 0, N, path,
-                       e_out[:N].data_ptr(), e_out[N:2 * N].data_ptr(), e_out[2 * N:].data_ptr(),
-                       stream.cuda_stream)
         if comm is not None:
-            comm.allreduce_sum_dev(e_out.data_ptr(), e_out.data_ptr(), e_out.numel(), stream.cuda_stream)
-        elif world > 1:
-            dist.all_reduce(e_out)
+            ds.ll_grad_allreduce_dev(comm, e_bias.data_ptr(), e_w.data_ptr(), 0, 0, nlin, path, e_out.data_ptr(), stream.cuda_stream)
+        else:
+            ds.ll_grad_dev(e_bias.data_ptr(), e_w.data_ptr(), 0, 0, nlin, 0, N, path,
+                           e_out[:N].data_ptr(), e_out[N:2 * N].data_ptr(), e_out[2 * N:].data_ptr(),
+                           stream.cuda_stream)
+            if world > 1:
+                dist.all_reduce(e_out)
         h_out.copy_(e_out, non_blocking=True)
         stream.synchronize()                # the caller reads ll / gradient on the host every step
 
@@ -521,11 +524,11 @@ def llgrad_record(args, wl, workload_key, pg, torch, dist, timer, world, rank, l
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "call": ("pyglm_b200_ll_grad on page-locked host buffers: parameter upload, evaluation and download of "
                              "ll / gradients replayed as one CUDA graph, one synchronise per step") if world == 1 else
-                            ("pyglm_b200_ll_grad_dev + all-reduce between a pinned-host upload of the parameters and a "
+                            ("pyglm_b200_ll_grad_allreduce_dev (evaluation + sum over ranks) between a pinned-host upload of the parameters and a "
                              "pinned-host download of ll / gradients, one stream synchronise per step"),
                     "blocks": len(e2e_blocks), "host_entry_value": host_entry,
                     "host_entry_call": "pyglm_b200_ll_grad with pageable numpy arrays in and out (staged by the library), wall clock"},
-            "gpu_launches": (int(info.get("launches_per_eval", 5)) + (1 if comm is not None else 0)) * args.steps,
+            "gpu_launches": int(info.get("launches_per_eval", 5)) * args.steps,
             "roofline": roof,
         }
         if world == 1 and cpu_budget_s > 0:              # CPU baseline on a bounded sample (rank 0, N=1 only)

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PYGLM_B200_ABI_VERSION 4
+#define PYGLM_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define PYGLM_B200_API __attribute__((visibility("default")))
@@ -262,6 +262,16 @@ PYGLM_B200_API int pyglm_b200_comm_connect(pyglm_b200_comm* comm, const void* al
 PYGLM_B200_API int pyglm_b200_allreduce_sum_dev(pyglm_b200_comm* comm, const double* d_in, double* d_out,
                                  int64_t n, void* stream);
 PYGLM_B200_API int pyglm_b200_comm_destroy(pyglm_b200_comm* comm);
+PYGLM_B200_API int32_t pyglm_b200_comm_world(const pyglm_b200_comm* comm);
+/* Time-sharded evaluation in one call: ll / gradients of ALL N neurons on this rank's time shard, summed over the ranks of
+ * `comm` (population.py:41-43: the reference adds the log-likelihoods of its data sequences the same way).  d_out is the
+ * contiguous result vector [ll (N) | g_bias (N) | g_w (N x (N*B+F))] on the device, identical on every rank afterwards.
+ * Where the fused kernel covers the population in one launch (N <= 32, 97..160 features) its final reduction IS the
+ * collective (each block exchanges its row with the peers); otherwise the evaluation is followed by allreduce_sum_dev.
+ * Asynchronous on `stream`; every rank must call it in the same order as its other collective calls on `comm`. */
+PYGLM_B200_API int pyglm_b200_ll_grad_allreduce_dev(pyglm_b200_dataset* ds, pyglm_b200_comm* comm,
+                                     const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
+                                     int32_t nlin, int32_t path, double* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Measurement helper (bench.py): FP64 FMA throughput of this GPU's CUDA cores in TFLOP/s, from a register-resident

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(engine_lib):
     for name in declared_symbols():
         assert hasattr(engine_lib, name), name
     assert sorted(engine.EXPORTS) == declared_symbols()
-    assert engine_lib.pyglm_b200_abi_version() == 4
+    assert engine_lib.pyglm_b200_abi_version() == 5
 
 
 def test_header_cites_reference_lines():

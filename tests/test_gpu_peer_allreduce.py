@@ -56,6 +56,34 @@ def _worker(rank, world, port, q):
                        out[:N].data_ptr(), out[N:2 * N].data_ptr(), out[2 * N:].data_ptr(), stream.cuda_stream)
         comm.allreduce_sum_dev(out.data_ptr(), out.data_ptr(), out.numel(), stream.cuda_stream)
         torch.cuda.synchronize()
+        # 3. the same through the one-call form (here it falls back to evaluation + collective: 30 features)
+        out1 = torch.zeros_like(out)
+        ds.ll_grad_allreduce_dev(comm, d_bias.data_ptr(), d_w.data_ptr(), d_A.data_ptr(), d_W.data_ptr(), "explinear", "auto",
+                                 out1.data_ptr(), stream.cuda_stream)
+        torch.cuda.synchronize()
+        ok &= bool(torch.equal(out1, out))
+        # 4. a population the fused kernel covers in one launch (N = 27, 135 features): its final reduction carries the sum
+        #    over ranks; bitwise equal to evaluation + collective, also when the two forms and plain all-reduces alternate
+        p2 = make_problem(5000, 27, 5, network=True, seed=5)
+        lo2, hi2, halo2 = time_shard(p2['T'], world, rank, R)
+        ds2 = pg.Dataset(p2['S'][lo2 - halo2:hi2], p2['dt'], p2['ibasis'], halo=halo2)
+        N2, NB2 = 27, 135
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        b2, w2, A2, W2 = t(p2['bias']), t(p2['w'].reshape(N2, NB2)), t(p2['A']), t(p2['W'])
+        ref2 = torch.zeros(N2 * (2 + NB2), dtype=torch.float64, device=dev)
+        ds2.ll_grad_dev(b2.data_ptr(), w2.data_ptr(), A2.data_ptr(), W2.data_ptr(), "explinear", 0, N2, "tc",
+                        ref2[:N2].data_ptr(), ref2[N2:2 * N2].data_ptr(), ref2[2 * N2:].data_ptr(), stream.cuda_stream)
+        comm.allreduce_sum_dev(ref2.data_ptr(), ref2.data_ptr(), ref2.numel(), stream.cuda_stream)
+        for it in range(5):
+            got2 = torch.full_like(ref2, float("nan"))
+            ds2.ll_grad_allreduce_dev(comm, b2.data_ptr(), w2.data_ptr(), A2.data_ptr(), W2.data_ptr(), "explinear", "tc",
+                                      got2.data_ptr(), stream.cuda_stream)
+            if it % 2:
+                x = torch.ones(1000, dtype=torch.float64, device=dev)
+                comm.allreduce_sum_dev(x.data_ptr(), x.data_ptr(), 1000, stream.cuda_stream)
+            torch.cuda.synchronize()
+            ok &= bool(torch.equal(got2, ref2))
+        ds2.close()
         q.put((rank, ok, out.cpu().numpy()))
         dist.barrier()
         comm.close()

@@ -20,29 +20,11 @@
 #include <algorithm>
 #include <new>
 
-#include "common.cuh"
+#include "allreduce.cuh"
 
 namespace pyglm {
 
 constexpr int kArThreads = 256;
-constexpr int kArMaxWorld = 16;
-constexpr int kArMaxBlocks = 128;
-
-struct ArPeers {
-    double* recv[kArMaxWorld];      // peer r's receive buffer: [2][world][cap]
-    unsigned* flag[kArMaxWorld];    // peer r's flags: [world][kArMaxBlocks]
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 
 __global__ void __launch_bounds__(kArThreads)
 allreduce_kernel(ArPeers peers, int rank, int world, int64_t cap, unsigned epoch,
@@ -91,7 +73,22 @@ struct pyglm_b200_comm {
     int num_sms = 0;
 };
 
+namespace pyglm {
+int ar_begin_epoch(pyglm_b200_comm* c, int64_t n, ArEpoch* out)
+{
+    PYGLM_REQUIRE(c != nullptr && out != nullptr, "allreduce: null communicator");
+    PYGLM_REQUIRE(n >= 0 && n <= c->cap, "allreduce: %lld doubles exceed the communicator capacity %lld", (long long)n, (long long)c->cap);
+    if (c->world > 1 && !c->connected) { set_error("allreduce before comm_connect"); return PYGLM_B200_ESTATE; }
+    c->epoch += 1;
+    if (c->epoch == 0) c->epoch = 1;                       // flags start at 0
+    out->peers = c->peers; out->rank = c->rank; out->world = c->world; out->cap = c->cap; out->epoch = c->epoch;
+    return PYGLM_B200_OK;
+}
+}  // namespace pyglm
+
 extern "C" {
+
+int32_t pyglm_b200_comm_world(const pyglm_b200_comm* c) { return c ? c->world : 0; }
 
 int pyglm_b200_comm_create(int32_t rank, int32_t world, int32_t device, int64_t max_doubles, pyglm_b200_comm** out)
 {
@@ -165,9 +162,8 @@ int pyglm_b200_allreduce_sum_dev(pyglm_b200_comm* c, const double* d_in, double*
         if (d_in != d_out) PYGLM_CUDA(cudaMemcpyAsync(d_out, d_in, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
         return PYGLM_B200_OK;
     }
-    if (!c->connected) { set_error("allreduce before comm_connect"); return PYGLM_B200_ESTATE; }
-    c->epoch += 1;
-    if (c->epoch == 0) c->epoch = 1;                       // flags start at 0
+    ArEpoch ep;
+    { int rc = ar_begin_epoch(c, n, &ep); if (rc) return rc; }
     int blocks = (int)std::min<int64_t>(ceil_div(n, 2 * kArThreads), std::min(kArMaxBlocks, c->num_sms));   // >= 512 doubles per block
     if (blocks < 1) blocks = 1;
     allreduce_kernel<<<blocks, kArThreads, 0, st>>>(c->peers, c->rank, c->world, c->cap, c->epoch, d_in, d_out, n);

@@ -6,6 +6,7 @@
 #include <new>
 #include <vector>
 
+#include "allreduce.cuh"
 #include "common.cuh"
 #include "llgrad_tc.cuh"
 
@@ -363,7 +364,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
                             const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
                             int nlin, int n_lo, int n_hi, int path,
                             double* d_ll, double* d_gb, double* d_gw,
-                            double* d_act, double* d_lam, cudaStream_t stream)
+                            double* d_act, double* d_lam, cudaStream_t stream, const void* ar = nullptr)
 {
     PYGLM_REQUIRE(nlin == PYGLM_B200_NLIN_EXP || nlin == PYGLM_B200_NLIN_SOFTPLUS, "bad nlin %d", nlin);
     PYGLM_REQUIRE(0 <= n_lo && n_lo <= n_hi && n_hi <= ds->N, "bad neuron range [%d,%d) for N=%d", n_lo, n_hi, ds->N);
@@ -390,6 +391,7 @@ static int ll_grad_dev_impl(pyglm_b200_dataset* ds,
         t.bias = d_bias; t.w = d_w; t.A = d_A; t.W = d_W;
         t.out_ll = d_ll; t.out_gb = d_gb; t.out_gw = d_gw;
         t.flags = nullptr;
+        t.ar = ar;
         if (nlin == PYGLM_B200_NLIN_EXP) {          // range flags of this call's columns (kExpSafe, tc_common.cuh)
             if (!ds->tc.planes_ready) { int rc = tc_ensure_planes(t, ds->tc, stream); if (rc) return rc; }
             PYGLM_CUDA(cudaMemsetAsync(ds->tc.colflag + n_lo, 0, (size_t)ncols * sizeof(unsigned), stream));
@@ -441,6 +443,30 @@ int pyglm_b200_ll_grad_dev(pyglm_b200_dataset* ds,
     TRY(ll_grad_dev_impl(ds, d_bias, d_w, d_A, d_W, nlin, n_lo, n_hi, path, d_out_ll, d_out_g_bias, d_out_g_w,
                          nullptr, nullptr, (cudaStream_t)stream));
     return ws_release(ds, (cudaStream_t)stream);
+}
+
+int pyglm_b200_ll_grad_allreduce_dev(pyglm_b200_dataset* ds, pyglm_b200_comm* comm,
+                                     const double* d_bias, const double* d_w, const int8_t* d_A, const double* d_W,
+                                     int32_t nlin, int32_t path, double* d_out, void* stream)
+{
+    DS_GUARD(ds);
+    PYGLM_REQUIRE(d_out != nullptr, "ll_grad_allreduce: null output");
+    const int N = ds->N;
+    const int64_t NB = ds->NF(), n = (int64_t)N * (2 + NB);
+    const int world = comm ? pyglm_b200_comm_world(comm) : 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(ws_acquire(ds, st));
+    const bool fuse = world > 1 && ds->T > 0 && !ds->tc.streamed && resolve_path(ds, path, false) == PYGLM_B200_PATH_TC &&
+                      tc_can_fuse_allreduce(N, NB);
+    if (fuse) {                                              // the evaluation's final reduction is the collective
+        ArEpoch ep;
+        TRY(ar_begin_epoch(comm, n, &ep));
+        TRY(ll_grad_dev_impl(ds, d_bias, d_w, d_A, d_W, nlin, 0, N, path, d_out, d_out + N, d_out + 2 * (int64_t)N, nullptr, nullptr, st, &ep));
+    } else {
+        TRY(ll_grad_dev_impl(ds, d_bias, d_w, d_A, d_W, nlin, 0, N, path, d_out, d_out + N, d_out + 2 * (int64_t)N, nullptr, nullptr, st));
+        if (world > 1) TRY(pyglm_b200_allreduce_sum_dev(comm, d_out, d_out, n, stream));
+    }
+    return ws_release(ds, st);
 }
 
 int pyglm_b200_range_flags(const pyglm_b200_dataset* ds, int32_t* out_flags)

@@ -25,6 +25,7 @@
 
 #include <algorithm>
 
+#include "allreduce.cuh"
 #include "llgrad_tc.cuh"
 #include "tc_common.cuh"
 
@@ -85,6 +86,9 @@ bool tc_supported(int64_t T, int N, int B, int x_dtype)
 {
     return x_dtype == PYGLM_B200_X_F32 && T > 0;
 }
+
+// the fused kernel's final reduction can carry the sum over ranks when one launch covers the population (V2 kernel)
+bool tc_can_fuse_allreduce(int N, int64_t nfeat) { return N <= kNcol && nfeat > 3 * kChunkF && nfeat <= kMaxChunks * kChunkF && nfeat + 1 <= kArMaxBlocks; }
 
 // N*B <= 160 features: the fused single-pass kernel; larger populations: the two GEMM kernels
 bool tc_uses_fused_kernel(int64_t nfeat) { return nfeat <= kMaxChunks * kChunkF; }
@@ -1331,6 +1335,76 @@ tc_final2_kernel(const double* __restrict__ part, int nctas, int nrows, int N, i
     }
 }
 
+// tc_final2_kernel with the sum over ranks folded in (time-sharded evaluation, csrc/allreduce.cu's protocol with one
+// block per feature row): a block writes its 32 column values into its slot of every peer's receive buffer, raises its
+// flag there, waits for the peers' flags of the same row and adds the slots in rank order -- the evaluation's last
+// kernel IS the collective, one launch and one flag round trip instead of two launches.  `out` is the contiguous result
+// vector [ll (N) | g_bias (N) | g_w (N x NB)]; all N neurons (N <= 32) are evaluated.
+__global__ void __launch_bounds__(32 * 32)
+tc_final2_allreduce_kernel(const double* __restrict__ part, int nctas, int nrows, int N, int B, int F,
+                           const float* __restrict__ sx, const int8_t* __restrict__ A, const double* __restrict__ W,
+                           ArEpoch ar, double* __restrict__ out)
+{
+    __shared__ double sh[32][2 * kNcol];
+    const int64_t NS = (int64_t)N * B, NB = NS + F;
+    const int64_t per_cta = (int64_t)nrows * kNcol + 2 * kNcol;
+    const int nl = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const bool tail = blockIdx.x == NB;                      // the ll / g_bias block
+    const int64_t off = tail ? (int64_t)nrows * kNcol : (int64_t)blockIdx.x * kNcol;
+    double s0 = 0.0, s1 = 0.0;
+    for (int c = slice; c < nctas; c += 32) {
+        const double* pc = part + c * per_cta + off + nl;
+        s0 += pc[0];
+        if (tail) s1 += pc[kNcol];
+    }
+    sh[slice][nl] = s0;
+    sh[slice][kNcol + nl] = s1;
+    __syncthreads();
+    const bool mine = slice == 0 && nl < N;
+    int64_t i0 = 0, i1 = 0;                                  // positions of this thread's value(s) in the result vector
+    if (mine) {
+#pragma unroll
+        for (int k = 1; k < 32; ++k) { s0 += sh[k][nl]; s1 += sh[k][kNcol + nl]; }
+        if (tail) {
+            i0 = nl; i1 = N + nl;
+        } else {
+            const int64_t j = blockIdx.x;
+            const int pre = (int)(j / B);
+            const double a = (A && j < NS) ? (double)A[(int64_t)pre * N + nl] : 1.0;
+            const double ww = (W && j < NS) ? W[(int64_t)pre * N + nl] : 1.0;
+            s0 = (a * ww) * s0 / ((double)sx[j] * (double)kRScale);
+            i0 = 2 * (int64_t)N + (int64_t)nl * NB + j;
+        }
+        const int64_t slot = ((int64_t)(ar.epoch & 1u) * ar.world + ar.rank) * ar.cap;
+        for (int r = 0; r < ar.world; ++r) {
+            double* dst = ar.peers.recv[r] + slot;
+            dst[i0] = s0;
+            if (tail) dst[i1] = s1;
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x < ar.world) {
+        st_release_sys(ar.peers.flag[threadIdx.x] + (int64_t)ar.rank * kArMaxBlocks + blockIdx.x, ar.epoch);
+        const unsigned* fl = ar.peers.flag[ar.rank] + (int64_t)threadIdx.x * kArMaxBlocks + blockIdx.x;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(fl) - ar.epoch) < 0) {
+            if (clock64() - t0 > (1ll << 37)) __trap();       // a peer never arrived: fail loudly, do not hang
+        }
+    }
+    __syncthreads();
+    if (mine) {
+        const double* src = ar.peers.recv[ar.rank] + (int64_t)(ar.epoch & 1u) * ar.world * ar.cap;
+        double t0s = 0.0, t1s = 0.0;
+        for (int r = 0; r < ar.world; ++r) {
+            t0s += __ldcg(src + (int64_t)r * ar.cap + i0);
+            if (tail) t1s += __ldcg(src + (int64_t)r * ar.cap + i1);
+        }
+        out[i0] = t0s;
+        if (tail) out[i1] = t1s;
+    }
+}
+
 // Sum the per-CTA partials in a fixed order and undo the scales.  One block per feature row j
 // (plus one for ll / g_bias): 32 columns x 32 slices of the CTA range, combined slice 0..31.
 constexpr int kFinalSlices = 32;
@@ -1716,7 +1790,10 @@ int launch_tc_ll_grad(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream)
                 }
             }
         }
-        if (v2)
+        if (v2 && a.ar)
+            tc_final2_allreduce_kernel<<<(unsigned)(NB + 1), 32 * 32, 0, stream>>>(
+                ws.part, nctas, 128 + tail2, a.N, a.B, a.F, ws.sx, a.A, a.W, *static_cast<const ArEpoch*>(a.ar), a.out_ll);
+        else if (v2)
             tc_final2_kernel<<<(unsigned)(NB + 1), 32 * 32, 0, stream>>>(
                 ws.part, nctas, 128 + tail2, a.N, a.B, a.F, n_lo, nc, ws.sx, a.A, a.W,
                 a.out_ll + c0, a.out_gb ? a.out_gb + c0 : nullptr, a.out_gw ? a.out_gw + (int64_t)c0 * NB : nullptr);

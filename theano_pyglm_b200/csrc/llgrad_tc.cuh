@@ -44,10 +44,12 @@ struct TcArgs {
     const double* bias; const double* w; const int8_t* A; const double* W;
     double* out_ll; double* out_gb; double* out_gw;
     unsigned* flags;              // [N] range flags (index = neuron) or nullptr
+    const void* ar = nullptr;     // ArEpoch*: fold the sum over ranks into the final reduction (out_ll = the whole result vector)
 };
 
 bool tc_supported(int64_t T, int N, int B, int x_dtype);
 bool tc_uses_fused_kernel(int64_t nfeat);
+bool tc_can_fuse_allreduce(int N, int64_t nfeat);
 // shared with the GEMM path
 int tc_ensure_planes(const TcArgs& a, TcWorkspace& ws, cudaStream_t stream);
 int tc_build_planes_direct(TcWorkspace& ws, const uint8_t* S, int64_t T, int N, int halo, const double* d_ibasis,

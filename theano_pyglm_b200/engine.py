@@ -30,7 +30,7 @@ EXPORTS = [
     "pyglm_b200_gibbs_begin", "pyglm_b200_gibbs_delta_ll", "pyglm_b200_gibbs_delta_ll_dev", "pyglm_b200_gibbs_commit",
     "pyglm_b200_gibbs_get_state", "pyglm_b200_gibbs_end",
     "pyglm_b200_comm_create", "pyglm_b200_comm_export", "pyglm_b200_comm_connect", "pyglm_b200_allreduce_sum_dev",
-    "pyglm_b200_comm_destroy", "pyglm_b200_measure_fp64_peak",
+    "pyglm_b200_comm_destroy", "pyglm_b200_comm_world", "pyglm_b200_ll_grad_allreduce_dev", "pyglm_b200_measure_fp64_peak",
 ]
 
 _lib = None
@@ -84,6 +84,9 @@ def load_library():
     lib.pyglm_b200_comm_connect.argtypes = [p, p]
     lib.pyglm_b200_allreduce_sum_dev.argtypes = [p, p, p, i64, p]
     lib.pyglm_b200_comm_destroy.argtypes = [p]
+    lib.pyglm_b200_comm_world.argtypes = [p]
+    lib.pyglm_b200_comm_world.restype = i32
+    lib.pyglm_b200_ll_grad_allreduce_dev.argtypes = [p, p, p, p, p, p, i32, i32, p, p]
     lib.pyglm_b200_measure_fp64_peak.argtypes = [i32, p]
     for name in EXPORTS:      # every declared symbol must resolve
         getattr(lib, name)
@@ -267,6 +270,14 @@ class Dataset:
                                                      vp(d_W) if d_W else None, nlin_code(nlin), n_lo, n_hi,
                                                      _PATHS.get(path, path), vp(d_ll), vp(d_gb) if d_gb else None,
                                                      vp(d_gw) if d_gw else None, vp(stream)))
+
+    def ll_grad_allreduce_dev(self, comm, d_bias, d_w, d_A, d_W, nlin, path, d_out, stream):
+        """Time-sharded evaluation: ll / gradients of all neurons on this rank's shard, summed over the ranks of `comm`
+        (a PeerComm), into the device vector d_out = [ll | g_bias | g_w].  Device addresses as integers."""
+        vp = C.c_void_p
+        _check(load_library().pyglm_b200_ll_grad_allreduce_dev(self._h, comm._h if comm is not None else None, vp(d_bias), vp(d_w),
+                                                               vp(d_A) if d_A else None, vp(d_W) if d_W else None,
+                                                               nlin_code(nlin), _PATHS.get(path, path), vp(d_out), vp(stream)))
 
     def range_flags(self):
         """int32 (N,): 1 for every neuron whose activation left the FP32-safe range of the exp nonlinearity in the last
