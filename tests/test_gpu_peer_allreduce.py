@@ -238,3 +238,67 @@ def test_neuron_sharded_map_matches_the_serial_coordinate_descent(engine_lib, x_
     assert abs(res[0][2] - res[0][4]) < 1e-6 * abs(res[0][4]), (res[0][2], res[0][4])
     d = np.abs(res[0][0] - res[0][3])
     assert np.max(d) < 0.1, float(np.max(d))
+
+
+def _tshard_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import copy
+        from theano_pyglm_b200.inference.coord_descent import coord_descent
+        from theano_pyglm_b200.models.model_factory import make_model
+        from theano_pyglm_b200.population import Population
+        from theano_pyglm_b200.utils.parallel_util import shard_data_by_time
+        N = 5
+        model = make_model('standard_glm', N=N, dt=0.001)
+        rng = np.random.default_rng(12)                              # the same recording on every rank
+        S = (rng.random((9001, N)) < 0.03).astype(float)
+        data = {'S': S, 'N': N, 'dt': 0.001, 'T': 9.001, 'stim': None, 'dt_stim': 0.1}
+        popn = Population(model, time_sharded=True)
+        R = popn.glm.imp_model.ibasis.shape[0]
+        popn.add_data(shard_data_by_time(data, R))
+        np.random.seed(4)
+        x0 = popn.sample()
+        for n in range(N):
+            x0['glms'][n]['imp']['w_ir'] *= 0.01
+        lp0 = popn.compute_log_p(x0)
+        f0, g0 = popn.glm_log_p_grad(x0, 2)
+        x_map = coord_descent(popn, x0=copy.deepcopy(x0), maxiter=2)
+        res = dict(lp0=lp0, f0=f0, g0=g0, P=popn.dense_glm_params(x_map), lp=popn.compute_log_p(x_map))
+        if rank == 0:                                                # the whole recording on one handle
+            full = Population(model)
+            full.add_data(dict(data))
+            fs, gs = full.glm_log_p_grad(x0, 2)
+            xs = coord_descent(full, x0=copy.deepcopy(x0), maxiter=2)
+            res.update(lp0_full=full.compute_log_p(x0), f0_full=fs, g0_full=gs, P_full=full.dense_glm_params(xs),
+                       lp_full=full.compute_log_p(xs))
+        q.put((rank, res))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_sharded_population_equals_the_whole_recording(engine_lib):
+    """Population(time_sharded=True): every rank holds its time shard (with the filter's left context) and every ll /
+    gradient is summed over the ranks, so log p, the per-neuron objective of coordinate descent and the MAP estimate are
+    those of the whole recording, identical on all ranks -- the serial drivers run unchanged."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tshard_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        rank, r = q.get(timeout=300)
+        res[rank] = r
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    a, b = res[0], res[1]
+    assert a['lp0'] == b['lp0'] and a['lp'] == b['lp'] and np.array_equal(a['P'], b['P'])      # one state on every rank
+    assert abs(a['lp0'] - a['lp0_full']) < 1e-7 * abs(a['lp0_full'])
+    assert abs(a['f0'] - a['f0_full']) < 1e-7 * abs(a['f0_full'])
+    assert np.max(np.abs(a['g0'] - a['g0_full'])) < 1e-5 * np.max(np.abs(a['g0_full']))
+    assert abs(a['lp'] - a['lp_full']) < 1e-6 * abs(a['lp_full'])
+    assert np.max(np.abs(a['P'] - a['P_full'])) < 0.1

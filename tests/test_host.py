@@ -304,3 +304,12 @@ def test_fit_network_sets_gaussian_weights_to_the_prior_mean():
     assert popn.network.log_p(x['net']) >= lp0
     x2 = Population(make_model('standard_glm', N=3, dt=0.001)).sample()
     assert fit_network(Population(make_model('standard_glm', N=3, dt=0.001)), x2) is x2      # constant weights: untouched
+
+
+def test_shard_data_by_time_without_a_process_group_is_the_whole_recording():
+    from theano_pyglm_b200.utils.parallel_util import shard_data_by_time, time_shard
+    S = np.arange(40).reshape(20, 2)
+    d = shard_data_by_time({'S': S, 'preprocessed': True, '_b200': object()}, R=7)
+    assert d['halo'] == 0 and np.array_equal(d['S'], S) and '_b200' not in d and d['preprocessed'] is False
+    # the planner the sharded form uses: contiguous blocks, left context of at most R bins
+    assert [time_shard(20, 3, r, 7) for r in range(3)] == [(0, 7, 0), (7, 14, 7), (14, 20, 7)]

@@ -16,8 +16,15 @@ from .glm import Glm
 
 
 class Population:
-    def __init__(self, model, device=0, x_dtype=None, path="auto"):
+    def __init__(self, model, device=0, x_dtype=None, path="auto", time_group=None, time_sharded=False):
+        """`time_sharded=True` (one process per GPU under torch.distributed; `time_group` = the process group, default
+        the world): every rank adds ITS time shard of each recording (`utils.parallel_util.shard_data_by_time`), and every
+        log-likelihood / gradient this object returns is the sum over the ranks' shards -- ll and its gradient are sums
+        over time bins, the algebra the reference uses to add data sequences (population.py:41-43).  All ranks then see
+        identical numbers, so the serial drivers (coord_descent, HMC) run unchanged and in lock-step on every rank."""
         self.model = model
+        self.time_sharded = bool(time_sharded)
+        self.time_group = time_group
         self.N = model['N']
         self.device = device
         self.path = path
@@ -72,7 +79,7 @@ class Population:
         self.latent.preprocess_data(data)
         self.network.preprocess_data(data)
         self.glm.preprocess_data(data)
-        data['_b200'] = engine.Dataset(data['S'], self.model['dt'], self.glm.imp_model.ibasis,
+        data['_b200'] = engine.Dataset(data['S'], self.model['dt'], self.glm.imp_model.ibasis, halo=int(data.get('halo', 0)),
                                        x_dtype=self.x_dtype, device=self.device, fstim=data.get('fstim'))
         data['preprocessed'] = True
         return data
@@ -165,8 +172,19 @@ class Population:
         """Per-neuron log-likelihoods (and gradients wrt the engine's dense blocks) on one sequence:
         ll (n,), g_bias (n,), g_w (n, N*B) for neurons [n_lo, n_hi)."""
         bias, w, A, W = self.glm.engine_params(x)
-        return self._handle(data).ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
-                                          path=self.path, grad=grad, w_stim=self.glm.stim_weights(x))
+        return self._sum_over_time_shards(
+            self._handle(data).ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, n_lo=n_lo, n_hi=n_hi,
+                                       path=self.path, grad=grad, w_stim=self.glm.stim_weights(x)))
+
+    def _sum_over_time_shards(self, out):
+        """Time-sharded populations: sum per-neuron ll / gradient blocks over the ranks (one collective per call)."""
+        if not self.time_sharded:
+            return out
+        from .utils.parallel_util import allreduce_sum, collective_device
+        single = not isinstance(out, tuple)
+        parts = allreduce_sum([out] if single else list(out), device=collective_device(self.device, self.time_group),
+                              group=self.time_group)
+        return parts[0] if single else tuple(parts)
 
     def compute_ll(self, vars):
         """sum_n ll_n on the current data sequence (population.py:71-86)."""
@@ -174,7 +192,8 @@ class Population:
 
     def _ll_grad_blocks(self, data, bias, w, A, W, ws, **kw):
         """ll, g_bias, g_w, g_w_stim (zero-width when the model has no stimulus) on one sequence."""
-        out = data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, path=self.path, w_stim=ws, **kw)
+        out = self._sum_over_time_shards(
+            data['_b200'].ll_grad(bias, w, A, W, nlin=self.glm.nlin_model.code, path=self.path, w_stim=ws, **kw))
         return out if len(out) == 4 else out + (np.zeros((len(out[0]), 0)),)
 
     def compute_log_prior(self, vars):

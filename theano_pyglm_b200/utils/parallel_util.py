@@ -44,6 +44,20 @@ def time_shard(T, world_size, rank, R):
     return lo, hi, min(R, lo)
 
 
+def shard_data_by_time(data, R, group=None):
+    """This rank's share of a recording for a time-sharded Population: bins [lo, hi) plus the R-bin left context the
+    spike-history filter needs (`halo`), as a data dictionary ready for `Population.add_data`."""
+    world, rank = world_rank(group)
+    T = data['S'].shape[0]
+    lo, hi, halo = time_shard(T, world, rank, R)
+    out = dict(data)
+    out['S'] = np.ascontiguousarray(data['S'][lo - halo:hi])
+    out['halo'] = halo
+    out.pop('_b200', None)
+    out['preprocessed'] = False
+    return out
+
+
 def _as_tensor(a, device):
     if isinstance(a, torch.Tensor):
         return a
