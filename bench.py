@@ -737,11 +737,12 @@ def filter_record(args, pg, torch, timer, local_rank):
     clocks = sampler.stop()
     ms /= args.steps
     # e2e: host spikes in (pageable numpy), filtered spike train resident on return: dataset_create
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
+    e2e_ms = []
+    for _ in range(7):
+        t0 = time.perf_counter()
         pg.Dataset(inp["S"], inp["dt"], inp["ibasis"], device=local_rank).close()
-    ms_e2e = (time.perf_counter() - t0) / reps * 1e3
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    ms_e2e = float(np.median(e2e_ms))                 # median of 7 (device allocations make the first ones slow)
     peak, peak_src = load_peaks()
     rd, wr = ds.filter_bytes()
     alg = rd + wr
