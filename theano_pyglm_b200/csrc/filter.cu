@@ -255,8 +255,9 @@ filter_kernel(const uint8_t* __restrict__ S, int64_t T, int N, int halo,
                     const float v0 = x0 * ps0, v1 = x1 * ps1;
                     const __half2 h1 = __floats2half2_rn(v0, v1);
                     const float2 f1 = __half22float2(h1);
-                    *d1 = h1;
-                    *d2 = __floats2half2_rn((v0 - f1.x) * 2048.0f, (v1 - f1.y) * 2048.0f);
+                    const __half2 h2 = __floats2half2_rn((v0 - f1.x) * 2048.0f, (v1 - f1.y) * 2048.0f);
+                    __stcs(reinterpret_cast<unsigned*>(d1), *reinterpret_cast<const unsigned*>(&h1));     // written once, read by a
+                    __stcs(reinterpret_cast<unsigned*>(d2), *reinterpret_cast<const unsigned*>(&h2));     // later kernel: streaming
                     d1 += (int64_t)rp * (ldp >> 1);
                     d2 += (int64_t)rp * (ldp >> 1);
                     src += rp * ostride;
