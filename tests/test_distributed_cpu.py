@@ -112,3 +112,72 @@ def test_neuron_sharded_state_splice_world2():
             assert np.array_equal(x['glms'][n]['imp']['g_%d' % n], np.full(5, 1.0 + owner + 0.1 * n))
             assert np.array_equal(x['net']['graph']['A'][:, n], (np.arange(N) + n + owner) % 2)
             assert np.array_equal(W[:, n], 10.0 * owner + n + 0.01 * np.arange(N))
+
+
+class _OracleHandle:
+    """Stands in for engine.Dataset in a CPU test of the host logic above it: evaluates this rank's time shard with the
+    float64 oracle (the product itself never does this: it has no CPU path)."""
+
+    def __init__(self, S, halo, dt, ibasis):
+        self.fS = orc.convolve_with_basis_direct(S, ibasis)[halo:]
+        self.S, self.dt = S[halo:], dt
+
+    def ll_grad(self, bias, w, A, W, nlin=None, n_lo=0, n_hi=None, path=None, grad=True, w_stim=None):
+        N = self.S.shape[1]
+        n_hi = N if n_hi is None else n_hi
+        A = np.ones((N, N), np.int8) if A is None else A             # null network = complete graph, unit weights
+        W = np.ones((N, N)) if W is None else np.asarray(W).reshape(N, N)
+        ll, gb, gw = orc.population_ll_grad(self.fS, self.S, self.dt, bias, w.reshape(N, N, -1), A, W, orc.NLIN_SOFTPLUS)
+        if not grad:
+            return ll[n_lo:n_hi]
+        return ll[n_lo:n_hi], gb[n_lo:n_hi], gw.reshape(N, -1)[n_lo:n_hi]
+
+
+def _tshard_pop_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from theano_pyglm_b200.models.model_factory import make_model
+        from theano_pyglm_b200.population import Population
+        from theano_pyglm_b200.utils.parallel_util import shard_data_by_time
+        N = 4
+        popn = Population(make_model('standard_glm', N=N, dt=0.001), time_sharded=True)
+        rng = np.random.default_rng(8)
+        S = (rng.random((2501, N)) < 0.03).astype(float)
+        ib = popn.glm.imp_model.ibasis
+        mine = shard_data_by_time({'S': S, 'N': N, 'dt': 0.001, 'T': 2.501}, ib.shape[0])
+        mine['_b200'] = _OracleHandle(mine['S'], mine['halo'], 0.001, ib)
+        mine['preprocessed'] = True
+        popn.data_sequences.append(mine)
+        popn.set_data(mine)
+        np.random.seed(3)
+        x = popn.sample()
+        whole = {'S': S, '_b200': _OracleHandle(S, 0, 0.001, ib), 'preprocessed': True}
+        ref = Population(make_model('standard_glm', N=N, dt=0.001))
+        ref.data_sequences.append(whole)
+        ref.set_data(whole)
+        f, g = popn.glm_log_p_grad(x, 1)
+        f0, g0 = ref.glm_log_p_grad(x, 1)
+        q.put((rank, popn.compute_log_p(x), ref.compute_log_p(x), f, f0, g, g0))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_time_sharded_population_sums_over_ranks_world2():
+    """Population(time_sharded=True) on two gloo ranks, each holding half of the recording (plus the filter's left context):
+    log p and the per-neuron objective / gradient of coordinate descent equal those of the whole recording on one handle."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tshard_pop_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(60)
+        assert pr.exitcode == 0
+    for rank, lp, lp0, f, f0, g, g0 in res:
+        assert abs(lp - lp0) < 1e-10 * abs(lp0)
+        assert abs(f - f0) < 1e-10 * abs(f0) and np.max(np.abs(g - g0)) < 1e-9 * np.max(np.abs(g0))
+    assert res[0][1] == res[1][1]
